@@ -1,0 +1,599 @@
+// api.cu -- the extern "C" surface declared in include/chalamet_b200.h.
+// No exceptions cross this boundary: every entry point is wrapped in a catch-all and returns a chpir_status.
+#include <chrono>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+#include "host_encode.hpp"
+
+namespace chpir {
+
+static thread_local std::string g_last_cuda_error;
+void set_last_cuda_error(cudaError_t e, const char *what) {
+  g_last_cuda_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + what;
+  (void)cudaGetLastError();  // clear the sticky-less error state
+}
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e, "cudaMalloc");
+      p = nullptr;
+      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    }
+    return CHPIR_OK;
+  }
+  template <class T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+  void *release() {
+    void *q = p;
+    p = nullptr;
+    return q;
+  }
+};
+
+struct EventTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventTimer() {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~EventTimer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  void start(cudaStream_t s) { cudaEventRecord(a, s); }
+  void stop(cudaStream_t s) { cudaEventRecord(b, s); }
+  float ms() {
+    float v = 0.f;
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&v, a, b);
+    return v;
+  }
+};
+
+// One in-flight respond: its own stream and buffers, so concurrent callers never share state.
+struct RespondSlot {
+  cudaStream_t stream = nullptr;
+  uint32_t *d_q = nullptr;
+  uint32_t *d_resp = nullptr;
+  uint32_t *h_resp = nullptr;  // pinned
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+}  // namespace chpir
+
+using namespace chpir;
+
+struct chpir_server {
+  chpir_ctx *ctx = nullptr;
+  uint64_t K = 0;
+  uint32_t ncols = 0, col_begin = 0, b = 0;
+  PackedLayout layout{};
+  RespondPlan plan{};
+  uint8_t *d_packed = nullptr;
+  uint64_t packed_bytes = 0;
+  chpir_setup_timing timing{};
+  float last_respond_ms = 0.f, last_gemm_ms = 0.f, last_expand_ms = 0.f;
+  std::mutex pool_mu;
+  std::vector<RespondSlot *> free_slots;
+  std::vector<RespondSlot *> all_slots;
+
+  ~chpir_server() {
+    if (ctx) cudaSetDevice(ctx->device);
+    for (RespondSlot *s : all_slots) {
+      if (s->stream) cudaStreamSynchronize(s->stream);
+      if (s->d_q) cudaFree(s->d_q);
+      if (s->d_resp) cudaFree(s->d_resp);
+      if (s->h_resp) cudaFreeHost(s->h_resp);
+      if (s->e0) cudaEventDestroy(s->e0);
+      if (s->e1) cudaEventDestroy(s->e1);
+      if (s->stream) cudaStreamDestroy(s->stream);
+      delete s;
+    }
+    if (d_packed) cudaFree(d_packed);
+  }
+
+  int acquire(RespondSlot **out) {
+    {
+      std::lock_guard<std::mutex> g(pool_mu);
+      if (!free_slots.empty()) {
+        *out = free_slots.back();
+        free_slots.pop_back();
+        return CHPIR_OK;
+      }
+    }
+    RespondSlot *s = new (std::nothrow) RespondSlot();
+    if (!s) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&s->d_q, K * 4) == cudaSuccess && cudaMalloc(&s->d_resp, size_t(ncols) * 4) == cudaSuccess &&
+              cudaMallocHost(&s->h_resp, size_t(ncols) * 4) == cudaSuccess && cudaEventCreate(&s->e0) == cudaSuccess &&
+              cudaEventCreate(&s->e1) == cudaSuccess;
+    {
+      std::lock_guard<std::mutex> g(pool_mu);
+      all_slots.push_back(s);
+    }
+    if (!ok) {
+      set_last_cuda_error(cudaGetLastError(), "respond slot allocation");
+      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    }
+    *out = s;
+    return CHPIR_OK;
+  }
+  void release(RespondSlot *s) {
+    std::lock_guard<std::mutex> g(pool_mu);
+    free_slots.push_back(s);
+  }
+};
+
+namespace {
+
+int validate_bits(uint32_t b) { return (b >= 4 && b <= 14) ? CHPIR_OK : CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH; }
+
+// Core of setup once D (K x ld u32, device) is resident.  d_dev columns [col0, col0+ncols) form this server's slice.
+int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col0, uint32_t ncols,
+               uint32_t col_begin_logical, uint32_t b, const chpir_setup_opts &o, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
+               chpir_server *srv) {
+  cudaStream_t st = ctx->stream;
+  srv->ctx = ctx;
+  srv->K = K;
+  srv->ncols = ncols;
+  srv->col_begin = col_begin_logical;
+  srv->b = b;
+  srv->layout = make_layout(b, ncols);
+  srv->packed_bytes = K * srv->layout.pitch_bytes();
+
+  // -- respond layout
+  EventTimer t_pack;
+  {
+    void *p = nullptr;
+    CHPIR_CUDA(cudaMalloc(&p, srv->packed_bytes), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+    srv->d_packed = static_cast<uint8_t *>(p);
+  }
+  t_pack.start(st);
+  if (int rc = launch_pack(d_dev, K, ld, col0, srv->layout, srv->d_packed, st); rc != CHPIR_OK) return rc;
+  t_pack.stop(st);
+  srv->plan = plan_respond(srv->layout, K, ctx->sm_count);
+
+  const uint32_t m = o.lwe_rows ? o.lwe_rows : CHPIR_LWE_DIMENSION;
+  if (!o.skip_hint) {
+    const size_t need = 8 + size_t(m) * ncols * 4;
+    if (!hint_out || hint_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
+    // -- A = generate_from_seed(m, K, seed) on device
+    DevBuf a, scratch, c;
+    if (int rc = a.alloc(size_t(m) * K * 4); rc != CHPIR_OK) return rc;
+    if (int rc = scratch.alloc(512); rc != CHPIR_OK) return rc;
+    if (int rc = c.alloc(size_t(m) * ncols * 4); rc != CHPIR_OK) return rc;
+    EventTimer t_exp, t_gemm;
+    t_exp.start(st);
+    if (int rc = launch_expand(seed, a.as<uint8_t>(), uint64_t(m) * K * 4, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
+    t_exp.stop(st);
+    // -- M = A * D[:, slice]
+    float tc_ms = 0.f;
+    t_gemm.start(st);
+    int rc;
+    if (o.gemm_variant == 1)
+      rc = launch_gemm_simt(a.as<uint32_t>(), d_dev + col0, ld, c.as<uint32_t>(), m, K, ncols, st);
+    else
+      rc = launch_gemm_tc(a.as<uint32_t>(), d_dev + col0, ld, c.as<uint32_t>(), m, K, ncols, b, ctx->sm_count, st, &tc_ms);
+    if (rc != CHPIR_OK) return rc;
+    t_gemm.stop(st);
+    const double t0 = now_s();
+    const uint32_t hdr[2] = {m, ncols};
+    std::memcpy(hint_out, hdr, 8);
+    CHPIR_CUDA(cudaMemcpyAsync(hint_out + 8, c.p, size_t(m) * ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
+    srv->timing.d2h_s = now_s() - t0;  // includes waiting for the kernels; corrected below
+    srv->timing.expand_a_s = t_exp.ms() * 1e-3;
+    srv->timing.gemm_s = t_gemm.ms() * 1e-3;
+    srv->timing.d2h_s -= (srv->timing.expand_a_s + srv->timing.gemm_s);
+    if (srv->timing.d2h_s < 0) srv->timing.d2h_s = 0;
+    srv->last_gemm_ms = tc_ms > 0.f ? tc_ms : t_gemm.ms();
+    srv->last_expand_ms = t_exp.ms();
+    if (hint_len) *hint_len = need;
+  } else {
+    CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
+    if (hint_len) *hint_len = 0;
+  }
+  srv->timing.pack_s = t_pack.ms() * 1e-3;
+  return CHPIR_OK;
+}
+
+int resolve_slice(const chpir_setup_opts &o, uint32_t N, uint32_t *c0, uint32_t *nc) {
+  *c0 = o.col_begin;
+  *nc = o.col_count ? o.col_count : (N > o.col_begin ? N - o.col_begin : 0);
+  if (*nc == 0 || uint64_t(*c0) + *nc > N) return CHPIR_ERR_INVALID_ARGUMENT;
+  return CHPIR_OK;
+}
+
+}  // namespace
+
+#define CHPIR_GUARD_BEGIN try {
+#define CHPIR_GUARD_END                          \
+  }                                              \
+  catch (const std::bad_alloc &) {               \
+    return CHPIR_ERR_HOST_ALLOCATION_FAILED;     \
+  }                                              \
+  catch (...) {                                  \
+    return CHPIR_ERR_INVALID_ARGUMENT;           \
+  }
+
+extern "C" {
+
+const char *chpir_strerror(int status) {
+  switch (status) {
+    case CHPIR_OK: return "ok";
+    case CHPIR_ERR_INVALID_MATRIX_DIMENSION: return "InvalidMatrixDimension";
+    case CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_MATRIX_MULTIPLICATION: return "IncompatibleDimensionForMatrixMultiplication";
+    case CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_ROW_VECTOR_TRANSPOSED_MATRIX_MULTIPLICATION:
+      return "IncompatibleDimensionForRowVectorTransposedMatrixMultiplication";
+    case CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES: return "FailedToDeserializeMatrixFromBytes";
+    case CHPIR_ERR_EMPTY_KV_DATABASE: return "EmptyKVDatabase";
+    case CHPIR_ERR_EXHAUSTED_ALL_ATTEMPTS_TO_BUILD_3_WISE_XOR_FILTER: return "ExhaustedAllAttemptsToBuild3WiseXorFilter";
+    case CHPIR_ERR_EXHAUSTED_ALL_ATTEMPTS_TO_BUILD_4_WISE_XOR_FILTER: return "ExhaustedAllAttemptsToBuild4WiseXorFilter";
+    case CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE: return "KVDatabaseSizeTooLarge";
+    case CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER: return "UnsupportedArityForBinaryFuseFilter";
+    case CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH: return "ImpossibleEncodedDBMatrixElementBitLength";
+    case CHPIR_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+    case CHPIR_ERR_BUFFER_TOO_SMALL: return "BufferTooSmall";
+    case CHPIR_ERR_CUDA_DEVICE_NOT_FOUND: return "CudaDeviceNotFound";
+    case CHPIR_ERR_CUDA_ALLOCATION_FAILED: return "CudaAllocationFailed";
+    case CHPIR_ERR_CUDA_TRANSFER_FAILED: return "CudaTransferFailed";
+    case CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED: return "CudaKernelLaunchFailed";
+    case CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED: return "CudaKernelExecutionFailed";
+    case CHPIR_ERR_CUDA_UNSUPPORTED_DEVICE: return "CudaUnsupportedDevice";
+    case CHPIR_ERR_HOST_ALLOCATION_FAILED: return "HostAllocationFailed";
+    default: return "UnknownStatus";
+  }
+}
+
+const char *chpir_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+int chpir_device_count(int *count) {
+  if (!count) return CHPIR_ERR_INVALID_ARGUMENT;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "cudaGetDeviceCount");
+    *count = 0;
+    return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+  }
+  *count = n;
+  return CHPIR_OK;
+}
+
+int chpir_ctx_create(int device_ordinal, chpir_ctx **out) {
+  CHPIR_GUARD_BEGIN
+  if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device_ordinal < 0 || device_ordinal >= n) {
+    (void)cudaGetLastError();
+    return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+  }
+  CHPIR_CUDA(cudaSetDevice(device_ordinal), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  cudaDeviceProp prop{};
+  CHPIR_CUDA(cudaGetDeviceProperties(&prop, device_ordinal), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  // sm_100a-only binary: no fallback, fail loudly on anything else
+  if (prop.major != 10) return CHPIR_ERR_CUDA_UNSUPPORTED_DEVICE;
+  chpir_ctx *c = new chpir_ctx();
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+  }
+  *out = c;
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+void chpir_ctx_destroy(chpir_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  delete ctx;
+}
+
+int chpir_find_mat_elem_bit_len(uint64_t n, uint32_t *b) {
+  if (!b) return CHPIR_ERR_INVALID_ARGUMENT;
+  return find_mat_elem_bit_len(n, b);
+}
+
+int chpir_db_matrix_shape(uint32_t arity, uint64_t n, uint64_t max_value_byte_len, uint32_t b, uint64_t *rows_k, uint64_t *cols_n) {
+  if (!rows_k || !cols_n) return CHPIR_ERR_INVALID_ARGUMENT;
+  return db_matrix_shape(arity, n, max_value_byte_len, b, rows_k, cols_n);
+}
+
+int chpir_encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_offsets, const uint8_t *value_blob,
+                             const uint64_t *value_offsets, uint32_t b, uint32_t max_attempt_count, const uint64_t *filter_seed_rng,
+                             uint32_t *d_out, uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN]) {
+  CHPIR_GUARD_BEGIN
+  if (n == 0) return CHPIR_ERR_EMPTY_KV_DATABASE;
+  if (!key_blob || !key_offsets || !value_blob || !value_offsets || !d_out || !filter_params_out) return CHPIR_ERR_INVALID_ARGUMENT;
+  return encode_kv_database(arity, n, key_blob, key_offsets, value_blob, value_offsets, b, max_attempt_count, filter_seed_rng, d_out,
+                            filter_params_out);
+  CHPIR_GUARD_END
+}
+
+int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k,
+                              uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
+                              size_t *hint_len, chpir_server **out) {
+  CHPIR_GUARD_BEGIN
+  if (!ctx || !seed || !d_device || !out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (rows_k == 0 || cols_n == 0) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
+  if (int rc = validate_bits(b); rc != CHPIR_OK) return rc;
+  chpir_setup_opts o{};
+  if (opts) o = *opts;
+  uint32_t c0, nc;
+  if (int rc = resolve_slice(o, cols_n, &c0, &nc); rc != CHPIR_OK) return rc;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  const double t0 = now_s();
+  chpir_server *srv = new chpir_server();
+  int rc = setup_core(ctx, seed, d_device, rows_k, cols_n, c0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv);
+  if (rc != CHPIR_OK) {
+    delete srv;
+    return rc;
+  }
+  srv->timing.total_s = now_s() - t0;
+  *out = srv;
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k, uint32_t cols_n,
+                       uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out) {
+  CHPIR_GUARD_BEGIN
+  if (!ctx || !seed || !d_host || !out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (rows_k == 0 || cols_n == 0) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
+  if (int rc = validate_bits(b); rc != CHPIR_OK) return rc;
+  chpir_setup_opts o{};
+  if (opts) o = *opts;
+  uint32_t c0, nc;
+  if (int rc = resolve_slice(o, cols_n, &c0, &nc); rc != CHPIR_OK) return rc;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  const double t0 = now_s();
+  // upload only this server's column slice, compacted to K x nc
+  DevBuf d;
+  if (int rc = d.alloc(rows_k * nc * 4); rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemcpy2DAsync(d.p, size_t(nc) * 4, d_host + c0, size_t(cols_n) * 4, size_t(nc) * 4, rows_k, cudaMemcpyHostToDevice, ctx->stream),
+             CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaStreamSynchronize(ctx->stream), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  const double t1 = now_s();
+  chpir_server *srv = new chpir_server();
+  int rc = setup_core(ctx, seed, d.as<uint32_t>(), rows_k, nc, 0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv);
+  if (rc != CHPIR_OK) {
+    delete srv;
+    return rc;
+  }
+  srv->timing.h2d_s = t1 - t0;
+  srv->timing.total_s = now_s() - t0;
+  *out = srv;
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t n, const uint8_t *key_blob,
+                               const uint64_t *key_offsets, const uint8_t *value_blob, const uint64_t *value_offsets,
+                               const uint64_t *filter_seed_rng, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
+                               size_t *hint_len, uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN], chpir_server **out) {
+  CHPIR_GUARD_BEGIN
+  if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  // server.rs:104-107
+  if (n == 0) return CHPIR_ERR_EMPTY_KV_DATABASE;
+  if (!ctx || !seed || !key_blob || !key_offsets || !value_blob || !value_offsets || !filter_params_out) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (arity != 3 && arity != 4) return CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER;
+  uint32_t b = 0;
+  if (int rc = find_mat_elem_bit_len(n, &b); rc != CHPIR_OK) return rc;
+  uint64_t max_vlen = 0;
+  for (uint64_t i = 0; i < n; i++) max_vlen = std::max<uint64_t>(max_vlen, value_offsets[i + 1] - value_offsets[i]);
+  uint64_t K = 0, N = 0;
+  if (int rc = db_matrix_shape(arity, n, max_vlen, b, &K, &N); rc != CHPIR_OK) return rc;
+  if (N > 0xffffffffull) return CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE;
+  const double t0 = now_s();
+  // pinned so the upload is a straight DMA
+  uint32_t *D = nullptr;
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMallocHost(&D, K * N * 4) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+  }
+  int rc = encode_kv_database(arity, n, key_blob, key_offsets, value_blob, value_offsets, b, CHPIR_SERVER_SETUP_MAX_ATTEMPT_COUNT,
+                              filter_seed_rng, D, filter_params_out);
+  const double t1 = now_s();
+  if (rc == CHPIR_OK) rc = chpir_server_setup(ctx, seed, D, K, uint32_t(N), b, opts, hint_out, hint_cap, hint_len, out);
+  cudaFreeHost(D);
+  if (rc == CHPIR_OK) {
+    (*out)->timing.host_encode_s = t1 - t0;
+    (*out)->timing.total_s += t1 - t0;
+  }
+  return rc;
+  CHPIR_GUARD_END
+}
+
+void chpir_server_destroy(chpir_server *srv) { delete srv; }
+
+int chpir_server_setup_timing(const chpir_server *srv, chpir_setup_timing *out) {
+  if (!srv || !out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = srv->timing;
+  return CHPIR_OK;
+}
+
+int chpir_server_get_info(const chpir_server *srv, chpir_server_info *out) {
+  if (!srv || !out) return CHPIR_ERR_INVALID_ARGUMENT;
+  out->rows_k = srv->K;
+  out->cols_n = srv->ncols;
+  out->col_begin = srv->col_begin;
+  out->mat_elem_bit_len = srv->b;
+  out->fields_per_word = srv->layout.fpw;
+  out->row_pitch_bytes = srv->layout.pitch_bytes();
+  out->packed_bytes = srv->packed_bytes;
+  return CHPIR_OK;
+}
+
+// Matrix::from_bytes validation (matrix.rs:973-1010) + the dimension check of
+// row_vector_x_compressed_transposed_matrix (matrix.rs:329-331), in that order.
+static int validate_query(const chpir_server *srv, const uint8_t *query, size_t len) {
+  if (!query || len <= 8) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  uint32_t rows, cols;
+  std::memcpy(&rows, query, 4);
+  std::memcpy(&cols, query + 4, 4);
+  const uint64_t n = uint64_t(rows) * cols;
+  if (n == 0) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  if (n * 4 != uint64_t(len - 8)) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  if (!(rows == 1 && cols == srv->K)) return CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_ROW_VECTOR_TRANSPOSED_MATRIX_MULTIPLICATION;
+  return CHPIR_OK;
+}
+
+int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_len, uint8_t *resp_out, size_t resp_cap, size_t *resp_len) {
+  CHPIR_GUARD_BEGIN
+  if (!srv) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (int rc = validate_query(srv, query, query_len); rc != CHPIR_OK) return rc;
+  const size_t need = 8 + size_t(srv->ncols) * 4;
+  if (!resp_out || resp_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
+  CHPIR_CUDA(cudaSetDevice(srv->ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  RespondSlot *s = nullptr;
+  if (int rc = srv->acquire(&s); rc != CHPIR_OK) return rc;
+  int rc = CHPIR_OK;
+  do {
+    if (cudaMemcpyAsync(s->d_q, query + 8, srv->K * 4, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+        cudaMemsetAsync(s->d_resp, 0, size_t(srv->ncols) * 4, s->stream) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+      break;
+    }
+    cudaEventRecord(s->e0, s->stream);
+    rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, s->d_q, s->d_resp, s->stream);
+    if (rc != CHPIR_OK) break;
+    cudaEventRecord(s->e1, s->stream);
+    if (cudaMemcpyAsync(s->h_resp, s->d_resp, size_t(srv->ncols) * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+      break;
+    }
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e, "respond");
+      rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+      break;
+    }
+    const uint32_t hdr[2] = {1u, srv->ncols};
+    std::memcpy(resp_out, hdr, 8);
+    std::memcpy(resp_out + 8, s->h_resp, size_t(srv->ncols) * 4);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->e0, s->e1) == cudaSuccess) srv->last_respond_ms = ms;
+    if (resp_len) *resp_len = need;
+  } while (false);
+  if (rc != CHPIR_OK && rc != CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED) set_last_cuda_error(cudaGetLastError(), "respond enqueue");
+  srv->release(s);
+  return rc;
+  CHPIR_GUARD_END
+}
+
+int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries, const size_t *query_lens, uint32_t nq, uint8_t *resp_out,
+                               size_t resp_stride) {
+  CHPIR_GUARD_BEGIN
+  if (!srv || !queries || !query_lens || !resp_out) return CHPIR_ERR_INVALID_ARGUMENT;
+  const size_t need = 8 + size_t(srv->ncols) * 4;
+  if (resp_stride < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
+  for (uint32_t i = 0; i < nq; i++)
+    if (int rc = validate_query(srv, queries[i], query_lens[i]); rc != CHPIR_OK) return rc;
+  for (uint32_t i = 0; i < nq; i++) {
+    size_t len = 0;
+    if (int rc = chpir_server_respond(srv, queries[i], query_lens[i], resp_out + size_t(i) * resp_stride, resp_stride, &len); rc != CHPIR_OK)
+      return rc;
+  }
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream) {
+  CHPIR_GUARD_BEGIN
+  if (!srv || !q_device || !resp_device) return CHPIR_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : srv->ctx->stream;
+  CHPIR_CUDA(cudaMemsetAsync(resp_device, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  for (uint32_t i = 0; i < nq; i++)
+    if (int rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, q_device + uint64_t(i) * srv->K,
+                                resp_device + uint64_t(i) * srv->ncols, st);
+        rc != CHPIR_OK)
+      return rc;
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_generate_from_seed(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols, uint64_t row_begin,
+                             uint64_t row_count, uint32_t *out_host) {
+  CHPIR_GUARD_BEGIN
+  if (!ctx || !seed || !out_host) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || cols == 0) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
+  if (row_begin + row_count > rows || row_count == 0) return CHPIR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  // only the prefix up to the last requested row has to be produced
+  const uint64_t total = (row_begin + row_count) * cols * 4;
+  DevBuf a, scratch;
+  if (int rc = a.alloc(total); rc != CHPIR_OK) return rc;
+  if (int rc = scratch.alloc(512); rc != CHPIR_OK) return rc;
+  if (int rc = launch_expand(seed, a.as<uint8_t>(), total, scratch.as<uint8_t>(), ctx->stream); rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemcpyAsync(out_host, a.as<uint8_t>() + row_begin * cols * 4, row_count * cols * 4, cudaMemcpyDeviceToHost, ctx->stream),
+             CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaStreamSynchronize(ctx->stream), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64_t a_cols, const uint32_t *b_host, uint64_t b_rows,
+                 uint64_t b_cols, uint32_t b_elem_bit_len, uint32_t variant, uint32_t *out_host) {
+  CHPIR_GUARD_BEGIN
+  if (!ctx || !a_host || !b_host || !out_host) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (a_rows == 0 || a_cols == 0 || b_rows == 0 || b_cols == 0) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
+  if (a_cols != b_rows) return CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_MATRIX_MULTIPLICATION;
+  if (a_rows > 0xffffffffull || b_cols > 0xffffffffull) return CHPIR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  DevBuf a, b, c;
+  if (int rc = a.alloc(a_rows * a_cols * 4); rc != CHPIR_OK) return rc;
+  if (int rc = b.alloc(b_rows * b_cols * 4); rc != CHPIR_OK) return rc;
+  if (int rc = c.alloc(a_rows * b_cols * 4); rc != CHPIR_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  CHPIR_CUDA(cudaMemcpyAsync(a.p, a_host, a_rows * a_cols * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(b.p, b_host, b_rows * b_cols * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  int rc;
+  float ms = 0.f;
+  if (variant == 1)
+    rc = launch_gemm_simt(a.as<uint32_t>(), b.as<uint32_t>(), uint32_t(b_cols), c.as<uint32_t>(), uint32_t(a_rows), a_cols, uint32_t(b_cols), st);
+  else
+    rc = launch_gemm_tc(a.as<uint32_t>(), b.as<uint32_t>(), uint32_t(b_cols), c.as<uint32_t>(), uint32_t(a_rows), a_cols, uint32_t(b_cols),
+                        b_elem_bit_len, ctx->sm_count, st, &ms);
+  if (rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemcpyAsync(out_host, c.p, a_rows * b_cols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_server_last_kernel_ms(const chpir_server *srv, float *respond_ms, float *gemm_ms, float *expand_ms) {
+  if (!srv) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (respond_ms) *respond_ms = srv->last_respond_ms;
+  if (gemm_ms) *gemm_ms = srv->last_gemm_ms;
+  if (expand_ms) *expand_ms = srv->last_expand_ms;
+  return CHPIR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""GPU parity for the offline path: A expansion (matrix.rs:541-558), hint GEMM (matrix.rs:1040-1059) and the complete
+Server::setup (server.rs:103) against the CPU oracle, plus end-to-end value recovery through the oracle's client."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import chalametpir_b200 as cp
+from oracle import oracle as O
+from conftest import make_db
+
+SEED = bytes(range(32))
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "vectors.json")
+
+
+def rand_u32(rng, shape):
+    return rng.integers(0, 2**32, size=shape, dtype=np.uint64).astype(np.uint32)
+
+
+# ------------------------------------------------------------------ A expansion
+@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 41), (1, 42), (1, 43), (3, 14), (7, 1000), (64, 4099)])
+def test_generate_from_seed_matches_oracle(rows, cols):
+    seed = bytes(random.Random(rows * 1000 + cols).randbytes(32))
+    assert np.array_equal(cp.generate_from_seed(rows, cols, seed), O.generate_from_seed(rows, cols, seed))
+
+
+def test_generate_from_seed_deep_in_the_stream():
+    # last rows of a 1774 x 20000 matrix: 142 MB into the XOF stream, several kernel launches with carried state
+    rows, cols = 1774, 20000
+    got = cp.generate_from_seed(rows, cols, SEED, row_begin=rows - 2, row_count=2)
+    assert np.array_equal(got, O.generate_rows_from_seed(cols, SEED, rows - 2, 2))
+
+
+# ------------------------------------------------------------------ hint GEMM
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("m,k,n,b", [(1, 1, 1, 9), (37, 301, 53, 10), (128, 4096, 128, 9), (200, 1000, 940, 9), (1774, 2048, 100, 14), (130, 77, 17, 4)])
+def test_matmul_matches_oracle(variant, m, k, n, b):
+    rng = np.random.default_rng(m + k + n)
+    A = rand_u32(rng, (m, k))
+    B = rng.integers(0, 1 << b, size=(k, n), dtype=np.uint32)
+    assert np.array_equal(cp.matmul(A, B, b, variant), O.matmul(A, B))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_matmul_identity(variant):  # matrix.rs:1275-1317
+    rng = np.random.default_rng(5)
+    A = rand_u32(rng, (300, 257))
+    assert np.array_equal(cp.matmul(A, np.eye(257, dtype=np.uint32), 4, variant), A)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_matmul_wraps_instead_of_saturating(variant):
+    """All-ones operands over a long K: every int32 partial sum overflows many times; the result must wrap mod 2^32."""
+    m, k, n, b = 128, 50000, 64, 14
+    A = np.full((m, k), 0xFFFFFFFF, dtype=np.uint32)
+    B = np.full((k, n), (1 << b) - 1, dtype=np.uint32)
+    want = np.uint32((0xFFFFFFFF * ((1 << b) - 1) * k) & 0xFFFFFFFF)
+    got = cp.matmul(A, B, b, variant)
+    assert np.all(got == want)
+    rng = np.random.default_rng(6)
+    A = rand_u32(rng, (m, k)) | 0x80808080
+    B = rng.integers(0, 1 << b, size=(k, n), dtype=np.uint32) | 0x2080
+    assert np.array_equal(cp.matmul(A, B, b, variant), O.matmul(A, B))
+
+
+def test_matmul_dimension_errors():
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.matmul(np.ones((2, 3), np.uint32), np.ones((4, 2), np.uint32), 9)
+    assert e.value.variant == "IncompatibleDimensionForMatrixMultiplication"
+
+
+# ------------------------------------------------------------------ Server::setup end to end
+@pytest.mark.parametrize("arity", [3, 4])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_setup_and_respond_end_to_end(arity, variant):  # integrations/src/test_pir.rs:12-142
+    db = make_db(3000, seed=arity * 7 + variant, val_len=(1, 300))
+    seed = bytes(random.Random(arity).randbytes(32))
+    srv, hint, fbytes = cp.Server.setup(seed, db, arity, filter_seed_rng=21, gemm_variant=variant)
+    assert len(fbytes) == 68
+    b = cp.find_mat_elem_bit_len(len(db))
+    D, fb2 = cp.encode_kv_database(db, b, arity, filter_seed_rng=21)
+    assert fb2 == fbytes
+    osrv, ohint = O.Server.setup_from_matrix(seed, D, b)
+    assert hint == ohint  # identical hint bytes (wire format header + 1774 x N u32)
+    client = O.Client.setup(seed, hint, fbytes)
+    keys = random.Random(1).sample(list(db), 10)
+    answered = 0
+    for key in keys:
+        try:
+            q = client.query(key)
+        except O.OracleError as ex:
+            assert ex.name == "ArithmeticOverflowAddingQueryIndicator"  # caller retries, test_pir.rs:66-70
+            continue
+        r = srv.respond(q)
+        assert r == osrv.respond(q)
+        assert client.process_response(key, r) == db[key]
+        answered += 1
+    assert answered >= 8
+    t = srv.setup_timing()
+    assert t["total_s"] > 0 and t["expand_a_s"] > 0 and t["gemm_s"] > 0
+
+
+def test_setup_column_slices_interleave_to_the_full_hint():
+    rng = np.random.default_rng(3)
+    K, N, b, lwe = 3000, 100, 9, 200
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    _, full = cp.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe)
+    assert full == O.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe, want_server=False)[1]
+    M = O.matrix_from_bytes(full)
+    for world in (2, 8):
+        bounds = [N * r // world for r in range(world + 1)]
+        for r in range(world):
+            _, part = cp.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe, col_begin=bounds[r], col_count=bounds[r + 1] - bounds[r])
+            assert np.array_equal(O.matrix_from_bytes(part), M[:, bounds[r] : bounds[r + 1]])
+
+
+def test_golden_fixtures_through_the_gpu_path():
+    g = json.load(open(GOLDEN))
+    seed = bytes.fromhex(g["seed"])
+    for case in g["cases"]:
+        rnd = random.Random(case["db_seed"])
+        db = {}
+        while len(db) < case["n"]:
+            db[rnd.randbytes(rnd.randint(16, 32))] = rnd.randbytes(rnd.randint(1, case["max_val"]))
+        srv, hint, fb = cp.Server.setup(seed, db, case["arity"], filter_seed_rng=case["filter_rng"], lwe_rows=case["lwe_rows"])
+        assert fb.hex() == case["filter_params"]
+        assert hashlib.sha256(hint).hexdigest() == case["hint_sha256"]
+        K = case["shape"][0]
+        q = np.frombuffer(O.turboshake128(b"q" + seed, 4 * K), dtype="<u4")
+        assert hashlib.sha256(srv.respond(O.matrix_to_bytes(q[None, :]))).hexdigest() == case["response_sha256"]

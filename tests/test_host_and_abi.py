@@ -1,0 +1,107 @@
+"""CPU-only checks of the product: the C-ABI library loads and exports every declared symbol, and the host-side half of
+Server::setup (filter construction + row encoding, which north_star keeps on the host) is byte-identical to the oracle."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import chalametpir_b200 as cp
+from chalametpir_b200._lib import EXPORTS, lib
+from oracle import oracle as O
+from conftest import ROOT, make_db
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "chalamet_b200.h")).read()
+    declared = set(re.findall(r"\b(chpir_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libchalamet_b200.so"
+
+
+def test_strerror_names_match_reference_variants():
+    assert lib.chpir_strerror(0) == b"ok"
+    assert lib.chpir_strerror(4) == b"FailedToDeserializeMatrixFromBytes"
+    assert lib.chpir_strerror(3) == b"IncompatibleDimensionForRowVectorTransposedMatrixMultiplication"
+    assert lib.chpir_strerror(5) == b"EmptyKVDatabase"
+    assert lib.chpir_strerror(11) == b"KVDatabaseSizeTooLarge"
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.Server.setup(bytes(32), make_db(10), 3)
+    assert e.value.variant == "CudaDeviceNotFound"
+
+
+@pytest.mark.parametrize("n", [1, 2, 10, 100, 2**8, 2**12, 2**16, 2**18, 2**20, 2**22, 2**30, 2**42])
+def test_bit_len_matches_oracle(n):
+    assert cp.find_mat_elem_bit_len(n) == O.find_mat_elem_bit_len(n)
+
+
+def test_bit_len_errors():
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.find_mat_elem_bit_len(2**50)
+    assert e.value.variant == "KVDatabaseSizeTooLarge"
+
+
+@pytest.mark.parametrize("arity", [3, 4])
+def test_shapes_match_oracle(arity):
+    rnd = random.Random(arity)
+    for n in [1, 2, 3, 7, 100, 1000, 2**16, 2**18, 2**20, 2**22] + [rnd.randint(1, 2**21) for _ in range(50)]:
+        b = O.find_mat_elem_bit_len(n)
+        K, N = cp.db_matrix_shape(arity, n, 1024, b)
+        assert K == O.filter_shape(arity, n)[2]
+        assert N == -(-(256 + 8 * 1024 + 8) // b)
+
+
+@pytest.mark.parametrize("arity", [3, 4])
+@pytest.mark.parametrize("n", [1, 2, 5, 300, 5000])
+def test_host_encode_is_byte_identical_to_oracle(arity, n):
+    db = make_db(n, seed=n + arity, val_len=(1, 120))
+    for b in (4, 9, 10, 14, O.find_mat_elem_bit_len(n)):
+        D, fb = cp.encode_kv_database(db, b, arity, filter_seed_rng=n)
+        D2, f2 = O.from_kv_database(db, b, arity, rng_seed=n)
+        assert fb == f2.to_bytes()
+        assert np.array_equal(D, D2)
+        # and the reference's own property: every value is recoverable (matrix.rs:1136-1232)
+        for k in list(db)[:20]:
+            assert O.recover_value(D, O.Filter.from_bytes(fb), k) == db[k]
+
+
+def test_host_encode_os_entropy_seed_is_still_valid():
+    db = make_db(500, seed=1)
+    D, fb = cp.encode_kv_database(db, 10, 3)  # filter seed from the OS, like the reference
+    D2, fb2 = cp.encode_kv_database(db, 10, 3)
+    assert fb != fb2  # fresh seed each time (binary_fuse_filter.rs:100)
+    f = O.Filter.from_bytes(fb)
+    for k, v in list(db.items())[:50]:
+        assert O.recover_value(D, f, k) == v
+
+
+def test_host_encode_errors():
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.encode_kv_database({}, 10, 3)
+    assert e.value.variant == "EmptyKVDatabase"
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.encode_kv_database(make_db(5), 10, 5)
+    assert e.value.variant == "UnsupportedArityForBinaryFuseFilter"
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.encode_kv_database(make_db(5), 15, 3)
+    assert e.value.variant == "ImpossibleEncodedDBMatrixElementBitLength"
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "chalametpir_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "chalamet_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
