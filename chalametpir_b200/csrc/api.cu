@@ -344,6 +344,8 @@ int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE
   if (int rc = resolve_slice(o, cols_n, &c0, &nc); rc != CHPIR_OK) return rc;
   std::lock_guard<std::mutex> g(ctx->mu);
   CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  // D was produced by the caller on some other stream: setup is a one-off, so order against everything in flight
+  CHPIR_CUDA(cudaDeviceSynchronize(), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
   const double t0 = now_s();
   chpir_server *srv = new chpir_server();
   int rc = setup_core(ctx, seed, d_device, rows_k, cols_n, c0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv);
@@ -526,7 +528,7 @@ int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries,
 int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream) {
   CHPIR_GUARD_BEGIN
   if (!srv || !q_device || !resp_device) return CHPIR_ERR_INVALID_ARGUMENT;
-  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : srv->ctx->stream;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL is the CUDA default stream, as for any launch
   CHPIR_CUDA(cudaMemsetAsync(resp_device, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   for (uint32_t i = 0; i < nq; i++)
     if (int rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, q_device + uint64_t(i) * srv->K,

@@ -1,9 +1,400 @@
-// placeholder until the tcgen05 kernel lands
+// gemm_tc.cu -- the setup hint GEMM  M = A . D mod 2^32  on the 5th-generation tensor cores (tcgen05, kind::i8).
+//
+// Replaces (reference): `impl Mul<&Matrix> for &Matrix` (chalametpir_common/src/matrix.rs:1040-1059) and the Vulkan
+// offload shaders/mat_x_mat.glsl:27-47 + shaders/mat_transpose.glsl:20-37.
+//
+// Arithmetic.  A is full-range u32 = 4 unsigned byte limbs a0..a3; D has b <= 14 bits = NB <= 2 byte limbs d0,d1.
+//   A.D mod 2^32 = sum_{i+j<=3} 2^{8(i+j)} (A_i . D_j)            (limb products with i+j >= 4 vanish mod 2^32)
+// Every A_i . D_j is a u8 x u8 GEMM with int32 accumulation.  int32 accumulation that WRAPS (instruction descriptor
+// saturate bit = 0) is exactly accumulation mod 2^32, so K needs no chunking; products with equal shift s = i+j share
+// one accumulator, giving 4 TMEM accumulators and 7 (NB=2) or 4 (NB=1) MMAs per 32-deep k-step.  The epilogue
+// recombines  acc0 + (acc1<<8) + (acc2<<16) + (acc3<<24)  and adds it into C with u32 atomics (split-K over CTAs is
+// exact because addition mod 2^32 is order independent).
+//
+// Data movement.  Two streaming pre-passes put the operands in the K-major byte layout the MMA wants:
+//   split_a_limbs      A[m][k] u32            -> A8[4][m][kp]   u8   (byte planes; the LE bytes of a u32 ARE the limbs)
+//   split_transpose_b  D[k][n] u32 (ld)       -> B8[NB][n][kp]  u8   (limb split + shared-memory tiled transpose)
+// The main kernel is warp specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, OOB zero fill for
+// the ragged M/N/K edges), warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace chpir {
-int launch_gemm_tc(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, uint32_t, int,
-                   cudaStream_t s, float *ms) {
-  if (ms) *ms = 0.f;
-  return launch_gemm_simt(A, B, ldb, C, m, k, n, s);
+namespace {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BN_MAX = 128;    // accumulator columns per shift; 4 * 128 = all 512 TMEM columns
+constexpr int BK = 128;        // bytes of K per stage row = one 128B swizzle row = 4 UMMA k-steps of 32
+constexpr int STAGES = 2;
+constexpr int A_TILE = BM * BK;      // 16 KB per limb
+constexpr int B_TILE = BN_MAX * BK;  // 16 KB per limb
+constexpr int kThreads = 192;
+
+// ----------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= uint64_t(1) << 16;                     // leading byte offset (ignored for swizzled K-major), canonical value 1
+  d |= uint64_t(1024 >> 4) << 32;             // stride byte offset: 8 rows * 128 B
+  d |= uint64_t(1) << 46;                     // descriptor version (sm_100)
+  d |= uint64_t(2) << 61;                     // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct __align__(8) Barriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+// grid: (tiles_m * tiles_n, splits).  One output tile x one K range per CTA.
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, uint32_t *__restrict__ C, uint32_t m,
+                   uint32_t n, uint32_t tiles_n, uint32_t bn, uint32_t kblocks_total, uint32_t kblocks_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Barriers bars;
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int STAGE_BYTES = 4 * A_TILE + NB * B_TILE;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+  const uint32_t kb0 = blockIdx.y * kblocks_per_split;
+  uint32_t kb1 = kb0 + kblocks_per_split;
+  if (kb1 > kblocks_total) kb1 = kblocks_total;
+  const uint32_t nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&bars.full[s], 1);
+      mbar_init(&bars.empty[s], 1);
+    }
+    mbar_init(&bars.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = bars.tmem_base;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        const uint32_t tx_bytes = 4 * A_TILE + NB * bn * BK;
+        for (uint32_t i = 0; i < nkb; i++) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&bars.empty[s], ph ^ 1);
+          mbar_expect_tx(&bars.full[s], tx_bytes);
+          uint8_t *st = smem + s * STAGE_BYTES;
+          const int kc = int((kb0 + i) * BK);
+#pragma unroll
+          for (int l = 0; l < 4; l++) tma_load_3d(st + l * A_TILE, &map_a, &bars.full[s], kc, int(tile_m * BM), l);
+#pragma unroll
+          for (int l = 0; l < NB; l++) tma_load_3d(st + 4 * A_TILE + l * B_TILE, &map_b, &bars.full[s], kc, int(tile_n * bn), l);
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer (one thread)
+      if (lane == 0) {
+        // kind::i8, u8 x u8 -> s32 (wrapping), K-major A and B, M = 128, N = bn
+        const uint32_t idesc = (2u << 4) | ((bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+        for (uint32_t i = 0; i < nkb; i++) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&bars.full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_base = a_base + 4 * A_TILE;
+#pragma unroll
+          for (int kk = 0; kk < BK / 32; kk++) {
+            const uint32_t first = (i == 0 && kk == 0) ? 0u : 1u;
+            uint64_t da[4], db[NB];
+#pragma unroll
+            for (int l = 0; l < 4; l++) da[l] = umma_desc_sw128(a_base + l * A_TILE + kk * 32);
+#pragma unroll
+            for (int l = 0; l < NB; l++) db[l] = umma_desc_sw128(b_base + l * B_TILE + kk * 32);
+            // accumulator s = i + j lives at TMEM columns [s*128, s*128 + bn)
+            umma_i8(tmem + 0 * BN_MAX, da[0], db[0], idesc, first);
+            umma_i8(tmem + 1 * BN_MAX, da[1], db[0], idesc, first);
+            umma_i8(tmem + 2 * BN_MAX, da[2], db[0], idesc, first);
+            umma_i8(tmem + 3 * BN_MAX, da[3], db[0], idesc, first);
+            if (NB == 2) {
+              umma_i8(tmem + 1 * BN_MAX, da[0], db[NB - 1], idesc, 1u);
+              umma_i8(tmem + 2 * BN_MAX, da[1], db[NB - 1], idesc, 1u);
+              umma_i8(tmem + 3 * BN_MAX, da[2], db[NB - 1], idesc, 1u);
+            }
+          }
+          umma_commit(&bars.empty[s]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&bars.acc_full);
+      }
+    } else {
+      // ---------------------------------------------------------------- epilogue: TMEM -> registers -> atomics on C
+      mbar_wait(&bars.acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_group = warp % 4;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+      const uint32_t row = tile_m * BM + lane_group * 32 + lane;
+      const uint32_t taddr = tmem + ((lane_group * 32) << 16);
+      for (uint32_t c0 = 0; c0 < bn; c0 += 16) {
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tmem_ld16(taddr + 0 * BN_MAX + c0, v0);
+        tmem_ld16(taddr + 1 * BN_MAX + c0, v1);
+        tmem_ld16(taddr + 2 * BN_MAX + c0, v2);
+        tmem_ld16(taddr + 3 * BN_MAX + c0, v3);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < m) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const uint32_t col = tile_n * bn + c0 + j;
+            const uint32_t v = v0[j] + (v1[j] << 8) + (v2[j] << 16) + (v3[j] << 24);
+            if (col < n && c0 + j < bn) atomicAdd(C + uint64_t(row) * n + col, v);
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// A[m][k] u32 -> planes[l][m][kp] u8, l = byte index.  One thread per 4 consecutive k.
+__global__ void split_a_limbs(const uint32_t *__restrict__ A, uint32_t m, uint64_t k, uint64_t kp, uint8_t *__restrict__ planes) {
+  const uint64_t groups = kp / 4;
+  const uint64_t total = uint64_t(m) * groups;
+  const uint64_t plane = uint64_t(m) * kp;
+  for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < total; idx += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t r = idx / groups, g = idx - r * groups;
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint64_t kk = 4 * g + j;
+      v[j] = kk < k ? __ldg(A + r * k + kk) : 0u;
+    }
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const uint32_t w = ((v[0] >> (8 * l)) & 0xffu) | (((v[1] >> (8 * l)) & 0xffu) << 8) | (((v[2] >> (8 * l)) & 0xffu) << 16) |
+                         (((v[3] >> (8 * l)) & 0xffu) << 24);
+      *reinterpret_cast<uint32_t *>(planes + l * plane + r * kp + 4 * g) = w;
+    }
+  }
+}
+
+// D[k][n] u32 (leading dimension ld) -> planes[l][n][kp] u8: limb split + transpose through a shared-memory tile.
+// Block = 256 threads, tile = 128 k x 32 n.
+template <int NB>
+__global__ void __launch_bounds__(256) split_transpose_b(const uint32_t *__restrict__ B, uint64_t k, uint32_t n, uint32_t ld, uint64_t kp,
+                                                          uint8_t *__restrict__ planes) {
+  __shared__ __align__(4) uint8_t tile[NB][32][128 + 4];
+  const uint64_t k0 = uint64_t(blockIdx.x) * 128;
+  const uint32_t n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // ty in 0..7
+  for (int kk = ty; kk < 128; kk += 8) {
+    const uint64_t gk = k0 + kk;
+    const uint32_t gn = n0 + tx;
+    const uint32_t v = (gk < k && gn < n) ? __ldg(B + gk * ld + gn) : 0u;
+#pragma unroll
+    for (int l = 0; l < NB; l++) tile[l][tx][kk] = uint8_t(v >> (8 * l));
+  }
+  __syncthreads();
+  const uint64_t plane = uint64_t(n) * kp;
+  for (int rowi = ty; rowi < NB * 32; rowi += 8) {
+    const int l = rowi / 32, nn = rowi % 32;
+    const uint32_t gn = n0 + nn;
+    const uint64_t gk = k0 + 4 * tx;
+    if (gn < n && gk < kp) {
+      const uint32_t w = *reinterpret_cast<const uint32_t *>(&tile[l][nn][4 * tx]);
+      *reinterpret_cast<uint32_t *>(planes + l * plane + uint64_t(gn) * kp + gk) = w;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// u8 tensor [planes][rows][k] with row pitch kp; box = 128 k-bytes x box_rows rows x 1 plane; 128B swizzle; OOB -> 0.
+int make_map(CUtensorMap *map, void *base, uint64_t k, uint64_t kp, uint64_t rows, uint32_t planes, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+  const cuuint64_t dims[3] = {k, rows, planes};
+  const cuuint64_t strides[2] = {kp, rows * kp};
+  const cuuint32_t box[3] = {BK, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+template <int NB>
+int run(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, int sm_count, cudaStream_t s,
+        float *kernel_ms) {
+  const uint64_t kp = (k + 15) / 16 * 16;
+  uint8_t *a8 = nullptr, *b8 = nullptr;
+  CHPIR_CUDA(cudaMalloc(&a8, 4ull * m * kp), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+  if (cudaMalloc(&b8, uint64_t(NB) * n * kp) != cudaSuccess) {
+    cudaFree(a8);
+    return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+  }
+  int rc = CHPIR_OK;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  do {
+    {
+      const uint64_t total = uint64_t(m) * (kp / 4);
+      const uint64_t want = (total + 255) / 256;
+      split_a_limbs<<<unsigned(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16), 256, 0, s>>>(A, m, k, kp, a8);
+      dim3 g(unsigned((kp + 127) / 128), (n + 31) / 32);
+      split_transpose_b<NB><<<g, 256, 0, s>>>(B, k, n, ldb, kp, b8);
+      if (cudaGetLastError() != cudaSuccess) {
+        rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+        break;
+      }
+    }
+    const uint32_t tiles_m = (m + BM - 1) / BM;
+    const uint32_t tiles_n0 = (n + BN_MAX - 1) / BN_MAX;
+    uint32_t bn = ((n + tiles_n0 - 1) / tiles_n0 + 15) / 16 * 16;
+    if (bn < 16) bn = 16;
+    const uint32_t tiles_n = (n + bn - 1) / bn;
+    const uint32_t kblocks = uint32_t((k + BK - 1) / BK);
+    // split K so that the grid fills whole waves of sm_count CTAs
+    const uint32_t tiles = tiles_m * tiles_n;
+    uint32_t best_splits = 1;
+    double best_eff = 0.0;
+    uint32_t max_splits = kblocks / 8;  // every split keeps >= 8 k-blocks (1024 k) of mainloop per epilogue
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 64) max_splits = 64;
+    for (uint32_t sp = 1; sp <= max_splits; sp++) {
+      const uint64_t units = uint64_t(tiles) * sp;
+      const uint64_t waves = (units + sm_count - 1) / sm_count;
+      const double eff = double(units) / double(waves * sm_count);
+      if (eff > best_eff + 0.02) best_eff = eff, best_splits = sp;
+    }
+    uint32_t kbps = (kblocks + best_splits - 1) / best_splits;
+    const uint32_t splits = (kblocks + kbps - 1) / kbps;
+
+    CUtensorMap map_a, map_b;
+    if ((rc = make_map(&map_a, a8, k, kp, m, 4, BM)) != CHPIR_OK) break;
+    if ((rc = make_map(&map_b, b8, k, kp, n, NB, bn)) != CHPIR_OK) break;
+    if (cudaMemsetAsync(C, 0, uint64_t(m) * n * 4, s) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+      break;
+    }
+    constexpr int smem_bytes = STAGES * (4 * A_TILE + NB * B_TILE) + 1024;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+      break;
+    }
+    cudaEventRecord(e0, s);
+    gemm_tc_kernel<NB><<<dim3(tiles, splits), kThreads, smem_bytes, s>>>(map_a, map_b, C, m, n, tiles_n, bn, kblocks, kbps);
+    cudaEventRecord(e1, s);
+    if (cudaGetLastError() != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+      break;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);  // the planes are freed below
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e, "gemm_tc_kernel");
+      rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+      break;
+    }
+    if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+  } while (false);
+  if (rc != CHPIR_OK && rc != CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED) set_last_cuda_error(cudaGetLastError(), "gemm_tc");
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a8);
+  cudaFree(b8);
+  return rc;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, uint32_t b_bits,
+                   int sm_count, cudaStream_t s, float *kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0.f;
+  if (b_bits == 0 || b_bits > 16) return CHPIR_ERR_INVALID_ARGUMENT;  // two byte limbs cover every legal element width (4..14)
+  if (k > 0x7fffffffull - BK) return CHPIR_ERR_INVALID_ARGUMENT;      // TMA coordinates are int32
+  return b_bits <= 8 ? run<1>(A, B, ldb, C, m, k, n, sm_count, s, kernel_ms) : run<2>(A, B, ldb, C, m, k, n, sm_count, s, kernel_ms);
+}
+
 }  // namespace chpir

@@ -417,7 +417,7 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
   PeelResult pr;
   if (int rc = peel(arity, digests, n, b, max_attempts, seed_rng, &pr); rc != CHPIR_OK) return rc;
 
-  uint64_t K, N;
+  uint64_t K = 0, N = 0;
   db_matrix_shape(arity, n, max_vlen, b, &K, &N);
   const uint32_t mask = (1u << b) - 1;
   const FilterParams &fp = pr.params;

@@ -33,36 +33,48 @@ namespace {
 constexpr int kMaxThreads = 768;
 constexpr int kUnroll = 4;
 
+// Streaming 16-byte load (read-only path, no L1 allocation).  Deliberately NOT volatile: the compiler may hoist and
+// batch these so that several are in flight per thread.
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 
-// acc[f] += qk * field_f(word) for the FPW b-bit fields of a little-endian u64 given as (lo, hi).
+// acc[f] += qk * G_f  with  G_f = (word >> f*B) mod 2^32  -- the field WITHOUT masking off the higher fields.
+// Because  field_f = G_f - (G_{f+1} << B)  holds as an integer identity, and everything downstream is linear mod 2^32,
+// the mask is applied once per kernel (unmask_fields) instead of once per element: one funnel shift + one IMAD per
+// element in the hot loop.
 template <int B>
 __device__ __forceinline__ void fma_fields(uint32_t lo, uint32_t hi, uint32_t qk, uint32_t *acc) {
   constexpr int FPW = 64 / B;
-  constexpr uint32_t MASK = (1u << B) - 1u;
 #pragma unroll
   for (int f = 0; f < FPW; f++) {
     const int o = f * B;
-    uint32_t v;
-    if (o + B <= 32) {
-      v = lo >> o;
-      if (o + B < 32) v &= MASK;
-    } else if (o >= 32) {
-      v = hi >> (o - 32);
-      if (f != FPW - 1) v &= MASK;  // bits above the last field are zero by construction
-    } else {
-      v = __funnelshift_r(lo, hi, o) & MASK;
-    }
-    acc[f] += qk * v;
+    uint32_t g;
+    if (o == 0)
+      g = lo;
+    else if (o < 32)
+      g = __funnelshift_r(lo, hi, o);
+    else if (o == 32)
+      g = hi;
+    else
+      g = hi >> (o - 32);
+    acc[f] += qk * g;
   }
 }
 
+// true_f = raw_f - (raw_{f+1} << B); the last field of a word has nothing above it (padding bits are zero).
+template <int B>
+__device__ __forceinline__ void unmask_fields(uint32_t *acc) {
+  constexpr int FPW = 64 / B;
+#pragma unroll
+  for (int f = 0; f + 1 < FPW; f++) acc[f] -= acc[f + 1] << B;
+}
+
 // One block: unit chunk blockIdx.y (cu units starting at ub), k-rows [blockIdx.x*rows_per_block, ...).
-// Thread t -> unit u = t % cu, row lane r = t / cu (< R).
+// Thread t -> unit u = t % cu, row lane r = t / cu (< R).  Each thread keeps kUnroll 16-byte loads of the NEXT
+// iteration in flight while it multiplies the current ones (register double buffering).
 template <int B>
 __global__ void __launch_bounds__(kMaxThreads) respond_kernel(const uint4 *__restrict__ packed, const uint32_t *__restrict__ q,
                                                                 uint32_t *__restrict__ resp, uint64_t K, uint32_t units, uint32_t cu,
@@ -82,30 +94,57 @@ __global__ void __launch_bounds__(kMaxThreads) respond_kernel(const uint4 *__res
   uint64_t k1 = k0 + rows_per_block;
   if (k1 > K) k1 = K;
 
-  if (active && k0 < K) {
+  if (active && k0 + r < k1) {
+    const uint64_t my_rows = (k1 - k0 - r + R - 1) / R;  // rows k0+r, k0+r+R, ... owned by this thread
+    const uint64_t full = my_rows / kUnroll;
+    const uint64_t step = uint64_t(R) * units;            // uint4 stride between my consecutive rows
     const uint4 *p = packed + (k0 + r) * units + unit;
-    const uint64_t step = uint64_t(R) * units;
-    uint64_t k = k0 + r;
-    // main loop: kUnroll independent 16-byte loads in flight per thread
-    for (; k + uint64_t(kUnroll - 1) * R < k1; k += uint64_t(kUnroll) * R, p += kUnroll * step) {
+    const uint32_t *pq = q + k0 + r;
+
+    if (full > 0) {
       uint4 w[kUnroll];
       uint32_t qk[kUnroll];
 #pragma unroll
-      for (int j = 0; j < kUnroll; j++) w[j] = ld_stream(p + j * step);
-#pragma unroll
-      for (int j = 0; j < kUnroll; j++) qk[j] = __ldg(q + k + uint64_t(j) * R);
-#pragma unroll
       for (int j = 0; j < kUnroll; j++) {
-        fma_fields<B>(w[j].x, w[j].y, qk[j], acc);
-        fma_fields<B>(w[j].z, w[j].w, qk[j], acc + FPW);
+        w[j] = ld_stream(p + j * step);
+        qk[j] = __ldg(pq + uint64_t(j) * R);
       }
+      for (uint64_t it = 0; it < full; it++) {
+        // prefetch the next group; on the last trip re-read the current one (in bounds, result unused)
+        const bool more = it + 1 < full;
+        const uint4 *pn = more ? p + kUnroll * step : p;
+        const uint32_t *pqn = more ? pq + uint64_t(kUnroll) * R : pq;
+        uint4 nw[kUnroll];
+        uint32_t nq[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+          nw[j] = ld_stream(pn + j * step);
+          nq[j] = __ldg(pqn + uint64_t(j) * R);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+          fma_fields<B>(w[j].x, w[j].y, qk[j], acc);
+          fma_fields<B>(w[j].z, w[j].w, qk[j], acc + FPW);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+          w[j] = nw[j];
+          qk[j] = nq[j];
+        }
+        p = pn;
+        pq = pqn;
+      }
+      p += kUnroll * step;  // p sat on the last full group
+      pq += uint64_t(kUnroll) * R;
     }
-    for (; k < k1; k += R, p += step) {
+    for (uint64_t i = full * kUnroll; i < my_rows; i++, p += step, pq += R) {
       const uint4 w = ld_stream(p);
-      const uint32_t qk = __ldg(q + k);
+      const uint32_t qk = __ldg(pq);
       fma_fields<B>(w.x, w.y, qk, acc);
       fma_fields<B>(w.z, w.w, qk, acc + FPW);
     }
+    unmask_fields<B>(acc);
+    unmask_fields<B>(acc + FPW);
   }
 
   // fold the R row lanes of each unit, then one atomic per (block, column)
@@ -149,8 +188,6 @@ __global__ void pack_kernel(const uint32_t *__restrict__ d, uint64_t K, uint32_t
 template <int B>
 int respond_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q, uint32_t *resp,
                      cudaStream_t s) {
-  const uint32_t chunks = (L.units + (P.threads / P.rows_per_iter) - 1) / (P.threads / P.rows_per_iter);
-  (void)chunks;
   const uint32_t cu = P.threads / P.rows_per_iter;  // units per chunk (plan stores threads = R * cu exactly)
   dim3 grid(P.grid, (L.units + cu - 1) / cu);
   const uint32_t block = ((P.threads + 31) / 32) * 32;
@@ -170,9 +207,12 @@ int pack_dispatch(const uint32_t *d, uint64_t K, uint32_t ld, uint32_t col_begin
 }
 
 template <int B>
-int occupancy_of() {
+int occupancy_of(int threads) {
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, respond_kernel<B>, kMaxThreads, 0) != cudaSuccess) occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, respond_kernel<B>, threads, 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    occ = 1;
+  }
   return occ;
 }
 
@@ -199,32 +239,27 @@ RespondPlan plan_respond(const PackedLayout &L, uint64_t K, int sm_count) {
   // column chunking only when one row has more units than a block has threads
   const uint32_t chunks = (L.units + kMaxThreads - 1) / kMaxThreads;
   const uint32_t cu = (L.units + chunks - 1) / chunks;
-  // rows per iteration: fill the block, prefer whole warps
+  auto occ_of = [&](uint32_t b, int threads) -> int {
+#define CHPIR_OCC(B) occupancy_of<B>(threads)
+    CHPIR_DISPATCH_B(b, CHPIR_OCC)
+#undef CHPIR_OCC
+  };
+  // rows per iteration R: maximise resident ACTIVE threads per SM (register- and warp-granularity aware), prefer
+  // smaller blocks on ties (finer K split, less tail)
   uint32_t best_r = 1;
-  double best_score = -1.0;
+  int best_occ = 1;
+  long best_active = -1;
   for (uint32_t r = 1; r * cu <= uint32_t(kMaxThreads); r++) {
-    const uint32_t th = r * cu;
-    const double util = double(th) / double(((th + 31) / 32) * 32);
-    const double size_pref = th >= 384 ? 1.0 : double(th) / 384.0;
-    const double score = util * size_pref;
-    if (score > best_score + 1e-9 || (score > best_score - 1e-9 && r > best_r && th <= 640)) best_score = score, best_r = r;
+    const int th = int(((r * cu + 31) / 32) * 32);
+    int occ = occ_of(L.b, th);
+    if (occ < 1) occ = 1;
+    const long active = long(occ) * long(r * cu);
+    if (active > best_active + best_active / 50) best_active = active, best_r = r, best_occ = occ;
   }
   P.rows_per_iter = best_r;
   P.threads = best_r * cu;
   // one wave of resident blocks; each block owns a contiguous k-range
-  int occ = 1;
-  auto occ_of = [&](uint32_t b) -> int {
-#define CHPIR_OCC(B) occupancy_of<B>()
-    CHPIR_DISPATCH_B(b, CHPIR_OCC)
-#undef CHPIR_OCC
-  };
-  occ = occ_of(L.b);
-  if (occ <= 0) occ = 1;
-  const uint32_t block_threads = ((P.threads + 31) / 32) * 32;
-  int by_threads = 2048 / int(block_threads);
-  if (by_threads < 1) by_threads = 1;
-  if (occ > by_threads) occ = by_threads;
-  uint64_t want_blocks = uint64_t(sm_count) * occ / chunks;
+  uint64_t want_blocks = uint64_t(sm_count) * best_occ / chunks;
   if (want_blocks < 1) want_blocks = 1;
   const uint64_t quantum = uint64_t(P.rows_per_iter) * kUnroll;
   uint64_t rpb = (K + want_blocks - 1) / want_blocks;

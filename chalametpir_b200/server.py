@@ -205,7 +205,7 @@ class Server:
 
     def respond_device(self, q_ptr: int, nq: int, resp_ptr: int, stream: int = 0) -> None:
         """Device-resident respond: q_ptr -> nq x K uint32, resp_ptr -> nq x cols_n uint32, enqueued on `stream`."""
-        check(lib.chpir_server_respond_device(self._h, q_ptr, nq, resp_ptr, stream or None))
+        check(lib.chpir_server_respond_device(self._h, q_ptr, nq, resp_ptr, stream or None))  # 0/None = CUDA default stream
 
     # ------------------------------------------------------------------ introspection
     def setup_timing(self) -> dict:

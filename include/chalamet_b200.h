@@ -28,6 +28,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CHPIR_API __attribute__((visibility("default")))
+#else
+#define CHPIR_API
+#endif
+
 #define CHPIR_LWE_DIMENSION 1774u     /* chalametpir_common/src/params.rs:1  */
 #define CHPIR_SEED_BYTE_LEN 32u       /* chalametpir_common/src/params.rs:5  */
 #define CHPIR_FILTER_PARAM_BYTE_LEN 68u /* chalametpir_common/src/binary_fuse_filter.rs:462-486 (64-bit usize) */
@@ -63,27 +69,27 @@ typedef enum chpir_status {
 typedef struct chpir_ctx chpir_ctx;       /* one GPU: device ordinal, streams, scratch pools           */
 typedef struct chpir_server chpir_server; /* server.rs:15-21 `Server`: packed D resident in HBM (a column slice) */
 
-const char *chpir_strerror(int status);
+CHPIR_API const char *chpir_strerror(int status);
 /* Last CUDA error string seen on this thread (diagnostics only). */
-const char *chpir_last_cuda_error(void);
+CHPIR_API const char *chpir_last_cuda_error(void);
 
 /* ---- device context: replaces gpu_utils::setup_gpu (gpu_utils.rs:25-79) ------------------------------ */
-int chpir_device_count(int *count);
-int chpir_ctx_create(int device_ordinal, chpir_ctx **out);
-void chpir_ctx_destroy(chpir_ctx *ctx);
+CHPIR_API int chpir_device_count(int *count);
+CHPIR_API int chpir_ctx_create(int device_ordinal, chpir_ctx **out);
+CHPIR_API void chpir_ctx_destroy(chpir_ctx *ctx);
 
 /* ---- host side that stays on the host (north_star); mirrors chalametpir_common --------------------- */
 /* server.rs:193-218 find_encoded_db_matrix_element_bit_length */
-int chpir_find_mat_elem_bit_len(uint64_t db_entry_count, uint32_t *mat_elem_bit_len);
+CHPIR_API int chpir_find_mat_elem_bit_len(uint64_t db_entry_count, uint32_t *mat_elem_bit_len);
 /* Shape of D for a DB: rows K = num_fingerprints (binary_fuse_filter.rs:52-67 / :261-276),
  * cols N = ceil((256 + 8*max_value_byte_len + 8) / b) (matrix.rs:699-700). */
-int chpir_db_matrix_shape(uint32_t arity, uint64_t db_entry_count, uint64_t max_value_byte_len, uint32_t mat_elem_bit_len,
+CHPIR_API int chpir_db_matrix_shape(uint32_t arity, uint64_t db_entry_count, uint64_t max_value_byte_len, uint32_t mat_elem_bit_len,
                           uint64_t *rows_k, uint64_t *cols_n);
 /* Matrix::from_kv_database::<ARITY> (matrix.rs:633-648, :687-755, :819-894) + BinaryFuseFilter::to_bytes.
  * Keys/values are passed flattened: blob + (n+1) offsets.  d_out (rows_k*cols_n u32, caller allocated) receives D.
  * filter_seed_rng: NULL -> OS entropy (reference behaviour: ChaCha20Rng::from_os_rng, binary_fuse_filter.rs:100,309);
  * otherwise a 64-bit seed for a deterministic stream of candidate filter seeds (tests / reproducible vectors). */
-int chpir_encode_kv_database(uint32_t arity, uint64_t db_entry_count, const uint8_t *key_blob, const uint64_t *key_offsets,
+CHPIR_API int chpir_encode_kv_database(uint32_t arity, uint64_t db_entry_count, const uint8_t *key_blob, const uint64_t *key_offsets,
                              const uint8_t *value_blob, const uint64_t *value_offsets, uint32_t mat_elem_bit_len,
                              uint32_t max_attempt_count, const uint64_t *filter_seed_rng, uint32_t *d_out,
                              uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN]);
@@ -102,20 +108,20 @@ typedef struct chpir_setup_opts {
 /* d_host: K x N row-major u32 (Matrix elems), values < 2^mat_elem_bit_len.
  * hint_out receives the wire-format hint slice: header (lwe_rows, col_count) + lwe_rows*col_count u32; with the
  * default full slice this is byte-identical to the reference's `hint_bytes`.  hint_out may be NULL iff skip_hint. */
-int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k,
+CHPIR_API int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k,
                        uint32_t cols_n, uint32_t mat_elem_bit_len, const chpir_setup_opts *opts, uint8_t *hint_out,
                        size_t hint_cap, size_t *hint_len, chpir_server **out);
 /* Same, with D already resident in device memory (K x N row-major u32) -- used for device-generated synthetic D. */
-int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k,
+CHPIR_API int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k,
                               uint32_t cols_n, uint32_t mat_elem_bit_len, const chpir_setup_opts *opts, uint8_t *hint_out,
                               size_t hint_cap, size_t *hint_len, chpir_server **out);
 /* Complete Server::setup::<ARITY>(seed, db) (server.rs:103): host filter + encode, then chpir_server_setup. */
-int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t db_entry_count,
+CHPIR_API int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t db_entry_count,
                                const uint8_t *key_blob, const uint64_t *key_offsets, const uint8_t *value_blob,
                                const uint64_t *value_offsets, const uint64_t *filter_seed_rng, const chpir_setup_opts *opts,
                                uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
                                uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN], chpir_server **out);
-void chpir_server_destroy(chpir_server *srv);
+CHPIR_API void chpir_server_destroy(chpir_server *srv);
 
 /* Phase split of the last setup on this server, seconds. */
 typedef struct chpir_setup_timing {
@@ -127,7 +133,7 @@ typedef struct chpir_setup_timing {
   double d2h_s;         /* hint download                                               */
   double total_s;
 } chpir_setup_timing;
-int chpir_server_setup_timing(const chpir_server *srv, chpir_setup_timing *out);
+CHPIR_API int chpir_server_setup_timing(const chpir_server *srv, chpir_setup_timing *out);
 
 /* Shape / footprint of the resident server. */
 typedef struct chpir_server_info {
@@ -139,30 +145,30 @@ typedef struct chpir_server_info {
   uint64_t row_pitch_bytes; /* bytes per k-row of the packed slice */
   uint64_t packed_bytes;    /* total resident packed bytes = what one respond streams */
 } chpir_server_info;
-int chpir_server_get_info(const chpir_server *srv, chpir_server_info *out);
+CHPIR_API int chpir_server_get_info(const chpir_server *srv, chpir_server_info *out);
 
 /* ---- respond: replaces Server::respond (server.rs:184-190) -> Matrix::from_bytes (matrix.rs:973-1010) +
  *      row_vector_x_compressed_transposed_matrix (matrix.rs:328-485) + to_bytes --------------------------- */
 /* query: wire format 1 x K.  resp_out: wire format 1 x col_count (3768 B at N=940). */
-int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_len, uint8_t *resp_out, size_t resp_cap,
+CHPIR_API int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_len, uint8_t *resp_out, size_t resp_cap,
                          size_t *resp_len);
 /* nq queries, each wire format 1 x K, concatenated responses each of `resp_stride` bytes. */
-int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries, const size_t *query_lens, uint32_t nq,
+CHPIR_API int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries, const size_t *query_lens, uint32_t nq,
                                uint8_t *resp_out, size_t resp_stride);
 /* Device-resident variants (inputs already in HBM): q_device = nq x K u32, resp_device = nq x col_count u32,
- * enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the context's stream); no synchronisation. */
-int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream);
+ * enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the CUDA default stream); no synchronisation. */
+CHPIR_API int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream);
 
 /* ---- building blocks exposed for parity tests and for composing other paths ------------------------ */
 /* Matrix::generate_from_seed (matrix.rs:541-558) on device; rows [row_begin, row_begin+row_count) of the rows x cols
  * matrix are copied to out_host (row_count*cols u32).  The whole prefix of the XOF stream is walked on device. */
-int chpir_generate_from_seed(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols,
+CHPIR_API int chpir_generate_from_seed(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols,
                              uint64_t row_begin, uint64_t row_count, uint32_t *out_host);
 /* &A * &D (matrix.rs:1040-1059) on device for host operands; variant as in chpir_setup_opts.gemm_variant. */
-int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64_t a_cols, const uint32_t *b_host, uint64_t b_rows,
+CHPIR_API int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64_t a_cols, const uint32_t *b_host, uint64_t b_rows,
                  uint64_t b_cols, uint32_t b_elem_bit_len, uint32_t variant, uint32_t *out_host);
 /* Device time (ms) of the dominant kernels in the last call on this ctx/server, for bench.py's roofline block. */
-int chpir_server_last_kernel_ms(const chpir_server *srv, float *respond_ms, float *gemm_ms, float *expand_ms);
+CHPIR_API int chpir_server_last_kernel_ms(const chpir_server *srv, float *respond_ms, float *gemm_ms, float *expand_ms);
 
 #ifdef __cplusplus
 }
