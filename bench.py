@@ -1,0 +1,483 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ChalametPIR server hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration `metric` is quoted on): 2^20 entries x 32-byte keys x 1 kB values,
+3-wise XOR binary fuse filter  ->  D is K x N = 1 179 648 x 940 with 9-bit entries, LWE dimension 1774.
+D is synthetic (uniform 9-bit entries from a counter hash, generated directly in HBM; SURVEY.md section 8d "synthetic-D").
+
+A "step" is one pass of Server::respond over a batch of `--queries-per-step` independent queries: every query streams
+the whole resident D once (single-query GEMV, the reference's `server_respond`).  `value` is whole-job queries/s with
+queries already resident in HBM; `e2e` is the same metric through the C ABI call `chpir_server_respond` with HOST
+buffers (pinned), H2D of each query and D2H of each response inside the timed region.
+`Server::setup` (A expansion + hint GEMM + pack) runs once before the timed steps and is reported under "setup".
+
+With N > 1 the columns of D (and so of the hint and of every response) are sliced across the ranks; per step rank 0
+broadcasts the query batch over NCCL, every rank answers for its slice, and the response slices are gathered on rank 0.
+The database is the same size at every N, so `scaling` is "strong".
+
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on the same
+workload; the Rust reference itself cannot be built in this image (no cargo/rustc), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+SEED_MU = bytes((7 * i + 3) & 0xFF for i in range(32))
+LWE = 1774
+VALUE_BYTES = 1024
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FALLBACK_BF16_TFLOPS = 1590.0
+
+
+def shape_of(log2n: int, arity: int, use_oracle: bool = False):
+    """(b, K, N) from the reference's formulas (server.rs:193-218, binary_fuse_filter.rs:52-67/:261-276, matrix.rs:699-700)."""
+    n = 1 << log2n
+    if use_oracle:  # the CPU arm must not touch the product library
+        from oracle import oracle as O
+
+        b = O.find_mat_elem_bit_len(n)
+        K = O.filter_shape(arity, n)[2]
+        N = -(-(256 + 8 * VALUE_BYTES + 8) // b)
+    else:
+        import chalametpir_b200 as cp
+
+        b = cp.find_mat_elem_bit_len(n)
+        K, N = cp.db_matrix_shape(arity, n, VALUE_BYTES, b)
+    return b, K, N
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", FALLBACK_BF16_TFLOPS)), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": FALLBACK_BF16_TFLOPS, "source": "fallback"}
+
+
+def slice_of(N: int, rank: int, world: int):
+    base, rem = divmod(N, world)
+    c0 = rank * base + min(rank, rem)
+    return c0, base + (1 if rank < rem else 0)
+
+
+def gen_d_slice(torch, K: int, c0: int, nc: int, b: int, device, salt: int = 0x5EED):
+    """D[k][n] = hash(k, n) mod 2^b for n in [c0, c0+nc): every rank derives its own slice of the same matrix."""
+    D = torch.empty((K, nc), dtype=torch.int32, device=device)
+    cols = torch.arange(c0, c0 + nc, device=device, dtype=torch.int64)
+    M32 = 0xFFFFFFFF
+    chunk = 1 << 16
+    for r0 in range(0, K, chunk):
+        r1 = min(K, r0 + chunk)
+        rows = torch.arange(r0, r1, device=device, dtype=torch.int64)
+        x = (rows[:, None] * 0x9E3779B1 + cols[None, :] * 0x85EBCA77 + salt) & M32
+        x ^= x >> 15
+        x = (x * 0x2C1B3C6D) & M32
+        x ^= x >> 12
+        x = (x * 0x297A2D39) & M32
+        x ^= x >> 15
+        D[r0:r1] = (x & ((1 << b) - 1)).to(torch.int32)
+    return D
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples taken while the GPU was busy: the upper half of the clock readings
+        busy = sorted(sm)[len(sm) // 2 :]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w": round(statistics.median(pw), 1), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def host_d(K: int, N: int, b: int, seed: int = 1234):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 1 << b, size=(K, N), dtype=np.uint16).astype(np.uint32)
+
+
+def cpu_respond_qps(K_full: int, N: int, b: int, frac: int, iters: int, min_iters: int = 3):
+    """Oracle (CPU restatement of Server::respond, matrix.rs:328-485) on a 1/frac row sample of the workload.
+    Respond is linear in K, so queries/s at full size = measured / frac."""
+    from oracle import oracle as O
+
+    Ks = max(3, K_full // frac)
+    D = host_d(Ks, N, b)
+    srv, _ = O.Server.setup_from_matrix(SEED_MU, D, b, want_hint=False)
+    del D
+    rng = np.random.default_rng(99)
+    q = rng.integers(0, 2**32, size=Ks, dtype=np.uint64).astype(np.uint32)
+    qb = O.matrix_to_bytes(q.reshape(1, -1))
+    srv.respond(qb)
+    times = []
+    for _ in range(max(iters, min_iters)):
+        t = time.perf_counter()
+        srv.respond(qb)
+        times.append(time.perf_counter() - t)
+    t_med = statistics.median(times)
+    scale = K_full / Ks
+    return {"qps_full": 1.0 / (t_med * scale), "ms_sample": t_med * 1e3, "rows_sample": Ks, "threads": O.num_threads(), "times": times,
+            "scale": scale}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference's Server::respond on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b, K, N = shape_of(args.log2n, args.arity, use_oracle=True)
+    frac = args.ref_sample_frac
+    from oracle import oracle as O
+
+    Ks = K // frac
+    D = host_d(Ks, N, b)
+    srv, _ = O.Server.setup_from_matrix(SEED_MU, D, b, want_hint=False)
+    del D
+    rng = np.random.default_rng(5)
+    qs = [O.matrix_to_bytes(rng.integers(0, 2**32, size=Ks, dtype=np.uint64).astype(np.uint32).reshape(1, -1)) for _ in range(args.queries_per_step)]
+    for _ in range(args.warmup):
+        for qb in qs[: max(1, args.queries_per_step // 4)]:
+            srv.respond(qb)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for qb in qs:
+            srv.respond(qb)
+    dt = time.perf_counter() - t0
+    scale = K / Ks
+    nq = args.steps * args.queries_per_step
+    qps = nq / (dt * scale)
+    threads = O.num_threads()
+    sample = (f"rows [0,{Ks}) of K={K} (1/{frac} of the database, all {N} columns); respond is linear in K, queries/s scaled by {scale:.3f}; "
+              f"{nq} queries; OpenMP threads={threads}")
+    line = {
+        "impl": "reference", "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * scale, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, b, K, N),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement (oracle/chalamet_oracle.c) of the reference's Server::respond; the Rust reference cannot be built here (no cargo/rustc)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, b, K, N):
+    return {
+        "workload": f"2^{args.log2n} entries x 32B keys x {VALUE_BYTES}B values, {args.arity}-wise XOR filter (BASELINE.json configs[2])",
+        "K": K, "N": N, "mat_elem_bit_len": b, "lwe_dimension": LWE, "queries_per_step": args.queries_per_step,
+        "sharding": f"columns/{args.gpus}" if args.gpus > 1 else "none",
+        "l2": "inputs larger than L2 (resident packed D per GPU >> 126 MB at N<=4; every query streams all of it)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import chalametpir_b200 as cp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE is 1)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    b, K, N = shape_of(args.log2n, args.arity)
+    c0, nc = slice_of(N, rank, world)
+    Q = args.queries_per_step
+
+    # ---------------- Server::setup on this rank's column slice (one-off; reported, not part of the timed steps)
+    D = gen_d_slice(torch, K, c0, nc, b, dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    srv, hint = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, skip_hint=args.skip_hint)
+    setup_wall = time.perf_counter() - t0
+    tm = srv.setup_timing()
+    km = srv.last_kernel_ms()
+    setup = {"wall_s": setup_wall, **{k: round(v, 6) for k, v in tm.items()}, "gemm_kernel_ms": km["gemm_ms"], "skipped_hint": bool(args.skip_hint)}
+
+    # ---------------- parity spot checks (outside every timed region; numpy / oracle as the checker)
+    parity = {}
+    cols = sorted(set(int(x) for x in np.linspace(0, nc - 1, num=min(nc, 6))))
+    Dcols = D[:, cols].cpu().numpy().astype(np.uint64)
+    if hint is not None and rank == 0:
+        from oracle import oracle as O
+
+        a0 = O.generate_rows_from_seed(K, SEED_MU, 0, 2).astype(np.uint64)  # rows 0,1 of A: the head of the XOF stream
+        # exact mod-2^32 dot products without overflow: split A into 16-bit halves
+        lo, hi = a0 & 0xFFFF, a0 >> 16
+        want = ((lo @ Dcols) + (((hi @ Dcols) & 0xFFFF) << 16)) & 0xFFFFFFFF
+        H = np.frombuffer(hint, dtype="<u4")
+        assert H[0] == LWE and H[1] == nc, "hint header"
+        got = H[2:].reshape(LWE, nc)[:2][:, cols].astype(np.uint64)
+        parity["hint_rows_0_1"] = bool(np.array_equal(got, want))
+        assert parity["hint_rows_0_1"], "hint rows 0..1 differ from the oracle"
+    del D
+    torch.cuda.empty_cache()
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000)
+    q_dev = torch.randint(-(2**31), 2**31, (Q, K), dtype=torch.int32, device=dev, generator=g)
+    if world > 1:
+        dist.broadcast(q_dev, 0)
+    resp_dev = torch.zeros((Q, nc), dtype=torch.int32, device=dev)
+    counts = [slice_of(N, r, world)[1] for r in range(world)]
+    pad = max(counts)
+    gather_buf = torch.zeros((world, Q, pad), dtype=torch.int32, device=dev) if world > 1 else None
+    send_buf = torch.zeros((Q, pad), dtype=torch.int32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(bcast: bool = True):
+        if world > 1 and bcast:
+            dist.broadcast(q_dev, 0)
+        srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
+        if world > 1:
+            send_buf[:, :nc] = resp_dev
+            dist.all_gather_into_tensor(gather_buf.view(-1), send_buf.view(-1))
+
+    step_device()
+    torch.cuda.synchronize()
+    # response parity on sampled columns
+    qh = (q_dev[0].cpu().numpy().view(np.uint32)).astype(np.uint64)
+    lo, hi = qh & 0xFFFF, qh >> 16
+    want = ((lo @ Dcols) + (((hi @ Dcols) & 0xFFFF) << 16)) & 0xFFFFFFFF
+    got = resp_dev[0].cpu().numpy().view(np.uint32)[cols].astype(np.uint64)
+    parity["respond_sampled_columns"] = bool(np.array_equal(got, want))
+    assert parity["respond_sampled_columns"], "respond differs from the exact dot product on sampled columns"
+
+    # ---------------- timed region: K steps, device-resident
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # kernel-only timing of the dominant kernel (respond GEMV), same launches without the collectives
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
+    k1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_kernel = k0.elapsed_time(k1) / (args.steps * Q)
+    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_kernel = float(t[0]), float(t[1])
+    n_queries = args.steps * Q
+    qps = n_queries / (ms_total * 1e-3)
+
+    # ---------------- e2e: C ABI with host (pinned) buffers, `--e2e-threads` concurrent callers as Arc<Server> sharing allows
+    qlen, rlen = 8 + 4 * K, 8 + 4 * nc
+    q_host = torch.empty((Q, qlen), dtype=torch.uint8).pin_memory()
+    r_host = torch.empty((Q, rlen), dtype=torch.uint8).pin_memory()
+    qh_np = q_host.numpy()
+    hdr = np.array([1, K], dtype="<u4").view(np.uint8)
+    qcpu = q_dev.cpu().numpy().view(np.uint8).reshape(Q, 4 * K)
+    for i in range(Q):
+        qh_np[i, :8] = hdr
+        qh_np[i, 8:] = qcpu[i]
+
+    def e2e_step():
+        nthreads = max(1, min(args.e2e_threads, Q))
+        errs = []
+
+        def work(tid):
+            try:
+                for i in range(tid, Q, nthreads):
+                    srv.respond_into(q_host[i].data_ptr(), qlen, r_host[i].data_ptr(), rlen)
+            except Exception as ex:  # pragma: no cover
+                errs.append(ex)
+
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errs:
+            raise errs[0]
+        if world > 1:
+            r_dev = torch.zeros((Q, pad), dtype=torch.int32, device=dev)
+            r_dev[:, :nc] = r_host[:, 8:].view(torch.int32).reshape(Q, nc).to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(gather_buf.view(-1), r_dev.view(-1))
+            if rank == 0:
+                gather_buf.cpu()
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_qps = n_queries / float(te[0])
+    # e2e parity: the host-path bytes equal the device-path result
+    got = r_host[0, 8:].numpy().view(np.uint32)
+    srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
+    torch.cuda.synchronize()
+    parity["e2e_equals_device_path"] = bool(np.array_equal(got, resp_dev[0].cpu().numpy().view(np.uint32)))
+    assert parity["e2e_equals_device_path"]
+
+    # ---------------- roofline of the dominant kernel
+    pk = peaks()
+    streamed = srv.packed_bytes + 4 * K + 4 * nc  # bytes one launch on this rank must move: resident packed slice + query + response
+    ref_layout = 4 * nc * ((K + 2) // 3 if b in (9, 10) else (K + 1) // 2 if b >= 11 else (K + 3) // 4) + 4 * K + 4 * nc
+    achieved = streamed / (ms_kernel * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "respond_kernel<9> (streaming u32 GEMV over K-major bit-packed D)", "achieved": achieved, "peak": pk["hbm_gbs"],
+        "peak_source": pk["source"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+        "bytes_per_launch": streamed, "bytes_per_launch_reference_layout": ref_layout, "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9,
+        "us_per_launch": ms_kernel * 1e3,
+    }
+    prof = os.path.join(ROOT, "profiles", "respond_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(f"2^{args.log2n}/{args.arity}/n{world}")
+        except Exception:
+            pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline on the host cores (rank 0, N = 1 only)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_respond_qps(K, N, b, args.cpu_sample_frac, iters=5)
+        cpu_baseline = {
+            "value": r["qps_full"], "unit": "queries/s", "cores": r["threads"], "kind": "port",
+            "sample": f"rows [0,{r['rows_sample']}) of K={K} (1/{args.cpu_sample_frac} of the database, all {N} columns), median of {len(r['times'])} queries = "
+                      f"{r['ms_sample']:.2f} ms; respond is linear in K so queries/s is scaled by 1/{r['scale']:.2f}; OpenMP threads={r['threads']} of {os.cpu_count()} cpus",
+        }
+
+    line = {
+        "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, b, K, N),
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * qlen, "d2h_bytes_per_step": Q * rlen,
+                "threads": max(1, min(args.e2e_threads, Q)), "api": "chpir_server_respond (C ABI, pinned host buffers)"},
+        "gpu_launches": 2 * args.steps * Q,  # the timed region and the kernel-only region each launch one respond kernel per query
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+        "setup": setup,
+        "respond_us_per_query_kernel": ms_kernel * 1e3,
+        "parity": parity,
+        "published_reference": {"server_respond_2^20_3wise_ms": {"m8g.8xlarge": 10.06, "m7i.8xlarge": 14.06}, "server_setup_2^20_3wise_s": {"m8g": 577, "m7i": 1282, "g6e(L40S offload)": 25.58}},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=20)
+    ap.add_argument("--arity", type=int, default=3, choices=[3, 4])
+    ap.add_argument("--queries-per-step", type=int, default=16)
+    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--skip-hint", action="store_true", help="make D resident only (no A expansion / hint GEMM) -- development shortcut")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frac", type=int, default=8)
+    ap.add_argument("--ref-sample-frac", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
