@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface declared in include/chalamet_b200.h.
 // No exceptions cross this boundary: every entry point is wrapped in a catch-all and returns a chpir_status.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <new>
@@ -170,37 +171,79 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   if (!o.skip_hint) {
     const size_t need = 8 + size_t(m) * ncols * 4;
     if (!hint_out || hint_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
-    // -- A = generate_from_seed(m, K, seed) on device
-    DevBuf a, scratch, c;
-    if (int rc = a.alloc(size_t(m) * K * 4); rc != CHPIR_OK) return rc;
+    DevBuf scratch, c;
     if (int rc = scratch.alloc(512); rc != CHPIR_OK) return rc;
     if (int rc = c.alloc(size_t(m) * ncols * 4); rc != CHPIR_OK) return rc;
-    EventTimer t_exp, t_gemm;
-    t_exp.start(st);
-    if (int rc = launch_expand(seed, a.as<uint8_t>(), uint64_t(m) * K * 4, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
-    t_exp.stop(st);
-    // -- M = A * D[:, slice]
-    float tc_ms = 0.f;
-    t_gemm.start(st);
-    int rc;
-    if (o.gemm_variant == 1)
-      rc = launch_gemm_simt(a.as<uint32_t>(), d_dev + col0, ld, c.as<uint32_t>(), m, K, ncols, st);
-    else
-      rc = launch_gemm_tc(a.as<uint32_t>(), d_dev + col0, ld, c.as<uint32_t>(), m, K, ncols, b, ctx->sm_count, st, &tc_ms);
-    if (rc != CHPIR_OK) return rc;
-    t_gemm.stop(st);
+    EventTimer t_all;
+    float gemm_ms = 0.f;
+    if (o.gemm_variant == 1) {
+      // debug path: A = generate_from_seed(m, K, seed) as u32 in HBM, then the SIMT u32 GEMM
+      DevBuf a;
+      if (int rc = a.alloc(size_t(m) * K * 4); rc != CHPIR_OK) return rc;
+      EventTimer t_gemm;
+      t_all.start(st);
+      if (int rc = launch_expand(seed, a.as<uint8_t>(), uint64_t(m) * K * 4, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
+      t_gemm.start(st);
+      if (int rc = launch_gemm_simt(a.as<uint32_t>(), d_dev + col0, ld, c.as<uint32_t>(), m, K, ncols, st); rc != CHPIR_OK) return rc;
+      t_gemm.stop(st);
+      t_all.stop(st);
+      CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
+      gemm_ms = t_gemm.ms();
+    } else {
+      // production path: A is squeezed out of the XOF 128 rows at a time, directly as the byte planes the tensor-core
+      // GEMM reads, into a two-buffer ring; each panel is multiplied as soon as it exists.  One stream: the XOF chain is
+      // serial and ~1000x longer than a panel GEMM, so there is nothing to gain from overlapping them.
+      GemmTcB *g = nullptr;
+      if (int rc = gemm_tc_prepare(d_dev + col0, ld, K, ncols, b, ctx->sm_count, st, &g); rc != CHPIR_OK) return rc;
+      struct Guard {
+        GemmTcB *g;
+        std::vector<cudaEvent_t> ev;
+        ~Guard() {
+          for (cudaEvent_t e : ev) cudaEventDestroy(e);
+          gemm_tc_free(g);
+        }
+      } guard{g, {}};
+      const uint32_t panels = (m + 127) / 128;
+      guard.ev.resize(2 * panels, nullptr);
+      for (auto &e : guard.ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+      CHPIR_CUDA(cudaMemsetAsync(c.p, 0, size_t(m) * ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      t_all.start(st);
+      if (int rc = expand_begin(seed, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
+      const uint64_t total_blocks = (uint64_t(m) * K * 4 + 167) / 168;
+      uint64_t blk = 0;
+      for (uint32_t p = 0; p < panels; p++) {
+        const uint32_t r1 = std::min<uint32_t>(m, (p + 1) * 128u);
+        const uint64_t blk_end = std::min<uint64_t>(total_blocks, (uint64_t(r1) * K * 4 + 167) / 168);
+        if (int rc = launch_expand_planes(gemm_tc_ring(g), m, K, gemm_tc_kp(g), scratch.as<uint8_t>(), blk, blk_end - blk, st); rc != CHPIR_OK)
+          return rc;
+        blk = blk_end;
+        cudaEventRecord(guard.ev[2 * p], st);
+        if (int rc = gemm_tc_panel(g, p & 1, r1 - p * 128u, c.as<uint32_t>() + size_t(p) * 128u * ncols, st); rc != CHPIR_OK) return rc;
+        cudaEventRecord(guard.ev[2 * p + 1], st);
+      }
+      t_all.stop(st);
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        set_last_cuda_error(e, "setup: expand + hint GEMM");
+        return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+      }
+      for (uint32_t p = 0; p < panels; p++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, guard.ev[2 * p], guard.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
+      }
+    }
+    const float all_ms = t_all.ms();
     const double t0 = now_s();
     const uint32_t hdr[2] = {m, ncols};
     std::memcpy(hint_out, hdr, 8);
     CHPIR_CUDA(cudaMemcpyAsync(hint_out + 8, c.p, size_t(m) * ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
-    srv->timing.d2h_s = now_s() - t0;  // includes waiting for the kernels; corrected below
-    srv->timing.expand_a_s = t_exp.ms() * 1e-3;
-    srv->timing.gemm_s = t_gemm.ms() * 1e-3;
-    srv->timing.d2h_s -= (srv->timing.expand_a_s + srv->timing.gemm_s);
-    if (srv->timing.d2h_s < 0) srv->timing.d2h_s = 0;
-    srv->last_gemm_ms = tc_ms > 0.f ? tc_ms : t_gemm.ms();
-    srv->last_expand_ms = t_exp.ms();
+    srv->timing.d2h_s = now_s() - t0;
+    srv->timing.gemm_s = gemm_ms * 1e-3;
+    srv->timing.expand_a_s = (all_ms - gemm_ms) * 1e-3;
+    srv->last_gemm_ms = gemm_ms;
+    srv->last_expand_ms = all_ms - gemm_ms;
     if (hint_len) *hint_len = need;
   } else {
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);

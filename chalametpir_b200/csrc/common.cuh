@@ -50,13 +50,29 @@ int launch_respond(const uint8_t *packed, const PackedLayout &L, uint64_t K, con
                    uint32_t *resp_dev, cudaStream_t s);
 
 // TurboSHAKE128(seed) squeezed into out_dev[0 .. total_bytes) (total_bytes % 4 == 0); serial chain on one warp.
+// state_scratch_dev: 512 bytes of device scratch (seed copy + sponge state carried between launches).
 int launch_expand(const uint8_t seed[32], uint8_t *out_dev, uint64_t total_bytes, uint8_t *state_scratch_dev, cudaStream_t s);
+// The same stream written as K-major byte planes into a ring of two 128-row panel buffers ([4][128][kp] each), for XOF
+// blocks [block_begin, block_begin + block_count) of a rows x cols u32 matrix.  expand_begin() first, once.
+int expand_begin(const uint8_t seed[32], uint8_t *state_scratch_dev, cudaStream_t s);
+int launch_expand_planes(uint8_t *ring_dev, uint64_t rows, uint64_t cols, uint64_t kp, uint8_t *state_scratch_dev, uint64_t block_begin,
+                         uint64_t block_count, cudaStream_t s);
 
 // C[m x n] = A[m x k] * B[k x n] mod 2^32, all u32 row-major in device memory (B with leading dimension ldb).
 int launch_gemm_simt(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, cudaStream_t s);
 
-// tcgen05 int8-limb GEMM (gemm_tc.cu).  A: m x k u32 (device), B: k x n u32 with entries < 2^b_bits (device, ld = ldb),
-// C: m x n u32 (ldc = n), overwritten.  workspace is allocated/freed internally.
+// tcgen05 int8-limb GEMM (gemm_tc.cu), one 128-row panel of A at a time.
+//   gemm_tc_prepare: limb-split + transpose B (k x n u32, entries < 2^b_bits, ld = ldb) once, allocate the A panel ring;
+//   gemm_tc_panel:   C_panel[rows x n] += A_panel . B for the panel in ring buffer `buf` (C zeroed by the caller);
+//   gemm_tc_load_panel_u32: fill ring buffer `buf` from u32 rows (when A is not produced by launch_expand_planes).
+struct GemmTcB;
+int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uint32_t b_bits, int sm_count, cudaStream_t s, GemmTcB **out);
+int gemm_tc_panel(const GemmTcB *g, int buf, uint32_t rows, uint32_t *C_panel, cudaStream_t s);
+int gemm_tc_load_panel_u32(const GemmTcB *g, int buf, const uint32_t *A_rows, uint32_t rows, cudaStream_t s);
+uint8_t *gemm_tc_ring(const GemmTcB *g);
+uint64_t gemm_tc_kp(const GemmTcB *g);
+void gemm_tc_free(GemmTcB *g);
+// Whole product, A: m x k u32 (device), C: m x n u32 (ldc = n), overwritten.  Workspace is allocated/freed internally.
 int launch_gemm_tc(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, uint32_t b_bits,
                    int sm_count, cudaStream_t s, float *kernel_ms);
 

@@ -224,11 +224,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-// A[m][k] u32 -> planes[l][m][kp] u8, l = byte index.  One thread per 4 consecutive k.
-__global__ void split_a_limbs(const uint32_t *__restrict__ A, uint32_t m, uint64_t k, uint64_t kp, uint8_t *__restrict__ planes) {
+// A[m][k] u32 -> planes[l][plane_rows][kp] u8 (rows 0..m-1 filled), l = byte index.  One thread per 4 consecutive k.
+__global__ void split_a_limbs(const uint32_t *__restrict__ A, uint32_t m, uint64_t k, uint64_t kp, uint32_t plane_rows,
+                              uint8_t *__restrict__ planes) {
   const uint64_t groups = kp / 4;
   const uint64_t total = uint64_t(m) * groups;
-  const uint64_t plane = uint64_t(m) * kp;
+  const uint64_t plane = uint64_t(plane_rows) * kp;
   for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < total; idx += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t r = idx / groups, g = idx - r * groups;
     uint32_t v[4];
@@ -304,97 +305,154 @@ int make_map(CUtensorMap *map, void *base, uint64_t k, uint64_t kp, uint64_t row
   return r == CUDA_SUCCESS ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
 }
 
-template <int NB>
-int run(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, int sm_count, cudaStream_t s,
-        float *kernel_ms) {
-  const uint64_t kp = (k + 15) / 16 * 16;
-  uint8_t *a8 = nullptr, *b8 = nullptr;
-  CHPIR_CUDA(cudaMalloc(&a8, 4ull * m * kp), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
-  if (cudaMalloc(&b8, uint64_t(NB) * n * kp) != cudaSuccess) {
-    cudaFree(a8);
-    return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-  }
-  int rc = CHPIR_OK;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  do {
-    {
-      const uint64_t total = uint64_t(m) * (kp / 4);
-      const uint64_t want = (total + 255) / 256;
-      split_a_limbs<<<unsigned(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16), 256, 0, s>>>(A, m, k, kp, a8);
-      dim3 g(unsigned((kp + 127) / 128), (n + 31) / 32);
-      split_transpose_b<NB><<<g, 256, 0, s>>>(B, k, n, ldb, kp, b8);
-      if (cudaGetLastError() != cudaSuccess) {
-        rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-        break;
-      }
-    }
-    const uint32_t tiles_m = (m + BM - 1) / BM;
-    const uint32_t tiles_n0 = (n + BN_MAX - 1) / BN_MAX;
-    uint32_t bn = ((n + tiles_n0 - 1) / tiles_n0 + 15) / 16 * 16;
-    if (bn < 16) bn = 16;
-    const uint32_t tiles_n = (n + bn - 1) / bn;
-    const uint32_t kblocks = uint32_t((k + BK - 1) / BK);
-    // split K so that the grid fills whole waves of sm_count CTAs
-    const uint32_t tiles = tiles_m * tiles_n;
-    uint32_t best_splits = 1;
-    double best_eff = 0.0;
-    uint32_t max_splits = kblocks / 8;  // every split keeps >= 8 k-blocks (1024 k) of mainloop per epilogue
-    if (max_splits < 1) max_splits = 1;
-    if (max_splits > 64) max_splits = 64;
-    for (uint32_t sp = 1; sp <= max_splits; sp++) {
-      const uint64_t units = uint64_t(tiles) * sp;
-      const uint64_t waves = (units + sm_count - 1) / sm_count;
-      const double eff = double(units) / double(waves * sm_count);
-      if (eff > best_eff + 0.02) best_eff = eff, best_splits = sp;
-    }
-    uint32_t kbps = (kblocks + best_splits - 1) / best_splits;
-    const uint32_t splits = (kblocks + kbps - 1) / kbps;
+}  // namespace
 
-    CUtensorMap map_a, map_b;
-    if ((rc = make_map(&map_a, a8, k, kp, m, 4, BM)) != CHPIR_OK) break;
-    if ((rc = make_map(&map_b, b8, k, kp, n, NB, bn)) != CHPIR_OK) break;
-    if (cudaMemsetAsync(C, 0, uint64_t(m) * n * 4, s) != cudaSuccess) {
-      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+// Everything the hint GEMM needs that depends only on the B operand (D): its K-major limb planes, the TMA map over
+// them and the launch geometry.  Built once per setup, then used for every 128-row panel of A.
+struct GemmTcB {
+  uint8_t *b8 = nullptr;
+  uint8_t *a_ring = nullptr;  // two panel buffers [4][128][kp]
+  uint64_t k = 0, kp = 0;
+  uint32_t n = 0, nb = 0, bn = 0, tiles_n = 0, kblocks = 0, kbps = 0, splits = 0;
+  CUtensorMap map_b{}, map_a[2]{};
+  ~GemmTcB() {
+    if (b8) cudaFree(b8);
+    if (a_ring) cudaFree(a_ring);
+  }
+};
+
+uint64_t gemm_tc_panel_bytes(const GemmTcB *g) { return 4ull * BM * g->kp; }
+uint8_t *gemm_tc_ring(const GemmTcB *g) { return g->a_ring; }
+uint64_t gemm_tc_kp(const GemmTcB *g) { return g->kp; }
+void gemm_tc_free(GemmTcB *g) { delete g; }
+
+int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uint32_t b_bits, int sm_count, cudaStream_t s, GemmTcB **out) {
+  *out = nullptr;
+  if (b_bits == 0 || b_bits > 16) return CHPIR_ERR_INVALID_ARGUMENT;  // two byte limbs cover every legal element width (4..14)
+  if (k > 0x7fffffffull - BK) return CHPIR_ERR_INVALID_ARGUMENT;      // TMA coordinates are int32
+  GemmTcB *g = new GemmTcB();
+  g->k = k;
+  g->kp = (k + 15) / 16 * 16;
+  g->n = n;
+  g->nb = b_bits <= 8 ? 1 : 2;
+  int rc = CHPIR_OK;
+  do {
+    if (cudaMalloc(&g->b8, uint64_t(g->nb) * n * g->kp) != cudaSuccess || cudaMalloc(&g->a_ring, 2 * gemm_tc_panel_bytes(g)) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_ALLOCATION_FAILED;
       break;
     }
-    constexpr int smem_bytes = STAGES * (4 * A_TILE + NB * B_TILE) + 1024;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
-      rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-      break;
-    }
-    cudaEventRecord(e0, s);
-    gemm_tc_kernel<NB><<<dim3(tiles, splits), kThreads, smem_bytes, s>>>(map_a, map_b, C, m, n, tiles_n, bn, kblocks, kbps);
-    cudaEventRecord(e1, s);
+    dim3 grid(unsigned((g->kp + 127) / 128), (n + 31) / 32);
+    if (g->nb == 1)
+      split_transpose_b<1><<<grid, 256, 0, s>>>(B, k, n, ldb, g->kp, g->b8);
+    else
+      split_transpose_b<2><<<grid, 256, 0, s>>>(B, k, n, ldb, g->kp, g->b8);
     if (cudaGetLastError() != cudaSuccess) {
       rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
       break;
     }
+    const uint32_t tiles_n0 = (n + BN_MAX - 1) / BN_MAX;
+    uint32_t bn = ((n + tiles_n0 - 1) / tiles_n0 + 15) / 16 * 16;
+    if (bn < 16) bn = 16;
+    g->bn = bn;
+    g->tiles_n = (n + bn - 1) / bn;
+    g->kblocks = uint32_t((k + BK - 1) / BK);
+    // one launch = one 128-row panel: split K so that tiles_n * splits fills whole waves of sm_count CTAs
+    uint32_t best_splits = 1;
+    double best_eff = 0.0;
+    uint32_t max_splits = g->kblocks / 8;  // every split keeps >= 8 k-blocks (1024 k) of mainloop per epilogue
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 148) max_splits = 148;
+    for (uint32_t sp = 1; sp <= max_splits; sp++) {
+      const uint64_t units = uint64_t(g->tiles_n) * sp;
+      const uint64_t waves = (units + sm_count - 1) / sm_count;
+      const double eff = double(units) / double(waves * sm_count);
+      if (eff > best_eff + 0.02) best_eff = eff, best_splits = sp;
+    }
+    g->kbps = (g->kblocks + best_splits - 1) / best_splits;
+    g->splits = (g->kblocks + g->kbps - 1) / g->kbps;
+    if ((rc = make_map(&g->map_b, g->b8, k, g->kp, n, g->nb, bn)) != CHPIR_OK) break;
+    for (int i = 0; i < 2; i++)
+      if ((rc = make_map(&g->map_a[i], g->a_ring + i * gemm_tc_panel_bytes(g), k, g->kp, BM, 4, BM)) != CHPIR_OK) break;
+    if (rc != CHPIR_OK) break;
+    constexpr int smem1 = STAGES * (4 * A_TILE + 1 * B_TILE) + 1024, smem2 = STAGES * (4 * A_TILE + 2 * B_TILE) + 1024;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+      break;
+    }
+  } while (false);
+  if (rc != CHPIR_OK) {
+    if (rc != CHPIR_ERR_INVALID_ARGUMENT) set_last_cuda_error(cudaGetLastError(), "gemm_tc_prepare");
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return CHPIR_OK;
+}
+
+// C_panel[rows x n] += A_panel . B  for the panel held in ring buffer `buf` (rows <= 128).  C must have been zeroed.
+int gemm_tc_panel(const GemmTcB *g, int buf, uint32_t rows, uint32_t *C_panel, cudaStream_t s) {
+  const dim3 grid(g->tiles_n, g->splits);
+  if (g->nb == 1) {
+    constexpr int smem_bytes = STAGES * (4 * A_TILE + 1 * B_TILE) + 1024;
+    gemm_tc_kernel<1><<<grid, kThreads, smem_bytes, s>>>(g->map_a[buf], g->map_b, C_panel, rows, g->n, g->tiles_n, g->bn, g->kblocks, g->kbps);
+  } else {
+    constexpr int smem_bytes = STAGES * (4 * A_TILE + 2 * B_TILE) + 1024;
+    gemm_tc_kernel<2><<<grid, kThreads, smem_bytes, s>>>(g->map_a[buf], g->map_b, C_panel, rows, g->n, g->tiles_n, g->bn, g->kblocks, g->kbps);
+  }
+  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+// u32 rows [row0, row0 + rows) of A (row-major, k columns) -> limb planes of ring buffer `buf`.
+int gemm_tc_load_panel_u32(const GemmTcB *g, int buf, const uint32_t *A_rows, uint32_t rows, cudaStream_t s) {
+  const uint64_t total = uint64_t(rows) * (g->kp / 4);
+  const uint64_t want = (total + 255) / 256;
+  split_a_limbs<<<unsigned(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16), 256, 0, s>>>(A_rows, rows, g->k, g->kp, BM,
+                                                                                             g->a_ring + buf * gemm_tc_panel_bytes(g));
+  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+// Whole product for operands already in device memory as u32 (chpir_matmul and the debug paths).
+int launch_gemm_tc(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, uint32_t b_bits,
+                   int sm_count, cudaStream_t s, float *kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0.f;
+  GemmTcB *g = nullptr;
+  if (int rc = gemm_tc_prepare(B, ldb, k, n, b_bits, sm_count, s, &g); rc != CHPIR_OK) return rc;
+  int rc = CHPIR_OK;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float total_ms = 0.f;
+  do {
+    if (cudaMemsetAsync(C, 0, uint64_t(m) * n * 4, s) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+      break;
+    }
+    for (uint32_t r0 = 0, p = 0; r0 < m && rc == CHPIR_OK; r0 += BM, p++) {
+      const uint32_t rows = m - r0 < uint32_t(BM) ? m - r0 : uint32_t(BM);
+      if ((rc = gemm_tc_load_panel_u32(g, p & 1, A + uint64_t(r0) * k, rows, s)) != CHPIR_OK) break;
+      cudaEventRecord(e0, s);
+      if ((rc = gemm_tc_panel(g, p & 1, rows, C + uint64_t(r0) * n, s)) != CHPIR_OK) break;
+      cudaEventRecord(e1, s);
+      if (kernel_ms) {
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) total_ms += ms;
+      }
+    }
+    if (rc != CHPIR_OK) break;
     cudaError_t e = cudaStreamSynchronize(s);  // the planes are freed below
     if (e != cudaSuccess) {
       set_last_cuda_error(e, "gemm_tc_kernel");
       rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
-      break;
     }
-    if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
   } while (false);
   if (rc != CHPIR_OK && rc != CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED) set_last_cuda_error(cudaGetLastError(), "gemm_tc");
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFree(a8);
-  cudaFree(b8);
+  gemm_tc_free(g);
+  if (kernel_ms) *kernel_ms = total_ms;
   return rc;
-}
-
-}  // namespace
-
-int launch_gemm_tc(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, uint32_t b_bits,
-                   int sm_count, cudaStream_t s, float *kernel_ms) {
-  if (kernel_ms) *kernel_ms = 0.f;
-  if (b_bits == 0 || b_bits > 16) return CHPIR_ERR_INVALID_ARGUMENT;  // two byte limbs cover every legal element width (4..14)
-  if (k > 0x7fffffffull - BK) return CHPIR_ERR_INVALID_ARGUMENT;      // TMA coordinates are int32
-  return b_bits <= 8 ? run<1>(A, B, ldb, C, m, k, n, sm_count, s, kernel_ms) : run<2>(A, B, ldb, C, m, k, n, sm_count, s, kernel_ms);
 }
 
 }  // namespace chpir
