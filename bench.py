@@ -411,7 +411,7 @@ def run_b200(args):
     ref_layout = 4 * nc * ((K + 2) // 3 if b in (9, 10) else (K + 1) // 2 if b >= 11 else (K + 3) // 4) + 4 * K + 4 * nc
     achieved = streamed / (ms_kernel * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "respond_kernel<9> (streaming u32 GEMV over K-major bit-packed D)", "achieved": achieved, "peak": pk["hbm_gbs"],
+        "bound": "hbm", "kernel": "respond_ring_kernel<9,4> (persistent streaming u32 GEMV over K-major bit-packed D, cp.async.bulk smem ring)", "achieved": achieved, "peak": pk["hbm_gbs"],
         "peak_source": pk["source"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
         "bytes_per_launch": streamed, "bytes_per_launch_reference_layout": ref_layout, "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9,
         "us_per_launch": ms_kernel * 1e3,

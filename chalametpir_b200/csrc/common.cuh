@@ -39,10 +39,19 @@ PackedLayout make_layout(uint32_t b, uint32_t ncols);
 int launch_pack(const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col_begin, const PackedLayout &L, uint8_t *packed,
                 cudaStream_t s);
 struct RespondPlan {
+  // register-pipelined kernel (respond_kernel): generic shapes
   uint32_t threads;         // block size = rows_per_iter * units (+ idle lanes)
   uint32_t rows_per_iter;   // k-rows one block covers per loop iteration
   uint32_t grid;            // blocks (K split)
   uint64_t rows_per_block;  // multiple of rows_per_iter
+  // bulk-copy ring kernel (respond_ring_kernel): the production path whenever a packed row fits one CTA
+  uint32_t ring;            // 1 = use it
+  uint32_t ring_R;          // row lanes (multiple of 4)
+  uint32_t ring_rpt;        // rows per thread per stage (1, 2 or 4)
+  uint32_t ring_stages;
+  uint32_t ring_grid, ring_block;
+  uint32_t ring_stage_bytes, ring_smem_bytes;
+  uint64_t ring_rows_per_cta;
 };
 RespondPlan plan_respond(const PackedLayout &L, uint64_t K, int sm_count);
 // resp must be zeroed by the caller on the same stream (the kernel accumulates with atomics, exact mod 2^32).

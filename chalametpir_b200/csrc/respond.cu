@@ -14,6 +14,9 @@
 // 3-per-u32 layout), so one query streams 1.27 GB instead of 1.48 GB at 2^20 entries.
 // Partial sums of different K-ranges are combined with u32 atomics: addition mod 2^32 is associative and
 // commutative, so the result is bit-identical regardless of order.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace chpir {
@@ -162,6 +165,156 @@ __global__ void __launch_bounds__(kMaxThreads) respond_kernel(const uint4 *__res
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Production kernel: persistent CTAs, one per SM, each streaming a contiguous K-range of the packed matrix through a
+// shared-memory ring filled by the bulk-copy engine (cp.async.bulk + mbarrier complete_tx), so that the bytes in
+// flight per SM are bounded by shared memory (~190 KB) instead of by registers.  One producer lane issues the copies
+// (matrix rows and the matching slice of q); the consumer threads own (unit, row-lane) pairs as in respond_kernel and
+// read 16-byte vectors from shared memory, conflict-free.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+constexpr int kRingMaxThreads = 1024;
+
+template <int B, int RPT>
+__global__ void __launch_bounds__(kRingMaxThreads, 1)
+    respond_ring_kernel(const uint8_t *__restrict__ packed, const uint32_t *__restrict__ q, uint32_t *__restrict__ resp, uint64_t K, uint32_t units,
+                        uint32_t R, uint32_t stages, uint32_t stage_bytes, uint64_t rows_per_cta, uint32_t ncols, uint32_t q_bulk) {
+  constexpr int FPW = 64 / B;
+  extern __shared__ __align__(128) uint8_t ring[];
+  const uint32_t S = R * RPT;  // rows per stage
+  const uint32_t pitch = units * 16;
+  const uint32_t d_bytes = S * pitch;
+  const uint32_t ring_base = smem_addr(ring);
+  const uint32_t bar_base = ring_base + stages * stage_bytes;  // full[stages], empty[stages]
+  const uint32_t t = threadIdx.x;
+  const uint32_t n_cons = R * units;
+  const uint32_t cons_warps = (n_cons + 31) / 32;
+  const uint32_t warp = t / 32, lane = t % 32;
+
+  const uint64_t k0 = uint64_t(blockIdx.x) * rows_per_cta;
+  uint64_t k1 = k0 + rows_per_cta;
+  if (k1 > K) k1 = K;
+  const uint32_t n_chunks = k0 < k1 ? uint32_t((k1 - k0 + S - 1) / S) : 0u;
+
+  if (t == 0) {
+    for (uint32_t s = 0; s < stages; s++) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (stages + s), cons_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t acc[2 * FPW];
+#pragma unroll
+  for (int i = 0; i < 2 * FPW; i++) acc[i] = 0;
+  const uint32_t u = t % units, r = t / units;
+  const bool active = t < n_cons;
+
+  if (warp == cons_warps) {
+    // ------------------------------------------------------------------ producer (one lane)
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t s = c % stages, ph = (c / stages) & 1;
+        mbar_wait(bar_base + 8 * (stages + s), ph ^ 1);
+        const uint64_t kc = k0 + uint64_t(c) * S;
+        const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
+        const bool qb = q_bulk && rows == S;
+        const uint32_t full = bar_base + 8 * s;
+        mbar_expect_tx(full, rows * pitch + (qb ? S * 4 : 0));
+        const uint32_t dst = ring_base + s * stage_bytes;
+        bulk_g2s(dst, packed + kc * pitch, rows * pitch, full, policy);
+        if (qb) bulk_g2s(dst + d_bytes, q + kc, S * 4, full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers
+    for (uint32_t c = 0; c < n_chunks; c++) {
+      const uint32_t s = c % stages, ph = (c / stages) & 1;
+      const uint64_t kc = k0 + uint64_t(c) * S;
+      const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
+      const bool qb = q_bulk && rows == S;
+      mbar_wait(bar_base + 8 * s, ph);
+      if (active) {
+        const uint32_t base = ring_base + s * stage_bytes + u * 16 + r * pitch;
+        const uint32_t qbase = ring_base + s * stage_bytes + d_bytes + r * 4;
+        uint4 w[RPT];
+        uint32_t qk[RPT];
+        // shared-memory reads are unconditional (rows past the end of a partial chunk hold stale bytes and are
+        // multiplied by zero), so that all RPT loads of a stage are in flight together
+#pragma unroll
+        for (int j = 0; j < RPT; j++)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w[j].x), "=r"(w[j].y), "=r"(w[j].z), "=r"(w[j].w)
+                       : "r"(base + j * R * pitch));
+        if (qb) {
+#pragma unroll
+          for (int j = 0; j < RPT; j++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qk[j]) : "r"(qbase + j * R * 4));
+        } else {
+#pragma unroll
+          for (int j = 0; j < RPT; j++) {
+            const uint32_t row = r + j * R;
+            qk[j] = row < rows ? __ldg(q + kc + row) : 0u;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+          fma_fields<B>(w[j].x, w[j].y, qk[j], acc);
+          fma_fields<B>(w[j].z, w[j].w, qk[j], acc + FPW);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * (stages + s));
+    }
+    unmask_fields<B>(acc);
+    unmask_fields<B>(acc + FPW);
+  }
+
+  // fold the R row lanes of each unit (the ring is free now), then one atomic per (CTA, column)
+  __syncthreads();
+  uint32_t *red = reinterpret_cast<uint32_t *>(ring);
+#pragma unroll
+  for (int i = 0; i < 2 * FPW; i++) {
+    if (t < kRingMaxThreads) red[t] = active ? acc[i] : 0u;
+    __syncthreads();
+    if (active && r == 0 && n_chunks > 0) {
+      uint32_t sum = 0;
+      for (uint32_t rr = 0; rr < R; rr++) sum += red[rr * units + u];
+      const uint32_t col = (2 * u + i / FPW) * FPW + (i % FPW);
+      if (col < ncols && sum != 0) atomicAdd(resp + col, sum);
+    }
+    __syncthreads();
+  }
+}
+
 template <int B>
 __global__ void pack_kernel(const uint32_t *__restrict__ d, uint64_t K, uint32_t ld, uint32_t col_begin, uint32_t ncols, uint32_t units,
                             uint4 *__restrict__ packed) {
@@ -194,6 +347,27 @@ int respond_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, c
   respond_kernel<B><<<grid, block, 0, s>>>(reinterpret_cast<const uint4 *>(packed), q, resp, K, L.units, cu, P.rows_per_iter, L.ncols,
                                            P.rows_per_block);
   return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+template <int B>
+int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q, uint32_t *resp,
+                          cudaStream_t s) {
+  const uint32_t q_bulk = (reinterpret_cast<uintptr_t>(q) % 16 == 0) ? 1u : 0u;
+  auto launch = [&](auto kernel) -> int {
+    static thread_local const void *configured = nullptr;  // per instantiation (the lambda is instantiated per kernel type)
+    if (configured != reinterpret_cast<const void *>(kernel)) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+      configured = reinterpret_cast<const void *>(kernel);
+    }
+    kernel<<<P.ring_grid, P.ring_block, P.ring_smem_bytes, s>>>(packed, q, resp, K, L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes,
+                                                                P.ring_rows_per_cta, L.ncols, q_bulk);
+    return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+  };
+  switch (P.ring_rpt) {
+    case 1: return launch(respond_ring_kernel<B, 1>);
+    case 2: return launch(respond_ring_kernel<B, 2>);
+    default: return launch(respond_ring_kernel<B, 4>);
+  }
 }
 
 template <int B>
@@ -234,6 +408,51 @@ int occupancy_of(int threads) {
     default: return CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH; \
   }
 
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+  const char *v = std::getenv(name);
+  return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
+// Geometry of the bulk-copy ring kernel.  Tunables can be overridden from the environment for experiments:
+// CHPIR_RESPOND_RING=0 disables it, CHPIR_RING_R / CHPIR_RING_RPT / CHPIR_RING_STAGES / CHPIR_RING_CTAS_PER_SM_X100.
+static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPlan *P) {
+  P->ring = 0;
+  if (env_u32("CHPIR_RESPOND_RING", 1) == 0) return;
+  const uint32_t units = L.units;
+  if (units == 0 || 4 * units > uint32_t(kRingMaxThreads) - 32) return;  // a row must fit the consumer threads of one CTA
+  uint32_t R = env_u32("CHPIR_RING_R", 0);
+  if (R == 0) {
+    R = (640 / units) & ~3u;
+    if (R < 4) R = 4;
+    if (R > 64) R = 64;
+  }
+  R = (R + 3) & ~3u;
+  while (R > 4 && R * units > uint32_t(kRingMaxThreads) - 32) R -= 4;
+  uint32_t rpt = env_u32("CHPIR_RING_RPT", 4);
+  if (rpt != 1 && rpt != 2) rpt = 4;
+  const uint32_t pitch = units * 16;
+  const uint32_t budget = 200 * 1024;
+  while (rpt > 1 && 3 * R * rpt * (pitch + 4) > budget) rpt /= 2;
+  const uint32_t S = R * rpt;
+  const uint32_t stage_bytes = S * (pitch + 4);
+  uint32_t stages = budget / stage_bytes;
+  const uint32_t want = env_u32("CHPIR_RING_STAGES", 0);
+  if (want && want < stages) stages = want;
+  if (stages > 32) stages = 32;
+  if (stages < 2) return;
+  P->ring = 1;
+  P->ring_R = R;
+  P->ring_rpt = rpt;
+  P->ring_stages = stages;
+  P->ring_stage_bytes = stage_bytes;
+  P->ring_smem_bytes = std::max<uint32_t>(stages * stage_bytes + 16 * stages, 4096 + 64);
+  P->ring_grid = uint32_t(sm_count);
+  const uint64_t per = (K + P->ring_grid - 1) / P->ring_grid;
+  P->ring_rows_per_cta = (per + S - 1) / S * S;
+  if (P->ring_rows_per_cta == 0) P->ring_rows_per_cta = S;
+  P->ring_block = ((R * units + 31) / 32 + 1) * 32;
+}
+
 RespondPlan plan_respond(const PackedLayout &L, uint64_t K, int sm_count) {
   RespondPlan P{};
   // column chunking only when one row has more units than a block has threads
@@ -268,11 +487,17 @@ RespondPlan plan_respond(const PackedLayout &L, uint64_t K, int sm_count) {
   P.rows_per_block = rpb;
   P.grid = uint32_t((K + rpb - 1) / rpb);
   if (P.grid == 0) P.grid = 1;
+  plan_ring(L, K, sm_count, &P);
   return P;
 }
 
 int launch_respond(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q_dev, uint32_t *resp_dev,
                    cudaStream_t s) {
+  if (P.ring) {
+#define CHPIR_RING(B) respond_ring_dispatch<B>(packed, L, K, P, q_dev, resp_dev, s)
+    CHPIR_DISPATCH_B(L.b, CHPIR_RING)
+#undef CHPIR_RING
+  }
 #define CHPIR_RESP(B) respond_dispatch<B>(packed, L, K, P, q_dev, resp_dev, s)
   CHPIR_DISPATCH_B(L.b, CHPIR_RESP)
 #undef CHPIR_RESP
