@@ -74,9 +74,9 @@ def peaks():
 
 
 def slice_of(N: int, rank: int, world: int):
-    base, rem = divmod(N, world)
-    c0 = rank * base + min(rank, rem)
-    return c0, base + (1 if rank < rem else 0)
+    from chalametpir_b200.sharding import slice_of as f
+
+    return f(N, rank, world)
 
 
 def gen_d_slice(torch, K: int, c0: int, nc: int, b: int, device, salt: int = 0x5EED):
@@ -297,17 +297,38 @@ def run_b200(args):
     resp_dev = torch.zeros((Q, nc), dtype=torch.int32, device=dev)
     counts = [slice_of(N, r, world)[1] for r in range(world)]
     pad = max(counts)
-    gather_buf = torch.zeros((world, Q, pad), dtype=torch.int32, device=dev) if world > 1 else None
-    send_buf = torch.zeros((Q, pad), dtype=torch.int32, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        # double-buffered so that the broadcast of batch i+1 and the gather of batch i-1 overlap the GEMVs of batch i
+        q_bufs = [q_dev, q_dev.clone()]
+        send_bufs = [torch.zeros((Q, pad), dtype=torch.int32, device=dev) for _ in range(2)]
+        gather_bufs = [torch.zeros((world, Q, pad), dtype=torch.int32, device=dev) for _ in range(2)]
 
-    def step_device(bcast: bool = True):
-        if world > 1 and bcast:
-            dist.broadcast(q_dev, 0)
-        srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
-        if world > 1:
-            send_buf[:, :nc] = resp_dev
-            dist.all_gather_into_tensor(gather_buf.view(-1), send_buf.view(-1))
+    def run_steps(n):
+        """n steps; per step: the query batch reaches every rank (broadcast from rank 0), every rank answers for its
+        column slice, the slices are gathered on every rank (rank 0 is the one that needs them)."""
+        if world == 1:
+            for _ in range(n):
+                srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
+            return
+        bw = dist.broadcast(q_bufs[0], 0, async_op=True)
+        gw = [None, None]
+        for i in range(n):
+            p = i & 1
+            bw.wait()
+            if i + 1 < n:
+                bw = dist.broadcast(q_bufs[p ^ 1], 0, async_op=True)
+            srv.respond_device(q_bufs[p].data_ptr(), Q, resp_dev.data_ptr(), stream)
+            if gw[p] is not None:
+                gw[p].wait()
+            send_bufs[p][:, :nc] = resp_dev
+            gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), async_op=True)
+        for w in gw:
+            if w is not None:
+                w.wait()
+
+    def step_device():
+        run_steps(1)
 
     step_device()
     torch.cuda.synchronize()
@@ -320,8 +341,7 @@ def run_b200(args):
     assert parity["respond_sampled_columns"], "respond differs from the exact dot product on sampled columns"
 
     # ---------------- timed region: K steps, device-resident
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    run_steps(max(args.warmup, 3))
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -329,8 +349,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        step_device()
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -380,11 +399,10 @@ def run_b200(args):
         if errs:
             raise errs[0]
         if world > 1:
-            r_dev = torch.zeros((Q, pad), dtype=torch.int32, device=dev)
-            r_dev[:, :nc] = r_host[:, 8:].view(torch.int32).reshape(Q, nc).to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gather_buf.view(-1), r_dev.view(-1))
+            send_bufs[0][:, :nc] = r_host[:, 8:].view(torch.int32).reshape(Q, nc).to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(gather_bufs[0].view(-1), send_bufs[0].view(-1))
             if rank == 0:
-                gather_buf.cpu()
+                gather_bufs[0].cpu()
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -407,14 +425,14 @@ def run_b200(args):
 
     # ---------------- roofline of the dominant kernel
     pk = peaks()
-    streamed = srv.packed_bytes + 4 * K + 4 * nc  # bytes one launch on this rank must move: resident packed slice + query + response
+    streamed = srv.packed_bytes + 4 * K + 4 * nc  # bytes one query on this rank must move: resident packed slice + query + response
     ref_layout = 4 * nc * ((K + 2) // 3 if b in (9, 10) else (K + 1) // 2 if b >= 11 else (K + 3) // 4) + 4 * K + 4 * nc
     achieved = streamed / (ms_kernel * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "respond_ring_kernel<9,4> (persistent streaming u32 GEMV over K-major bit-packed D, cp.async.bulk smem ring)", "achieved": achieved, "peak": pk["hbm_gbs"],
         "peak_source": pk["source"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
-        "bytes_per_launch": streamed, "bytes_per_launch_reference_layout": ref_layout, "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9,
-        "us_per_launch": ms_kernel * 1e3,
+        "queries_per_launch": Q, "bytes_per_launch": Q * streamed, "bytes_per_query": streamed, "bytes_per_query_reference_layout": ref_layout,
+        "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9, "us_per_launch": ms_kernel * 1e3 * Q,
     }
     prof = os.path.join(ROOT, "profiles", "respond_traffic.json")
     if os.path.exists(prof):
@@ -444,7 +462,7 @@ def run_b200(args):
         "config": workload_config(args, b, K, N),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * qlen, "d2h_bytes_per_step": Q * rlen,
                 "threads": max(1, min(args.e2e_threads, Q)), "api": "chpir_server_respond (C ABI, pinned host buffers)"},
-        "gpu_launches": 2 * args.steps * Q,  # the timed region and the kernel-only region each launch one respond kernel per query
+        "gpu_launches": 2 * args.steps,  # the timed region and the kernel-only region each launch one respond kernel (grid.y = query) per step
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,

@@ -90,6 +90,11 @@ struct chpir_server {
   std::mutex pool_mu;
   std::vector<RespondSlot *> free_slots;
   std::vector<RespondSlot *> all_slots;
+  // chpir_server_respond_batch: one batch in flight per server, buffers grown on demand
+  std::mutex batch_mu;
+  cudaStream_t batch_stream = nullptr;
+  uint32_t *batch_q = nullptr, *batch_resp = nullptr, *batch_h_resp = nullptr;
+  uint32_t batch_cap = 0;
 
   ~chpir_server() {
     if (ctx) cudaSetDevice(ctx->device);
@@ -103,7 +108,31 @@ struct chpir_server {
       if (s->stream) cudaStreamDestroy(s->stream);
       delete s;
     }
+    if (batch_stream) {
+      cudaStreamSynchronize(batch_stream);
+      cudaStreamDestroy(batch_stream);
+    }
+    if (batch_q) cudaFree(batch_q);
+    if (batch_resp) cudaFree(batch_resp);
+    if (batch_h_resp) cudaFreeHost(batch_h_resp);
     if (d_packed) cudaFree(d_packed);
+  }
+
+  int reserve_batch(uint32_t nq) {
+    if (!batch_stream && cudaStreamCreateWithFlags(&batch_stream, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    if (nq <= batch_cap) return CHPIR_OK;
+    if (batch_q) cudaFree(batch_q);
+    if (batch_resp) cudaFree(batch_resp);
+    if (batch_h_resp) cudaFreeHost(batch_h_resp);
+    batch_q = batch_resp = batch_h_resp = nullptr;
+    batch_cap = 0;
+    if (cudaMalloc(&batch_q, size_t(nq) * K * 4) != cudaSuccess || cudaMalloc(&batch_resp, size_t(nq) * ncols * 4) != cudaSuccess ||
+        cudaMallocHost(&batch_h_resp, size_t(nq) * ncols * 4) != cudaSuccess) {
+      set_last_cuda_error(cudaGetLastError(), "respond batch allocation");
+      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    }
+    batch_cap = nq;
+    return CHPIR_OK;
   }
 
   int acquire(RespondSlot **out) {
@@ -525,7 +554,7 @@ int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_l
       break;
     }
     cudaEventRecord(s->e0, s->stream);
-    rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, s->d_q, s->d_resp, s->stream);
+    rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, s->d_q, s->d_resp, 1, s->stream);
     if (rc != CHPIR_OK) break;
     cudaEventRecord(s->e1, s->stream);
     if (cudaMemcpyAsync(s->h_resp, s->d_resp, size_t(srv->ncols) * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) {
@@ -559,10 +588,27 @@ int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries,
   if (resp_stride < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
   for (uint32_t i = 0; i < nq; i++)
     if (int rc = validate_query(srv, queries[i], query_lens[i]); rc != CHPIR_OK) return rc;
+  if (nq == 0) return CHPIR_OK;
+  CHPIR_CUDA(cudaSetDevice(srv->ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  std::lock_guard<std::mutex> g(srv->batch_mu);
+  if (int rc = srv->reserve_batch(nq); rc != CHPIR_OK) return rc;
+  cudaStream_t st = srv->batch_stream;
+  // all uploads, one launch over the whole batch (grid.y = query), one download
+  for (uint32_t i = 0; i < nq; i++)
+    CHPIR_CUDA(cudaMemcpyAsync(srv->batch_q + size_t(i) * srv->K, queries[i] + 8, srv->K * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemsetAsync(srv->batch_resp, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  if (int rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, srv->batch_q, srv->batch_resp, nq, st); rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemcpyAsync(srv->batch_h_resp, srv->batch_resp, size_t(nq) * srv->ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "respond batch");
+    return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+  }
+  const uint32_t hdr[2] = {1u, srv->ncols};
   for (uint32_t i = 0; i < nq; i++) {
-    size_t len = 0;
-    if (int rc = chpir_server_respond(srv, queries[i], query_lens[i], resp_out + size_t(i) * resp_stride, resp_stride, &len); rc != CHPIR_OK)
-      return rc;
+    uint8_t *o = resp_out + size_t(i) * resp_stride;
+    std::memcpy(o, hdr, 8);
+    std::memcpy(o + 8, srv->batch_h_resp + size_t(i) * srv->ncols, size_t(srv->ncols) * 4);
   }
   return CHPIR_OK;
   CHPIR_GUARD_END
@@ -573,12 +619,7 @@ int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uin
   if (!srv || !q_device || !resp_device) return CHPIR_ERR_INVALID_ARGUMENT;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL is the CUDA default stream, as for any launch
   CHPIR_CUDA(cudaMemsetAsync(resp_device, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  for (uint32_t i = 0; i < nq; i++)
-    if (int rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, q_device + uint64_t(i) * srv->K,
-                                resp_device + uint64_t(i) * srv->ncols, st);
-        rc != CHPIR_OK)
-      return rc;
-  return CHPIR_OK;
+  return launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, q_device, resp_device, nq, st);
   CHPIR_GUARD_END
 }
 

@@ -54,9 +54,10 @@ struct RespondPlan {
   uint64_t ring_rows_per_cta;
 };
 RespondPlan plan_respond(const PackedLayout &L, uint64_t K, int sm_count);
-// resp must be zeroed by the caller on the same stream (the kernel accumulates with atomics, exact mod 2^32).
+// nq queries (q_dev: nq x K, resp_dev: nq x ncols).  resp must be zeroed by the caller on the same stream (the kernel
+// accumulates with atomics, exact mod 2^32).
 int launch_respond(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q_dev,
-                   uint32_t *resp_dev, cudaStream_t s);
+                   uint32_t *resp_dev, uint32_t nq, cudaStream_t s);
 
 // TurboSHAKE128(seed) squeezed into out_dev[0 .. total_bytes) (total_bytes % 4 == 0); serial chain on one warp.
 // state_scratch_dev: 512 bytes of device scratch (seed copy + sponge state carried between launches).

@@ -216,6 +216,9 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
   const uint32_t cons_warps = (n_cons + 31) / 32;
   const uint32_t warp = t / 32, lane = t % 32;
 
+  // blockIdx.y = query of a batch (q: nq x K, resp: nq x ncols); the CTAs of consecutive queries overlap head to tail
+  q += uint64_t(blockIdx.y) * K;
+  resp += uint64_t(blockIdx.y) * ncols;
   const uint64_t k0 = uint64_t(blockIdx.x) * rows_per_cta;
   uint64_t k1 = k0 + rows_per_cta;
   if (k1 > K) k1 = K;
@@ -351,15 +354,16 @@ int respond_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, c
 
 template <int B>
 int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q, uint32_t *resp,
-                          cudaStream_t s) {
-  const uint32_t q_bulk = (reinterpret_cast<uintptr_t>(q) % 16 == 0) ? 1u : 0u;
+                          uint32_t nq, cudaStream_t s) {
+  // bulk copies of q need 16-byte aligned sources for every query of the batch
+  const uint32_t q_bulk = (reinterpret_cast<uintptr_t>(q) % 16 == 0 && (nq == 1 || (K * 4) % 16 == 0)) ? 1u : 0u;
   auto launch = [&](auto kernel) -> int {
     static thread_local const void *configured = nullptr;  // per instantiation (the lambda is instantiated per kernel type)
     if (configured != reinterpret_cast<const void *>(kernel)) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
       configured = reinterpret_cast<const void *>(kernel);
     }
-    kernel<<<P.ring_grid, P.ring_block, P.ring_smem_bytes, s>>>(packed, q, resp, K, L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes,
+    kernel<<<dim3(P.ring_grid, nq), P.ring_block, P.ring_smem_bytes, s>>>(packed, q, resp, K, L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes,
                                                                 P.ring_rows_per_cta, L.ncols, q_bulk);
     return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   };
@@ -491,16 +495,24 @@ RespondPlan plan_respond(const PackedLayout &L, uint64_t K, int sm_count) {
   return P;
 }
 
-int launch_respond(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q_dev, uint32_t *resp_dev,
-                   cudaStream_t s) {
-  if (P.ring) {
-#define CHPIR_RING(B) respond_ring_dispatch<B>(packed, L, K, P, q_dev, resp_dev, s)
-    CHPIR_DISPATCH_B(L.b, CHPIR_RING)
-#undef CHPIR_RING
-  }
+static int launch_respond_one(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q_dev,
+                              uint32_t *resp_dev, cudaStream_t s) {
 #define CHPIR_RESP(B) respond_dispatch<B>(packed, L, K, P, q_dev, resp_dev, s)
   CHPIR_DISPATCH_B(L.b, CHPIR_RESP)
 #undef CHPIR_RESP
+}
+
+int launch_respond(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q_dev, uint32_t *resp_dev,
+                   uint32_t nq, cudaStream_t s) {
+  if (nq == 0) return CHPIR_OK;
+  if (P.ring && nq <= 65535) {
+#define CHPIR_RING(B) respond_ring_dispatch<B>(packed, L, K, P, q_dev, resp_dev, nq, s)
+    CHPIR_DISPATCH_B(L.b, CHPIR_RING)
+#undef CHPIR_RING
+  }
+  for (uint32_t i = 0; i < nq; i++)
+    if (int rc = launch_respond_one(packed, L, K, P, q_dev + uint64_t(i) * K, resp_dev + uint64_t(i) * L.ncols, s); rc != CHPIR_OK) return rc;
+  return CHPIR_OK;
 }
 
 int launch_pack(const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col_begin, const PackedLayout &L, uint8_t *packed, cudaStream_t s) {

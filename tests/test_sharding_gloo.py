@@ -1,0 +1,67 @@
+"""N > 1 host logic on CPU: two gloo ranks shard the columns, answer for their slice (the oracle stands in for the GPU
+kernels here -- this test is about partition / padding / gather / re-interleave, not arithmetic) and gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from chalametpir_b200 import sharding
+from oracle import oracle as O
+
+SEED = bytes(range(32))
+
+
+def test_slice_of_partitions_exactly():
+    for n in (1, 7, 118, 846, 940, 941):
+        for world in (1, 2, 3, 4, 8):
+            got = [sharding.slice_of(n, r, world) for r in range(world)]
+            assert got[0][0] == 0 and sum(c for _, c in got) == n
+            for (b0, c0), (b1, _) in zip(got, got[1:]):
+                assert b0 + c0 == b1
+            assert max(c for _, c in got) - min(c for _, c in got) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, K, N, b, lwe, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(123)  # same D and queries on every rank
+        D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+        Q = 3
+        q = rng.integers(0, 2**32, size=(Q, K), dtype=np.uint64).astype(np.uint32)
+        qt = torch.from_numpy(q.view(np.int32)).clone()
+        if rank != 0:
+            qt.zero_()
+        dist.broadcast(qt, 0)  # the query batch reaches every rank
+        q_here = qt.numpy().view(np.uint32)
+        c0, nc = sharding.slice_of(N, rank, world)
+        srv, hint = O.Server.setup_from_matrix(SEED, np.ascontiguousarray(D[:, c0 : c0 + nc]), b, lwe_rows=lwe)
+        local = np.stack([O.matrix_from_bytes(srv.respond(O.matrix_to_bytes(q_here[i : i + 1])))[0] for i in range(Q)])
+        full = sharding.gather_response_slices(dist, torch, torch.from_numpy(local.view(np.int32)), N, world)
+        hints = [None] * world
+        dist.all_gather_object(hints, hint)
+        if rank == 0:
+            ref_srv, ref_hint = O.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe)
+            for i in range(Q):
+                want = ref_srv.respond(O.matrix_to_bytes(q[i : i + 1]))
+                assert sharding.response_bytes(full[i].numpy().view(np.uint32)) == want
+            assert sharding.interleave_hint_slices(hints) == ref_hint
+            open(os.path.join(out_dir, "ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N", [(2, 37), (2, 940 // 8), (3, 50)])
+def test_two_rank_gloo_column_sharding(tmp_path, world, N):
+    mp.spawn(_worker, args=(world, _free_port(), 997, N, 9, 16, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
