@@ -264,7 +264,8 @@ def run_b200(args):
     D = gen_d_slice(torch, K, c0, nc, b, dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    srv, hint = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, skip_hint=args.skip_hint)
+    srv, hint = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, skip_hint=args.skip_hint,
+                                                   batch_tc=0 if args.no_batch_tc else 1)
     setup_wall = time.perf_counter() - t0
     tm = srv.setup_timing()
     km = srv.last_kernel_ms()
@@ -423,6 +424,39 @@ def run_b200(args):
     parity["e2e_equals_device_path"] = bool(np.array_equal(got, resp_dev[0].cpu().numpy().view(np.uint32)))
     assert parity["e2e_equals_device_path"]
 
+    # ---------------- batched respond on the tensor cores (BASELINE.json configs[3]: 64-query int8-limb GEMM; 128 fill one M tile)
+    batched = None
+    if not args.no_batch_tc:
+        del q_host, r_host
+        BQ = args.batch_queries
+        qb_dev = torch.randint(-(2**31), 2**31, (BQ, K), dtype=torch.int32, device=dev, generator=g)
+        rb_dev = torch.empty((BQ, nc), dtype=torch.int32, device=dev)
+        srv.respond_device_tc(qb_dev.data_ptr(), BQ, rb_dev.data_ptr(), stream)
+        srv.respond_device(qb_dev.data_ptr(), min(BQ, 4), resp_dev.data_ptr() if Q >= 4 else rb_dev.data_ptr(), stream)
+        torch.cuda.synchronize()
+        if Q >= 4:
+            parity["batched_tc_equals_gemv"] = bool(torch.equal(rb_dev[: min(BQ, 4)], resp_dev[: min(BQ, 4)]))
+            assert parity["batched_tc_equals_gemv"]
+        for _ in range(2):
+            srv.respond_device_tc(qb_dev.data_ptr(), BQ, rb_dev.data_ptr(), stream)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        nb = max(3, args.steps // 4)
+        for _ in range(nb):
+            srv.respond_device_tc(qb_dev.data_ptr(), BQ, rb_dev.data_ptr(), stream)
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1) / nb], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        ms_b = float(tb[0])
+        nlimb = 7 if b > 8 else 4
+        int8_ops = nlimb * 2 * 128 * K * (-(-nc // 128) * 128)
+        batched = {"queries_per_batch": BQ, "ms_per_batch": ms_b, "queries_per_s": BQ / (ms_b * 1e-3), "includes": "limb split of the query block + int8-limb GEMM; device-resident queries, no collectives",
+                   "issued_int8_tops": int8_ops * -(-BQ // 128) / (ms_b * 1e-3) / 1e12, "d_plane_bytes_streamed_per_batch": (2 if b > 8 else 1) * K * nc * -(-BQ // 128)}
+        del qb_dev, rb_dev
+
     # ---------------- roofline of the dominant kernel
     pk = peaks()
     streamed = srv.packed_bytes + 4 * K + 4 * nc  # bytes one query on this rank must move: resident packed slice + query + response
@@ -468,6 +502,7 @@ def run_b200(args):
         "clocks": clocks,
         "setup": setup,
         "respond_us_per_query_kernel": ms_kernel * 1e3,
+        "batched_respond_tc": batched,
         "parity": parity,
         "published_reference": {"server_respond_2^20_3wise_ms": {"m8g.8xlarge": 10.06, "m7i.8xlarge": 14.06}, "server_setup_2^20_3wise_s": {"m8g": 577, "m7i": 1282, "g6e(L40S offload)": 25.58}},
     }
@@ -488,6 +523,8 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=4)
     ap.add_argument("--skip-hint", action="store_true", help="make D resident only (no A expansion / hint GEMM) -- development shortcut")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch-tc", action="store_true", help="skip the tensor-core batched respond measurement")
+    ap.add_argument("--batch-queries", type=int, default=128)
     ap.add_argument("--cpu-sample-frac", type=int, default=8)
     ap.add_argument("--ref-sample-frac", type=int, default=4)
     args = ap.parse_args()

@@ -24,6 +24,7 @@ class SetupOpts(C.Structure):
         ("col_count", C.c_uint32),
         ("gemm_variant", C.c_uint32),
         ("skip_hint", C.c_uint32),
+        ("batch_tc", C.c_uint32),
     ]
 
 
@@ -65,6 +66,7 @@ EXPORTS = [
     "chpir_server_respond",
     "chpir_server_respond_batch",
     "chpir_server_respond_device",
+    "chpir_server_respond_device_tc",
     "chpir_generate_from_seed",
     "chpir_matmul",
     "chpir_server_last_kernel_ms",
@@ -104,6 +106,7 @@ lib.chpir_server_get_info.argtypes = [_vp, C.POINTER(ServerInfo)]
 lib.chpir_server_respond.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp]
 lib.chpir_server_respond_batch.argtypes = [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32, _vp, C.c_size_t]
 lib.chpir_server_respond_device.argtypes = [_vp, _vp, C.c_uint32, _vp, _vp]
+lib.chpir_server_respond_device_tc.argtypes = [_vp, _vp, C.c_uint32, _vp, _vp]
 lib.chpir_generate_from_seed.argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
 lib.chpir_matmul.argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _vp]
 lib.chpir_server_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]

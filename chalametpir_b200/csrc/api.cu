@@ -85,6 +85,8 @@ struct chpir_server {
   RespondPlan plan{};
   uint8_t *d_packed = nullptr;
   uint64_t packed_bytes = 0;
+  GemmTcB *gemm = nullptr;  // D's byte-limb planes + operand ring, kept for the tensor-core batched respond
+  std::mutex gemm_mu;
   chpir_setup_timing timing{};
   float last_respond_ms = 0.f, last_gemm_ms = 0.f, last_expand_ms = 0.f;
   std::mutex pool_mu;
@@ -116,6 +118,7 @@ struct chpir_server {
     if (batch_resp) cudaFree(batch_resp);
     if (batch_h_resp) cudaFreeHost(batch_h_resp);
     if (d_packed) cudaFree(d_packed);
+    if (gemm) gemm_tc_free(gemm);
   }
 
   int reserve_batch(uint32_t nq) {
@@ -229,7 +232,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
         std::vector<cudaEvent_t> ev;
         ~Guard() {
           for (cudaEvent_t e : ev) cudaEventDestroy(e);
-          gemm_tc_free(g);
+          if (g) gemm_tc_free(g);
         }
       } guard{g, {}};
       const uint32_t panels = (m + 127) / 128;
@@ -261,6 +264,10 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, guard.ev[2 * p], guard.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
       }
+      if (o.batch_tc != 2) {  // the planes exist: keep them for the batched respond
+        srv->gemm = g;
+        guard.g = nullptr;
+      }
     }
     const float all_ms = t_all.ms();
     const double t0 = now_s();
@@ -277,6 +284,10 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   } else {
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
     if (hint_len) *hint_len = 0;
+  }
+  if (o.batch_tc == 1 && !srv->gemm) {
+    if (int rc = gemm_tc_prepare(d_dev + col0, ld, K, ncols, b, ctx->sm_count, st, &srv->gemm); rc != CHPIR_OK) return rc;
+    CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
   }
   srv->timing.pack_s = t_pack.ms() * 1e-3;
   return CHPIR_OK;
@@ -620,6 +631,23 @@ int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uin
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);  // NULL is the CUDA default stream, as for any launch
   CHPIR_CUDA(cudaMemsetAsync(resp_device, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   return launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, q_device, resp_device, nq, st);
+  CHPIR_GUARD_END
+}
+
+int chpir_server_respond_device_tc(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream) {
+  CHPIR_GUARD_BEGIN
+  if (!srv || !q_device || !resp_device) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (!srv->gemm) return CHPIR_ERR_INVALID_ARGUMENT;  // set up without limb planes
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  std::lock_guard<std::mutex> g(srv->gemm_mu);
+  CHPIR_CUDA(cudaMemsetAsync(resp_device, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  // 128 queries per pass over D: the query block is the "A" operand of the hint GEMM, D's planes the "B" operand
+  for (uint32_t q0 = 0, p = 0; q0 < nq; q0 += 128, p++) {
+    const uint32_t rows = std::min<uint32_t>(128u, nq - q0);
+    if (int rc = gemm_tc_load_panel_u32(srv->gemm, p & 1, q_device + size_t(q0) * srv->K, rows, st); rc != CHPIR_OK) return rc;
+    if (int rc = gemm_tc_panel(srv->gemm, p & 1, rows, resp_device + size_t(q0) * srv->ncols, st); rc != CHPIR_OK) return rc;
+  }
+  return CHPIR_OK;
   CHPIR_GUARD_END
 }
 

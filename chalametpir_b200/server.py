@@ -106,8 +106,8 @@ class Server:
 
     # ------------------------------------------------------------------ setup
     @staticmethod
-    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False) -> SetupOpts:
-        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0)
+    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0) -> SetupOpts:
+        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc)
 
     @staticmethod
     def setup(seed_mu: bytes, db: Mapping[bytes, bytes], arity: int = 3, *, device: int = 0, filter_seed_rng: Optional[int] = None,
@@ -206,6 +206,10 @@ class Server:
     def respond_device(self, q_ptr: int, nq: int, resp_ptr: int, stream: int = 0) -> None:
         """Device-resident respond: q_ptr -> nq x K uint32, resp_ptr -> nq x cols_n uint32, enqueued on `stream`."""
         check(lib.chpir_server_respond_device(self._h, q_ptr, nq, resp_ptr, stream or None))  # 0/None = CUDA default stream
+
+    def respond_device_tc(self, q_ptr: int, nq: int, resp_ptr: int, stream: int = 0) -> None:
+        """Batched respond on the tensor cores (limb-decomposed int8 GEMM): same arguments as respond_device."""
+        check(lib.chpir_server_respond_device_tc(self._h, q_ptr, nq, resp_ptr, stream or None))
 
     # ------------------------------------------------------------------ introspection
     def setup_timing(self) -> dict:

@@ -103,6 +103,9 @@ typedef struct chpir_setup_opts {
   uint32_t col_count;    /* 0 = all columns                                                               */
   uint32_t gemm_variant; /* 0 = default (tcgen05 int8-limb GEMM); 1 = SIMT u32 reference kernel (debug)    */
   uint32_t skip_hint;    /* 1 = only make D resident (pack), no A expansion / GEMM                        */
+  uint32_t batch_tc;     /* batched respond on the tensor cores (chpir_server_respond_device_tc): 0 = keep D's byte-limb
+                            planes resident iff the hint GEMM built them anyway, 1 = always build and keep them,
+                            2 = never keep them (saves 2*K*N bytes of HBM)                                */
 } chpir_setup_opts;
 
 /* d_host: K x N row-major u32 (Matrix elems), values < 2^mat_elem_bit_len.
@@ -158,6 +161,13 @@ CHPIR_API int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const
 /* Device-resident variants (inputs already in HBM): q_device = nq x K u32, resp_device = nq x col_count u32,
  * enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the CUDA default stream); no synchronisation. */
 CHPIR_API int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream);
+
+/* Batched respond as a limb-decomposed int8 GEMM on the tensor cores (north_star (2), BASELINE.json configs[3]): the nq x K
+ * query matrix plays the role A plays in setup, D's resident byte-limb planes are the B operand, so D is streamed once per
+ * 128 queries instead of once per query.  Same inputs/outputs as chpir_server_respond_device; resp_device is overwritten.
+ * Calls on one server must be stream-ordered with respect to each other (they share the operand staging ring).
+ * Returns CHPIR_ERR_INVALID_ARGUMENT if the server was set up without limb planes (chpir_setup_opts.batch_tc). */
+CHPIR_API int chpir_server_respond_device_tc(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream);
 
 /* ---- building blocks exposed for parity tests and for composing other paths ------------------------ */
 /* Matrix::generate_from_seed (matrix.rs:541-558) on device; rows [row_begin, row_begin+row_count) of the rows x cols

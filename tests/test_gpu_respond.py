@@ -191,3 +191,40 @@ def test_full_size_respond_properties(arity, n_log2):
     q1, q2 = rand_u32(rng, K), rand_u32(rng, K)
     assert np.array_equal(respond(q1 + q2), respond(q1) + respond(q2))
     srv.close()
+
+
+@pytest.mark.parametrize("b,K,N,nq", [(9, 4099, 941, 5), (10, 30011, 846, 130), (8, 2500, 37, 64), (14, 777, 129, 3), (4, 5000, 300, 128)])
+def test_respond_tensor_core_batch_matches_oracle(b, K, N, nq):
+    """Batched respond as a limb-decomposed int8 GEMM (north_star (2)): bit-exact against the oracle's Server::respond
+    for every query of the batch, and identical to the streaming GEMV path."""
+    import torch
+
+    rng = np.random.default_rng(b * 1000 + nq)
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    srv, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True, batch_tc=1)
+    Q = rand_u32(rng, (nq, K))
+    Q[0] = 0xFFFFFFFF  # all limbs saturated: int32 accumulators must wrap, not clamp
+    dq = torch.from_numpy(Q.view(np.int32)).cuda()
+    dr = torch.full((nq, N), -1, dtype=torch.int32, device="cuda")
+    dg = torch.empty((nq, N), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    srv.respond_device_tc(dq.data_ptr(), nq, dr.data_ptr(), st)
+    srv.respond_device(dq.data_ptr(), nq, dg.data_ptr(), st)
+    torch.cuda.synchronize()
+    got = dr.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, dg.cpu().numpy().view(np.uint32))
+    osrv, _ = O.Server.setup_from_matrix(SEED, D, b, want_hint=False)
+    for i in sorted(set([0, 1, nq // 2, nq - 1])):
+        assert np.array_equal(got[i], O.matrix_from_bytes(osrv.respond(qbytes(Q[i])))[0]), i
+    srv.close()
+
+
+def test_respond_tensor_core_batch_needs_planes():
+    srv, _ = cp.Server.setup_from_matrix(SEED, np.ones((64, 8), np.uint32), 9, skip_hint=True)
+    import torch
+
+    dq = torch.zeros((1, 64), dtype=torch.int32, device="cuda")
+    dr = torch.zeros((1, 8), dtype=torch.int32, device="cuda")
+    with pytest.raises(cp.ChalametPIRError) as e:
+        srv.respond_device_tc(dq.data_ptr(), 1, dr.data_ptr(), 0)
+    assert e.value.variant == "InvalidArgument"
