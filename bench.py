@@ -270,6 +270,37 @@ def run_b200(args):
     tm = srv.setup_timing()
     km = srv.last_kernel_ms()
     setup = {"wall_s": setup_wall, **{k: round(v, 6) for k, v in tm.items()}, "gemm_kernel_ms": km["gemm_ms"], "skipped_hint": bool(args.skip_hint)}
+    if not args.skip_hint:
+        # tensor roofline of the hint GEMM: issued int8 ops = limb pairs x 2 x padded M x K x padded N, summed over the 128-row panels
+        nlimb = 7 if b > 8 else 4
+        m_pad, n_pad = -(-LWE // 128) * 128, -(-nc // 128) * 128 if nc > 128 else -(-nc // 16) * 16
+        issued = nlimb * 2 * m_pad * K * n_pad
+        useful = nlimb * 2 * LWE * K * nc
+        int8_peak = 2.0 * peaks()["bf16_tflops"]  # no int8 figure in MEASURED_PEAKS.json: 2 x the bf16 dense figure (kind::i8 runs at twice the kind::f16 rate)
+        gs = km["gemm_ms"] * 1e-3
+        setup["gemm_roofline"] = {
+            "bound": "tensor", "kernel": "gemm_tc_kernel<2> (tcgen05 kind::i8 limb GEMM, 14 panel launches)", "achieved": issued / gs / 1e12, "useful": useful / gs / 1e12,
+            "peak": int8_peak, "peak_source": f"2 x bf16_tflops ({peaks()['source']})", "unit": "TOP/s", "frac": issued / gs / 1e12 / int8_peak,
+            "u32_mac_equivalent_tmacs": LWE * K * nc / gs / 1e12,
+        }
+        setup["xof_ns_per_permutation"] = tm["expand_a_s"] / (LWE * K * 4 / 168.0) * 1e9
+    if world > 1 and hint is not None:
+        # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
+        from chalametpir_b200 import sharding
+
+        t0 = time.perf_counter()
+        H = torch.from_numpy(np.frombuffer(hint, dtype=np.uint8)[8:].view(np.int32).reshape(LWE, nc).copy()).to(dev)
+        padw = max(sharding.slice_counts(N, world))
+        sendh = torch.zeros((LWE, padw), dtype=torch.int32, device=dev)
+        sendh[:, :nc] = H
+        allh = torch.empty((world, LWE, padw), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allh.view(-1), sendh.view(-1))
+        full_hint = sharding.unpad_gathered(torch, allh, sharding.slice_counts(N, world))
+        torch.cuda.synchronize()
+        setup["hint_gather_s"] = time.perf_counter() - t0
+        setup["hint_bytes_total"] = 8 + 4 * LWE * N
+        assert full_hint.shape == (LWE, N)
+        del H, sendh, allh, full_hint
 
     # ---------------- parity spot checks (outside every timed region; numpy / oracle as the checker)
     parity = {}

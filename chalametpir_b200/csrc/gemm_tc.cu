@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) {
         // kind::i8, u8 x u8 -> s32 (wrapping), K-major A and B, M = 128, N = bn
         const uint32_t idesc = (2u << 4) | ((bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+        const uint32_t idesc_wide = (2u << 4) | (((BN_MAX + bn) >> 3) << 17) | (uint32_t(BM >> 4) << 24);
         for (uint32_t i = 0; i < nkb; i++) {
           const int s = i % STAGES;
           const uint32_t ph = (i / STAGES) & 1;
@@ -177,14 +178,26 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int l = 0; l < NB; l++) db[l] = umma_desc_sw128(b_base + l * B_TILE + kk * 32);
             // accumulator s = i + j lives at TMEM columns [s*128, s*128 + bn)
-            umma_i8(tmem + 0 * BN_MAX, da[0], db[0], idesc, first);
-            umma_i8(tmem + 1 * BN_MAX, da[1], db[0], idesc, first);
-            umma_i8(tmem + 2 * BN_MAX, da[2], db[0], idesc, first);
-            umma_i8(tmem + 3 * BN_MAX, da[3], db[0], idesc, first);
-            if (NB == 2) {
-              umma_i8(tmem + 1 * BN_MAX, da[0], db[NB - 1], idesc, 1u);
-              umma_i8(tmem + 2 * BN_MAX, da[1], db[NB - 1], idesc, 1u);
-              umma_i8(tmem + 3 * BN_MAX, da[2], db[NB - 1], idesc, 1u);
+            if (NB == 2 && first != 0u) {
+              // Steady state: the d0 and d1 tiles are adjacent in shared memory (rows 0..127 and 128..128+bn of one
+              // K-major tile) and the accumulators of shift i and i+1 are adjacent in TMEM, so A_i x [d0; d1] is ONE
+              // MMA of N = 128 + bn that lands A_i.d0 in acc_i and A_i.d1 in acc_{i+1}.  4 MMAs instead of 7 for the same
+              // tensor work, and every A_i tile is read from shared memory once instead of twice.
+              umma_i8(tmem + 0 * BN_MAX, da[0], db[0], idesc_wide, 1u);
+              umma_i8(tmem + 1 * BN_MAX, da[1], db[0], idesc_wide, 1u);
+              umma_i8(tmem + 2 * BN_MAX, da[2], db[0], idesc_wide, 1u);
+              umma_i8(tmem + 3 * BN_MAX, da[3], db[0], idesc, 1u);
+            } else {
+              // very first k-step (accumulators are overwritten, not accumulated) and the single-limb case
+              umma_i8(tmem + 0 * BN_MAX, da[0], db[0], idesc, first);
+              umma_i8(tmem + 1 * BN_MAX, da[1], db[0], idesc, first);
+              umma_i8(tmem + 2 * BN_MAX, da[2], db[0], idesc, first);
+              umma_i8(tmem + 3 * BN_MAX, da[3], db[0], idesc, first);
+              if (NB == 2) {
+                umma_i8(tmem + 1 * BN_MAX, da[0], db[NB - 1], idesc, 1u);
+                umma_i8(tmem + 2 * BN_MAX, da[1], db[NB - 1], idesc, 1u);
+                umma_i8(tmem + 3 * BN_MAX, da[2], db[NB - 1], idesc, 1u);
+              }
             }
           }
           umma_commit(&bars.empty[s]);  // frees the smem stage once these MMAs have read it
