@@ -265,11 +265,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     srv, hint = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, skip_hint=args.skip_hint,
-                                                   batch_tc=0 if args.no_batch_tc else 1)
+                                                   batch_tc=0 if args.no_batch_tc else 1, a_expand="host" if args.a_expand == "host" else "device")
     setup_wall = time.perf_counter() - t0
     tm = srv.setup_timing()
     km = srv.last_kernel_ms()
-    setup = {"wall_s": setup_wall, **{k: round(v, 6) for k, v in tm.items()}, "gemm_kernel_ms": km["gemm_ms"], "skipped_hint": bool(args.skip_hint)}
+    setup = {"a_expand": "host" if args.a_expand == "host" else "device", "wall_s": setup_wall, **{k: round(v, 6) for k, v in tm.items()}, "gemm_kernel_ms": km["gemm_ms"], "skipped_hint": bool(args.skip_hint)}
     if not args.skip_hint:
         # tensor roofline of the hint GEMM: issued int8 ops = limb pairs x 2 x padded M x K x padded N, summed over the 128-row panels
         nlimb = 7 if b > 8 else 4
@@ -284,6 +284,19 @@ def run_b200(args):
             "u32_mac_equivalent_tmacs": LWE * K * nc / gs / 1e12,
         }
         setup["xof_ns_per_permutation"] = tm["expand_a_s"] / (LWE * K * 4 / 168.0) * 1e9
+    # the same setup with the XOF chain walked by a host core and uploads + panel GEMMs pipelined behind it (a_expand = "host"):
+    # byte-identical hint, several times lower latency (the chain is serial; a CPU core runs it faster than a GPU warp)
+    if not args.skip_hint and args.a_expand == "both":
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        srv_h, hint_h = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, batch_tc=2, a_expand="host")
+        wall_h = time.perf_counter() - t0
+        th = srv_h.setup_timing()
+        setup["host_pipelined"] = {"wall_s": wall_h, **{k: round(v, 6) for k, v in th.items()}, "gemm_kernel_ms": srv_h.last_kernel_ms()["gemm_ms"],
+                                   "xof_impl": cp.host_xof_impl(), "xof_ns_per_permutation": th["xof_host_busy_s"] / (LWE * K * 4 / 168.0) * 1e9,
+                                   "hint_identical_to_device_mode": bool(hint_h == hint)}
+        assert hint_h == hint, "host-pipelined setup produced a different hint"
+        del srv_h, hint_h
     if world > 1 and hint is not None:
         # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
         from chalametpir_b200 import sharding
@@ -553,6 +566,8 @@ def main():
     ap.add_argument("--queries-per-step", type=int, default=16)
     ap.add_argument("--e2e-threads", type=int, default=4)
     ap.add_argument("--skip-hint", action="store_true", help="make D resident only (no A expansion / hint GEMM) -- development shortcut")
+    ap.add_argument("--a-expand", default="both", choices=["device", "host", "both"],
+                    help="where Server::setup walks the TurboSHAKE128 chain of A: GPU warp, host core (pipelined), or both one after the other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch-tc", action="store_true", help="skip the tensor-core batched respond measurement")
     ap.add_argument("--batch-queries", type=int, default=128)

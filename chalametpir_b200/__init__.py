@@ -14,6 +14,8 @@ from .server import (
     find_mat_elem_bit_len,
     generate_from_seed,
     get_ctx,
+    host_generate_from_seed,
+    host_xof_impl,
     matmul,
 )
 
@@ -31,5 +33,7 @@ __all__ = [
     "find_mat_elem_bit_len",
     "generate_from_seed",
     "get_ctx",
+    "host_generate_from_seed",
+    "host_xof_impl",
     "matmul",
 ]

@@ -25,11 +25,17 @@ class SetupOpts(C.Structure):
         ("gemm_variant", C.c_uint32),
         ("skip_hint", C.c_uint32),
         ("batch_tc", C.c_uint32),
+        ("a_expand", C.c_uint32),
+        ("host_chunk_rows", C.c_uint32),
     ]
 
 
+A_EXPAND_DEVICE = 0
+A_EXPAND_HOST_PIPELINED = 1
+
+
 class SetupTiming(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("host_encode_s", "h2d_s", "pack_s", "expand_a_s", "gemm_s", "d2h_s", "total_s")]
+    _fields_ = [(n, C.c_double) for n in ("host_encode_s", "h2d_s", "pack_s", "expand_a_s", "gemm_s", "d2h_s", "total_s", "xof_host_busy_s")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -70,6 +76,8 @@ EXPORTS = [
     "chpir_generate_from_seed",
     "chpir_matmul",
     "chpir_server_last_kernel_ms",
+    "chpir_host_generate_from_seed",
+    "chpir_host_xof_impl",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -109,4 +117,7 @@ lib.chpir_server_respond_device.argtypes = [_vp, _vp, C.c_uint32, _vp, _vp]
 lib.chpir_server_respond_device_tc.argtypes = [_vp, _vp, C.c_uint32, _vp, _vp]
 lib.chpir_generate_from_seed.argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
 lib.chpir_matmul.argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _vp]
+lib.chpir_host_generate_from_seed.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _vp]
+lib.chpir_host_xof_impl.restype = C.c_char_p
+lib.chpir_host_xof_impl.argtypes = []
 lib.chpir_server_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]

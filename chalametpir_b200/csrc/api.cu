@@ -1,13 +1,17 @@
 // api.cu -- the extern "C" surface declared in include/chalamet_b200.h.
 // No exceptions cross this boundary: every entry point is wrapped in a catch-all and returns a chpir_status.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 
 #include "common.cuh"
 #include "host_encode.hpp"
+#include "host_xof.hpp"
 
 namespace chpir {
 
@@ -174,6 +178,148 @@ namespace {
 
 int validate_bits(uint32_t b) { return (b >= 4 && b <= 14) ? CHPIR_OK : CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH; }
 
+// ---- host-pipelined A (chpir_setup_opts.a_expand = CHPIR_A_EXPAND_HOST_PIPELINED) ----------------------------------------
+// The XOF squeeze is one serial chain; a CPU core walks it several times faster than a GPU warp.  A producer thread squeezes
+// the stream (= the row-major u32 bytes of A, matrix.rs:552-555) into a small ring of pinned chunks of whole rows; this thread
+// uploads every chunk into a 128-row u32 staging panel and, once a panel is complete, splits it into byte planes and runs the
+// tensor-core GEMM for it -- all on one stream, so uploads and GEMMs hide entirely behind the producer.
+struct HostXofStream {
+  HostXof x;
+  uint8_t carry[kXofRate];
+  uint32_t carry_off = 0, carry_len = 0;
+  int impl = 0;
+  void fill(uint8_t *dst, uint64_t n) {
+    const uint64_t take = std::min<uint64_t>(carry_len, n);
+    std::memcpy(dst, carry + carry_off, take);
+    carry_off += uint32_t(take), carry_len -= uint32_t(take);
+    dst += take, n -= take;
+    const uint64_t blocks = n / kXofRate;
+    host_xof_squeeze_blocks(&x, dst, blocks, impl);
+    dst += blocks * kXofRate, n -= blocks * kXofRate;
+    if (n) {
+      host_xof_squeeze_blocks(&x, carry, 1, impl);
+      std::memcpy(dst, carry, n);
+      carry_off = uint32_t(n), carry_len = uint32_t(kXofRate - n);
+    }
+  }
+};
+
+int hint_host_pipelined(chpir_ctx *ctx, const uint8_t *seed, const GemmTcB *g, uint32_t m, uint64_t K, uint32_t ncols, uint32_t *c_dev,
+                        uint32_t chunk_rows_opt, cudaStream_t st, float *gemm_ms_out, double *xof_busy_s) {
+  constexpr int NB = 4;
+  const uint64_t row_bytes = K * 4;
+  uint32_t chunk_rows = chunk_rows_opt ? chunk_rows_opt : uint32_t(std::max<uint64_t>(1, (32ull << 20) / row_bytes));
+  chunk_rows = std::min(chunk_rows, 128u);
+  // chunks never straddle a panel: (first row, row count) in production order
+  std::vector<std::pair<uint32_t, uint32_t>> chunks;
+  for (uint32_t p0 = 0; p0 < m; p0 += 128)
+    for (uint32_t r = p0; r < std::min(m, p0 + 128); r += chunk_rows) chunks.push_back({r, std::min(chunk_rows, std::min(m, p0 + 128) - r)});
+
+  struct Ring {
+    uint8_t *pinned[NB] = {};
+    cudaEvent_t copied[NB] = {};
+    std::vector<cudaEvent_t> ev;
+    ~Ring() {
+      for (auto p : pinned)
+        if (p) cudaFreeHost(p);
+      for (auto e : copied)
+        if (e) cudaEventDestroy(e);
+      for (auto e : ev)
+        if (e) cudaEventDestroy(e);
+    }
+  } ring;
+  for (int i = 0; i < NB; i++) {
+    if (cudaMallocHost(&ring.pinned[i], uint64_t(chunk_rows) * row_bytes) != cudaSuccess) {
+      set_last_cuda_error(cudaGetLastError(), "pinned XOF chunk ring");
+      return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+    }
+    if (cudaEventCreateWithFlags(&ring.copied[i], cudaEventDisableTiming) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+  }
+  DevBuf staging;  // one 128-row u32 panel; the stream is in order, so the split of panel p precedes the uploads of panel p+1
+  if (int rc = staging.alloc(uint64_t(std::min(m, 128u)) * row_bytes); rc != CHPIR_OK) return rc;
+  const uint32_t panels = (m + 127) / 128;
+  ring.ev.resize(2 * panels, nullptr);
+  for (auto &e : ring.ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t filled = 0, issued = 0;  // chunks produced / chunks whose upload has been enqueued (event recorded)
+  std::atomic<bool> abort{false};
+  double busy = 0.0;
+  const int device = ctx->device;
+  std::thread producer([&] {
+    cudaSetDevice(device);
+    HostXofStream xs;
+    host_xof_init(&xs.x, seed);
+    for (uint64_t i = 0; i < chunks.size() && !abort.load(); i++) {
+      const int b = int(i % NB);
+      if (i >= NB) {
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return issued > i - NB || abort.load(); });
+        }
+        if (abort.load()) break;
+        cudaEventSynchronize(ring.copied[b]);  // the upload of chunk i - NB has left this buffer
+      }
+      const double t0 = now_s();
+      xs.fill(ring.pinned[b], uint64_t(chunks[i].second) * row_bytes);
+      busy += now_s() - t0;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        filled = i + 1;
+      }
+      cv.notify_all();
+    }
+  });
+  int rc = CHPIR_OK;
+  for (uint64_t i = 0; i < chunks.size() && rc == CHPIR_OK; i++) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return filled > i; });
+    }
+    const int b = int(i % NB);
+    const uint32_t r0 = chunks[i].first, nr = chunks[i].second, p = r0 / 128, panel_end = std::min(m, (p + 1) * 128);
+    if (cudaMemcpyAsync(staging.as<uint8_t>() + uint64_t(r0 - p * 128) * row_bytes, ring.pinned[b], uint64_t(nr) * row_bytes, cudaMemcpyHostToDevice,
+                        st) != cudaSuccess ||
+        cudaEventRecord(ring.copied[b], st) != cudaSuccess) {
+      set_last_cuda_error(cudaGetLastError(), "XOF chunk upload");
+      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      issued = i + 1;
+    }
+    cv.notify_all();
+    if (rc == CHPIR_OK && r0 + nr == panel_end) {
+      const uint32_t rows = panel_end - p * 128;
+      rc = gemm_tc_load_panel_u32(g, int(p & 1), staging.as<uint32_t>(), rows, st);
+      cudaEventRecord(ring.ev[2 * p], st);
+      if (rc == CHPIR_OK) rc = gemm_tc_panel(g, int(p & 1), rows, c_dev + size_t(p) * 128u * ncols, st);
+      cudaEventRecord(ring.ev[2 * p + 1], st);
+    }
+  }
+  if (rc != CHPIR_OK) {
+    abort.store(true);
+    cv.notify_all();
+  }
+  producer.join();
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == CHPIR_OK && e != cudaSuccess) {
+    set_last_cuda_error(e, "setup: host-pipelined A + hint GEMM");
+    rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+  }
+  float gemm_ms = 0.f;
+  if (rc == CHPIR_OK)
+    for (uint32_t p = 0; p < panels; p++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ring.ev[2 * p], ring.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
+    }
+  *gemm_ms_out = gemm_ms;
+  *xof_busy_s = busy;
+  return rc;
+}
+
 // Core of setup once D (K x ld u32, device) is resident.  d_dev columns [col0, col0+ncols) form this server's slice.
 int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col0, uint32_t ncols,
                uint32_t col_begin_logical, uint32_t b, const chpir_setup_opts &o, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
@@ -207,7 +353,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
     if (int rc = scratch.alloc(512); rc != CHPIR_OK) return rc;
     if (int rc = c.alloc(size_t(m) * ncols * 4); rc != CHPIR_OK) return rc;
     EventTimer t_all;
-    float gemm_ms = 0.f;
+    float gemm_ms = 0.f, host_wall_ms = 0.f;
     if (o.gemm_variant == 1) {
       // debug path: A = generate_from_seed(m, K, seed) as u32 in HBM, then the SIMT u32 GEMM
       DevBuf a;
@@ -241,35 +387,43 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
         if (cudaEventCreate(&e) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
       CHPIR_CUDA(cudaMemsetAsync(c.p, 0, size_t(m) * ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
       t_all.start(st);
-      if (int rc = expand_begin(seed, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
-      const uint64_t total_blocks = (uint64_t(m) * K * 4 + 167) / 168;
-      uint64_t blk = 0;
-      for (uint32_t p = 0; p < panels; p++) {
-        const uint32_t r1 = std::min<uint32_t>(m, (p + 1) * 128u);
-        const uint64_t blk_end = std::min<uint64_t>(total_blocks, (uint64_t(r1) * K * 4 + 167) / 168);
-        if (int rc = launch_expand_planes(gemm_tc_ring(g), m, K, gemm_tc_kp(g), scratch.as<uint8_t>(), blk, blk_end - blk, st); rc != CHPIR_OK)
+      if (o.a_expand == CHPIR_A_EXPAND_HOST_PIPELINED) {
+        const double w0 = now_s();
+        if (int rc = hint_host_pipelined(ctx, seed, g, m, K, ncols, c.as<uint32_t>(), o.host_chunk_rows, st, &gemm_ms, &srv->timing.xof_host_busy_s);
+            rc != CHPIR_OK)
           return rc;
-        blk = blk_end;
-        cudaEventRecord(guard.ev[2 * p], st);
-        if (int rc = gemm_tc_panel(g, p & 1, r1 - p * 128u, c.as<uint32_t>() + size_t(p) * 128u * ncols, st); rc != CHPIR_OK) return rc;
-        cudaEventRecord(guard.ev[2 * p + 1], st);
-      }
-      t_all.stop(st);
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) {
-        set_last_cuda_error(e, "setup: expand + hint GEMM");
-        return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
-      }
-      for (uint32_t p = 0; p < panels; p++) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, guard.ev[2 * p], guard.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
+        host_wall_ms = float((now_s() - w0) * 1e3);
+      } else {
+        if (int rc = expand_begin(seed, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
+        const uint64_t total_blocks = (uint64_t(m) * K * 4 + 167) / 168;
+        uint64_t blk = 0;
+        for (uint32_t p = 0; p < panels; p++) {
+          const uint32_t r1 = std::min<uint32_t>(m, (p + 1) * 128u);
+          const uint64_t blk_end = std::min<uint64_t>(total_blocks, (uint64_t(r1) * K * 4 + 167) / 168);
+          if (int rc = launch_expand_planes(gemm_tc_ring(g), m, K, gemm_tc_kp(g), scratch.as<uint8_t>(), blk, blk_end - blk, st); rc != CHPIR_OK)
+            return rc;
+          blk = blk_end;
+          cudaEventRecord(guard.ev[2 * p], st);
+          if (int rc = gemm_tc_panel(g, p & 1, r1 - p * 128u, c.as<uint32_t>() + size_t(p) * 128u * ncols, st); rc != CHPIR_OK) return rc;
+          cudaEventRecord(guard.ev[2 * p + 1], st);
+        }
+        t_all.stop(st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+          set_last_cuda_error(e, "setup: expand + hint GEMM");
+          return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+        }
+        for (uint32_t p = 0; p < panels; p++) {
+          float ms = 0.f;
+          if (cudaEventElapsedTime(&ms, guard.ev[2 * p], guard.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
+        }
       }
       if (o.batch_tc != 2) {  // the planes exist: keep them for the batched respond
         srv->gemm = g;
         guard.g = nullptr;
       }
     }
-    const float all_ms = t_all.ms();
+    const float all_ms = host_wall_ms > 0.f ? host_wall_ms : t_all.ms();
     const double t0 = now_s();
     const uint32_t hdr[2] = {m, ncols};
     std::memcpy(hint_out, hdr, 8);
@@ -701,6 +855,31 @@ int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64
   return CHPIR_OK;
   CHPIR_GUARD_END
 }
+
+int chpir_host_generate_from_seed(const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols, uint64_t row_begin,
+                                  uint64_t row_count, uint32_t impl, uint32_t *out_host) {
+  CHPIR_GUARD_BEGIN
+  if (!seed || !out_host || impl > 3) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || cols == 0 || row_begin + row_count > rows) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
+  HostXofStream xs;
+  xs.impl = int(impl);
+  host_xof_init(&xs.x, seed);
+  uint8_t probe[kXofRate];
+  HostXof tmp = xs.x;
+  if (!host_xof_squeeze_blocks(&tmp, probe, 1, int(impl))) return CHPIR_ERR_INVALID_ARGUMENT;  // implementation not on this CPU
+  // walk to the first requested byte: whole blocks are skipped, the partial one is squeezed and dropped
+  const uint64_t skip = row_begin * cols * 4;
+  host_xof_skip_blocks(&xs.x, skip / kXofRate);
+  if (skip % kXofRate) {
+    uint8_t drop[kXofRate];
+    xs.fill(drop, skip % kXofRate);
+  }
+  xs.fill(reinterpret_cast<uint8_t *>(out_host), row_count * cols * 4);
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+const char *chpir_host_xof_impl(void) { return host_xof_impl_name(); }
 
 int chpir_server_last_kernel_ms(const chpir_server *srv, float *respond_ms, float *gemm_ms, float *expand_ms) {
   if (!srv) return CHPIR_ERR_INVALID_ARGUMENT;

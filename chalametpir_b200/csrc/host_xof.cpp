@@ -1,0 +1,261 @@
+// host_xof.cpp -- the TurboSHAKE128 stream of Matrix::generate_from_seed (chalametpir_common/src/matrix.rs:541-558) produced on a HOST
+// core, for the host-pipelined setup mode (chpir_setup_opts.a_expand = CHPIR_A_EXPAND_HOST_PIPELINED).
+//
+// The squeeze is one serial chain of Keccak-p[1600,12] permutations (RFC 9861), so what matters is the latency of one
+// permutation on one core.  A CPU core runs that chain several times faster than one GPU warp can (csrc/expand.cu); the
+// reference's own `gpu` feature also expands A on the CPU (chalametpir_server/src/server.rs:115) and uploads it.  Two
+// implementations, picked at run time:
+//   * AVX-512 (F + VL): one 64-bit lane per qword slot, a plane A[0..4][y] per zmm register; theta and chi are three-input
+//     vpternlogq, rho is vprolvq, pi is the slot permutation that makes chi register-wise, and the only cross-register data
+//     movement per round is one 5x5 qword transposition;
+//   * scalar 64-bit code (two rounds unrolled, lanes in locals), built twice: baseline x86-64 and BMI2 (rorx / andn).
+// impl 0 times each available variant once (~1 ms) and keeps the fastest.
+#include "host_xof.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace chpir {
+namespace {
+
+constexpr uint64_t kRC[12] = {0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+                              0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+                              0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+
+static inline uint64_t rol(uint64_t v, unsigned r) { return (v << r) | (v >> ((64 - r) & 63)); }
+
+// One round, reading lanes A.. and writing lanes E.. (the classic two-array formulation: pi is a renaming).
+#define CHPIR_ROUND(A, E, RC)                                                                  \
+  do {                                                                                         \
+    const uint64_t c0 = A[0] ^ A[5] ^ A[10] ^ A[15] ^ A[20];                                   \
+    const uint64_t c1 = A[1] ^ A[6] ^ A[11] ^ A[16] ^ A[21];                                   \
+    const uint64_t c2 = A[2] ^ A[7] ^ A[12] ^ A[17] ^ A[22];                                   \
+    const uint64_t c3 = A[3] ^ A[8] ^ A[13] ^ A[18] ^ A[23];                                   \
+    const uint64_t c4 = A[4] ^ A[9] ^ A[14] ^ A[19] ^ A[24];                                   \
+    const uint64_t d0 = c4 ^ rol(c1, 1), d1 = c0 ^ rol(c2, 1), d2 = c1 ^ rol(c3, 1);           \
+    const uint64_t d3 = c2 ^ rol(c4, 1), d4 = c3 ^ rol(c0, 1);                                 \
+    uint64_t b0, b1, b2, b3, b4;                                                               \
+    b0 = A[0] ^ d0, b1 = rol(A[6] ^ d1, 44), b2 = rol(A[12] ^ d2, 43), b3 = rol(A[18] ^ d3, 21), b4 = rol(A[24] ^ d4, 14); \
+    E[0] = b0 ^ (~b1 & b2) ^ (RC), E[1] = b1 ^ (~b2 & b3), E[2] = b2 ^ (~b3 & b4), E[3] = b3 ^ (~b4 & b0), E[4] = b4 ^ (~b0 & b1); \
+    b0 = rol(A[3] ^ d3, 28), b1 = rol(A[9] ^ d4, 20), b2 = rol(A[10] ^ d0, 3), b3 = rol(A[16] ^ d1, 45), b4 = rol(A[22] ^ d2, 61); \
+    E[5] = b0 ^ (~b1 & b2), E[6] = b1 ^ (~b2 & b3), E[7] = b2 ^ (~b3 & b4), E[8] = b3 ^ (~b4 & b0), E[9] = b4 ^ (~b0 & b1); \
+    b0 = rol(A[1] ^ d1, 1), b1 = rol(A[7] ^ d2, 6), b2 = rol(A[13] ^ d3, 25), b3 = rol(A[19] ^ d4, 8), b4 = rol(A[20] ^ d0, 18); \
+    E[10] = b0 ^ (~b1 & b2), E[11] = b1 ^ (~b2 & b3), E[12] = b2 ^ (~b3 & b4), E[13] = b3 ^ (~b4 & b0), E[14] = b4 ^ (~b0 & b1); \
+    b0 = rol(A[4] ^ d4, 27), b1 = rol(A[5] ^ d0, 36), b2 = rol(A[11] ^ d1, 10), b3 = rol(A[17] ^ d2, 15), b4 = rol(A[23] ^ d3, 56); \
+    E[15] = b0 ^ (~b1 & b2), E[16] = b1 ^ (~b2 & b3), E[17] = b2 ^ (~b3 & b4), E[18] = b3 ^ (~b4 & b0), E[19] = b4 ^ (~b0 & b1); \
+    b0 = rol(A[2] ^ d2, 62), b1 = rol(A[8] ^ d3, 55), b2 = rol(A[14] ^ d4, 39), b3 = rol(A[15] ^ d0, 41), b4 = rol(A[21] ^ d1, 2); \
+    E[20] = b0 ^ (~b1 & b2), E[21] = b1 ^ (~b2 & b3), E[22] = b2 ^ (~b3 & b4), E[23] = b3 ^ (~b4 & b0), E[24] = b4 ^ (~b0 & b1); \
+  } while (0)
+
+#define CHPIR_SQUEEZE_BODY                                  \
+  uint64_t a[25], e[25];                                    \
+  std::memcpy(a, s, sizeof a);                              \
+  for (uint64_t i = 0; i < nblocks; i++) {                  \
+    for (int r = 0; r < 12; r += 2) {                       \
+      CHPIR_ROUND(a, e, kRC[r]);                            \
+      CHPIR_ROUND(e, a, kRC[r + 1]);                        \
+    }                                                       \
+    std::memcpy(out + i * kXofRate, a, kXofRate);           \
+  }                                                         \
+  std::memcpy(s, a, sizeof a);
+
+void squeeze_scalar(uint64_t s[25], uint8_t *out, uint64_t nblocks) { CHPIR_SQUEEZE_BODY }
+
+#if defined(__x86_64__)
+// the same code with rorx / andn available: about twice as fast as the baseline x86-64 build of it
+__attribute__((target("bmi,bmi2"))) void squeeze_bmi2(uint64_t s[25], uint8_t *out, uint64_t nblocks) { CHPIR_SQUEEZE_BODY }
+#endif
+
+#if defined(__x86_64__)
+// ---- AVX-512.  Plane representation: register P[y], qword slot x holds A[x][y] (slots 5..7 are don't-care).
+struct Avx512Consts {
+  alignas(64) uint64_t rho[5][8];      // rho[y][x] = rotation of lane (x, y)
+  alignas(64) uint64_t pi[5][8];       // pi[X][Y] = (3Y + X) % 5: slot of old plane X that lands at new position (X, Y)
+  alignas(64) uint64_t rot_m1[8], rot_p1[8];
+  alignas(64) uint64_t t_ab[8];  // first-level transposition index vector (see squeeze_avx512)
+  alignas(64) uint64_t rc[12][8];
+};
+
+constexpr unsigned kRho[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+
+const Avx512Consts &avx512_consts() {
+  static const Avx512Consts c = [] {
+    Avx512Consts k{};
+    for (int y = 0; y < 5; y++)
+      for (int x = 0; x < 8; x++) k.rho[y][x] = x < 5 ? kRho[x + 5 * y] : 0;
+    for (int X = 0; X < 5; X++)
+      for (int Y = 0; Y < 8; Y++) k.pi[X][Y] = Y < 5 ? uint64_t((3 * Y + X) % 5) : uint64_t(Y);
+    for (int x = 0; x < 8; x++) {
+      k.rot_m1[x] = x < 5 ? uint64_t((x + 4) % 5) : uint64_t(x);
+      k.rot_p1[x] = x < 5 ? uint64_t((x + 1) % 5) : uint64_t(x);
+    }
+    // Transposition of the column representation R[X] (slot Y) into planes T[Y] (slot X).
+    //   W01 = permutex2var(R0, t_ab, R1): slots (2Y, 2Y+1) = (R0[Y], R1[Y]) for Y = 0..3;  W23 likewise from R2, R3.
+    //   T[Y] (Y < 4) = permutex2var(W01, t_cd + 2Y, W23) -> slots 0..3, then slot 4 <- R4[Y] by a masked permute.
+    //   T[4] is gathered on its own (4 two-source permutes).
+    for (int i = 0; i < 8; i++) k.t_ab[i] = uint64_t((i >> 1) + ((i & 1) ? 8 : 0));
+    for (int r = 0; r < 12; r++) k.rc[r][0] = kRC[r];
+    return k;
+  }();
+  return c;
+}
+
+__attribute__((target("avx512f,avx512vl"))) void squeeze_avx512(uint64_t s[25], uint8_t *out, uint64_t nblocks) {
+  const Avx512Consts &k = avx512_consts();
+  const __mmask8 m5 = 0x1f;
+  __m512i P0 = _mm512_maskz_loadu_epi64(m5, s + 0), P1 = _mm512_maskz_loadu_epi64(m5, s + 5), P2 = _mm512_maskz_loadu_epi64(m5, s + 10),
+          P3 = _mm512_maskz_loadu_epi64(m5, s + 15), P4 = _mm512_maskz_loadu_epi64(m5, s + 20);
+  const __m512i rho0 = _mm512_load_si512(k.rho[0]), rho1 = _mm512_load_si512(k.rho[1]), rho2 = _mm512_load_si512(k.rho[2]),
+                rho3 = _mm512_load_si512(k.rho[3]), rho4 = _mm512_load_si512(k.rho[4]);
+  const __m512i pi0 = _mm512_load_si512(k.pi[0]), pi1 = _mm512_load_si512(k.pi[1]), pi2 = _mm512_load_si512(k.pi[2]),
+                pi3 = _mm512_load_si512(k.pi[3]), pi4 = _mm512_load_si512(k.pi[4]);
+  const __m512i im1 = _mm512_load_si512(k.rot_m1), ip1 = _mm512_load_si512(k.rot_p1);
+  const __m512i tab = _mm512_load_si512(k.t_ab);
+  // second-level transposition indices: slots 0,1 from W01 pair Y, slots 2,3 from W23 pair Y (+8 selects the second source)
+  const __m512i tq0 = _mm512_setr_epi64(0, 1, 8, 9, 0, 0, 0, 0), tq1 = _mm512_setr_epi64(2, 3, 10, 11, 0, 0, 0, 0),
+                tq2 = _mm512_setr_epi64(4, 5, 12, 13, 0, 0, 0, 0), tq3 = _mm512_setr_epi64(6, 7, 14, 15, 0, 0, 0, 0);
+  const __m512i b0 = _mm512_set1_epi64(0), b1 = _mm512_set1_epi64(1), b2 = _mm512_set1_epi64(2), b3 = _mm512_set1_epi64(3);
+  // T[4]: slot X = R[X][4]
+  const __m512i t4a = _mm512_setr_epi64(4, 12, 0, 0, 0, 0, 0, 0);   // (R0, R1) -> slots 0, 1
+  const __m512i t4b = _mm512_setr_epi64(0, 0, 4, 12, 0, 0, 0, 0);   // (R2, R3) -> slots 2, 3
+  const __m512i t4c = _mm512_setr_epi64(0, 1, 10, 11, 0, 0, 0, 0);  // merge the two pairs
+  const __m512i t4d = _mm512_setr_epi64(0, 1, 2, 3, 12, 0, 0, 0);   // slot 4 <- R4[4]
+  for (uint64_t blk = 0; blk < nblocks; blk++) {
+    for (int r = 0; r < 12; r++) {
+      // theta
+      const __m512i C = _mm512_ternarylogic_epi64(_mm512_ternarylogic_epi64(P0, P1, P2, 0x96), P3, P4, 0x96);
+      const __m512i Cm = _mm512_permutexvar_epi64(im1, C);
+      const __m512i Cp = _mm512_rol_epi64(_mm512_permutexvar_epi64(ip1, C), 1);
+      P0 = _mm512_ternarylogic_epi64(P0, Cm, Cp, 0x96);
+      P1 = _mm512_ternarylogic_epi64(P1, Cm, Cp, 0x96);
+      P2 = _mm512_ternarylogic_epi64(P2, Cm, Cp, 0x96);
+      P3 = _mm512_ternarylogic_epi64(P3, Cm, Cp, 0x96);
+      P4 = _mm512_ternarylogic_epi64(P4, Cm, Cp, 0x96);
+      // rho, then pi as a slot permutation inside each plane: Q[X] slot Y = B[X][Y]
+      const __m512i Q0 = _mm512_permutexvar_epi64(pi0, _mm512_rolv_epi64(P0, rho0));
+      const __m512i Q1 = _mm512_permutexvar_epi64(pi1, _mm512_rolv_epi64(P1, rho1));
+      const __m512i Q2 = _mm512_permutexvar_epi64(pi2, _mm512_rolv_epi64(P2, rho2));
+      const __m512i Q3 = _mm512_permutexvar_epi64(pi3, _mm512_rolv_epi64(P3, rho3));
+      const __m512i Q4 = _mm512_permutexvar_epi64(pi4, _mm512_rolv_epi64(P4, rho4));
+      // chi is register-wise in this representation: R[X] slot Y = A'[X][Y]; iota on (0, 0)
+      const __m512i R0 = _mm512_xor_si512(_mm512_ternarylogic_epi64(Q0, Q1, Q2, 0xD2), _mm512_load_si512(k.rc[r]));
+      const __m512i R1 = _mm512_ternarylogic_epi64(Q1, Q2, Q3, 0xD2);
+      const __m512i R2 = _mm512_ternarylogic_epi64(Q2, Q3, Q4, 0xD2);
+      const __m512i R3 = _mm512_ternarylogic_epi64(Q3, Q4, Q0, 0xD2);
+      const __m512i R4 = _mm512_ternarylogic_epi64(Q4, Q0, Q1, 0xD2);
+      // transpose back to planes
+      const __m512i W01 = _mm512_permutex2var_epi64(R0, tab, R1), W23 = _mm512_permutex2var_epi64(R2, tab, R3);
+      P0 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq0, W23), 0x10, b0, R4);
+      P1 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq1, W23), 0x10, b1, R4);
+      P2 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq2, W23), 0x10, b2, R4);
+      P3 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq3, W23), 0x10, b3, R4);
+      const __m512i e01 = _mm512_permutex2var_epi64(R0, t4a, R1), e23 = _mm512_permutex2var_epi64(R2, t4b, R3);
+      P4 = _mm512_permutex2var_epi64(_mm512_permutex2var_epi64(e01, t4c, e23), t4d, R4);
+    }
+    // 168 bytes = lanes 0..20: planes 0..3 whole, lane (0, 4)
+    uint8_t *o = out + blk * kXofRate;
+    _mm512_mask_storeu_epi64(o, m5, P0);
+    _mm512_mask_storeu_epi64(o + 40, m5, P1);
+    _mm512_mask_storeu_epi64(o + 80, m5, P2);
+    _mm512_mask_storeu_epi64(o + 120, m5, P3);
+    _mm512_mask_storeu_epi64(o + 160, 0x01, P4);
+  }
+  _mm512_mask_storeu_epi64(s + 0, m5, P0);
+  _mm512_mask_storeu_epi64(s + 5, m5, P1);
+  _mm512_mask_storeu_epi64(s + 10, m5, P2);
+  _mm512_mask_storeu_epi64(s + 15, m5, P3);
+  _mm512_mask_storeu_epi64(s + 20, m5, P4);
+}
+
+bool have_avx512() {
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl");
+  return ok;
+}
+bool have_bmi2() {
+  static const bool ok = __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2");
+  return ok;
+}
+#else
+bool have_avx512() { return false; }
+bool have_bmi2() { return false; }
+#endif
+
+bool run_impl(int impl, uint64_t s[25], uint8_t *out, uint64_t nblocks) {
+  switch (impl) {
+    case kXofScalar: squeeze_scalar(s, out, nblocks); return true;
+#if defined(__x86_64__)
+    case kXofBmi2:
+      if (!have_bmi2()) return false;
+      squeeze_bmi2(s, out, nblocks);
+      return true;
+    case kXofAvx512:
+      if (!have_avx512()) return false;
+      squeeze_avx512(s, out, nblocks);
+      return true;
+#endif
+    default: return false;
+  }
+}
+
+// impl 0: whichever implementation walks the chain fastest on this CPU (measured once, ~1 ms each)
+int best_impl() {
+  static const int best = [] {
+    int win = kXofScalar;
+    double win_t = 1e30;
+    std::vector<uint8_t> buf(2048 * kXofRate);
+    for (int impl : {kXofScalar, kXofBmi2, kXofAvx512}) {
+      uint64_t st[25] = {1, 2, 3};
+      if (!run_impl(impl, st, buf.data(), 64)) continue;  // warm up / availability
+      double t = 1e30;
+      for (int rep = 0; rep < 3; rep++) {
+        const auto t0 = std::chrono::steady_clock::now();
+        run_impl(impl, st, buf.data(), 2048);
+        t = std::min(t, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      }
+      if (t < win_t) win_t = t, win = impl;
+    }
+    return win;
+  }();
+  return best;
+}
+
+}  // namespace
+
+void host_xof_init(HostXof *x, const uint8_t seed[32]) {
+  // absorb(seed) ; finalize::<0x1F>() : pad10*1 over the 168-byte rate; the first permutation happens in the squeeze
+  std::memset(x->s, 0, sizeof x->s);
+  std::memcpy(x->s, seed, 32);
+  x->s[4] ^= 0x1full;
+  x->s[20] ^= 0x80ull << 56;
+}
+
+bool host_xof_squeeze_blocks(HostXof *x, uint8_t *out, uint64_t nblocks, int impl) {
+  return run_impl(impl == kXofAuto ? best_impl() : impl, x->s, out, nblocks);
+}
+
+void host_xof_skip_blocks(HostXof *x, uint64_t nblocks) {
+  // the permutation without the 168-byte copy is not worth a second code path: squeeze into a scratch block
+  uint8_t scratch[64 * kXofRate];
+  const int impl = best_impl();
+  while (nblocks) {
+    const uint64_t n = std::min<uint64_t>(nblocks, 64);
+    run_impl(impl, x->s, scratch, n);
+    nblocks -= n;
+  }
+}
+
+const char *host_xof_impl_name() {
+  switch (best_impl()) {
+    case kXofAvx512: return "avx512";
+    case kXofBmi2: return "bmi2";
+    default: return "scalar";
+  }
+}
+
+}  // namespace chpir

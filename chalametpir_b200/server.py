@@ -106,8 +106,11 @@ class Server:
 
     # ------------------------------------------------------------------ setup
     @staticmethod
-    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0) -> SetupOpts:
-        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc)
+    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0, a_expand="device", host_chunk_rows=0) -> SetupOpts:
+        """a_expand: "device" (default; TurboSHAKE128 chain on one GPU warp) or "host" (one host core squeezes the chain and the
+        uploads + panel GEMMs are pipelined behind it -- same bytes, several times lower setup latency)."""
+        mode = {"device": 0, "host": 1, 0: 0, 1: 1}[a_expand]
+        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc, mode, host_chunk_rows)
 
     @staticmethod
     def setup(seed_mu: bytes, db: Mapping[bytes, bytes], arity: int = 3, *, device: int = 0, filter_seed_rng: Optional[int] = None,
@@ -241,6 +244,20 @@ def generate_from_seed(rows: int, cols: int, seed: bytes, row_begin: int = 0, ro
     s = _seed_arr(seed)
     check(lib.chpir_generate_from_seed(get_ctx(device), s.ctypes.data, rows, cols, row_begin, row_count, out.ctypes.data))
     return out
+
+
+def host_generate_from_seed(rows: int, cols: int, seed: bytes, row_begin: int = 0, row_count: Optional[int] = None, impl: int = 0) -> np.ndarray:
+    """Matrix::generate_from_seed (matrix.rs:541-558) on one host core: the producer of the host-pipelined setup mode
+    (csrc/host_xof.cpp).  impl: 0 = fastest on this CPU, 1 = portable scalar, 2 = BMI2, 3 = AVX-512."""
+    row_count = rows - row_begin if row_count is None else row_count
+    out = np.empty((row_count, cols), dtype=np.uint32)
+    s = _seed_arr(seed)
+    check(lib.chpir_host_generate_from_seed(s.ctypes.data, rows, cols, row_begin, row_count, impl, out.ctypes.data))
+    return out
+
+
+def host_xof_impl() -> str:
+    return lib.chpir_host_xof_impl().decode()
 
 
 def matmul(a: np.ndarray, b: np.ndarray, b_elem_bit_len: int = 32, variant: int = 0, device: int = 0) -> np.ndarray:

@@ -106,7 +106,20 @@ typedef struct chpir_setup_opts {
   uint32_t batch_tc;     /* batched respond on the tensor cores (chpir_server_respond_device_tc): 0 = keep D's byte-limb
                             planes resident iff the hint GEMM built them anyway, 1 = always build and keep them,
                             2 = never keep them (saves 2*K*N bytes of HBM)                                */
+  uint32_t a_expand;     /* where the LWE matrix A = generate_from_seed(lwe_rows, K, seed) (matrix.rs:541-558) is squeezed out of
+                            TurboSHAKE128: CHPIR_A_EXPAND_DEVICE (default) or CHPIR_A_EXPAND_HOST_PIPELINED            */
+  uint32_t host_chunk_rows; /* host-pipelined mode: rows of A per pinned upload chunk; 0 = about 32 MB worth (tests shrink it) */
 } chpir_setup_opts;
+
+/* chpir_setup_opts.a_expand.  The squeeze is ONE serial chain of Keccak-p[1600,12] permutations (49.8 M of them at
+ * 2^20 entries); neither mode changes a single byte of A or of the hint.
+ *   DEVICE:         one warp walks the chain on the GPU and writes the GEMM's byte planes directly (csrc/expand.cu).
+ *   HOST_PIPELINED: one host core walks the chain (csrc/host_xof.cpp) into a ring of pinned chunks that are uploaded and
+ *                   multiplied panel by panel while the core keeps squeezing -- what the reference's own `gpu` feature does
+ *                   with its CPU-side generate_from_seed + upload (server.rs:115-123), but overlapped.  A CPU core runs the
+ *                   chain several times faster than a GPU warp, so this is the low-latency setup. */
+#define CHPIR_A_EXPAND_DEVICE 0u
+#define CHPIR_A_EXPAND_HOST_PIPELINED 1u
 
 /* d_host: K x N row-major u32 (Matrix elems), values < 2^mat_elem_bit_len.
  * hint_out receives the wire-format hint slice: header (lwe_rows, col_count) + lwe_rows*col_count u32; with the
@@ -135,6 +148,8 @@ typedef struct chpir_setup_timing {
   double gemm_s;        /* hint GEMM                                                   */
   double d2h_s;         /* hint download                                               */
   double total_s;
+  double xof_host_busy_s; /* host-pipelined mode: time the producer core spent inside the XOF (0 in device mode); expand_a_s is the
+                             wall time of the whole expansion phase in either mode            */
 } chpir_setup_timing;
 CHPIR_API int chpir_server_setup_timing(const chpir_server *srv, chpir_setup_timing *out);
 
@@ -177,6 +192,14 @@ CHPIR_API int chpir_generate_from_seed(chpir_ctx *ctx, const uint8_t seed[CHPIR_
 /* &A * &D (matrix.rs:1040-1059) on device for host operands; variant as in chpir_setup_opts.gemm_variant. */
 CHPIR_API int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64_t a_cols, const uint32_t *b_host, uint64_t b_rows,
                  uint64_t b_cols, uint32_t b_elem_bit_len, uint32_t variant, uint32_t *out_host);
+/* Matrix::generate_from_seed (matrix.rs:541-558) on a host core (csrc/host_xof.cpp; no GPU involved): rows
+ * [row_begin, row_begin+row_count) of the rows x cols matrix.  impl: 0 = fastest available on this CPU, 1 = portable scalar,
+ * 2 = BMI2 scalar, 3 = AVX-512 (CHPIR_ERR_INVALID_ARGUMENT if the CPU lacks it).  This is the producer of the
+ * host-pipelined setup mode, exposed so that it can be checked against the device expander and the oracle byte for byte. */
+CHPIR_API int chpir_host_generate_from_seed(const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols, uint64_t row_begin,
+                                  uint64_t row_count, uint32_t impl, uint32_t *out_host);
+/* Name of the implementation impl = 0 resolves to on this CPU ("avx512", "bmi2" or "scalar"). */
+CHPIR_API const char *chpir_host_xof_impl(void);
 /* Device time (ms) of the dominant kernels in the last call on this ctx/server, for bench.py's roofline block. */
 CHPIR_API int chpir_server_last_kernel_ms(const chpir_server *srv, float *respond_ms, float *gemm_ms, float *expand_ms);
 

@@ -133,3 +133,45 @@ def test_golden_fixtures_through_the_gpu_path():
         K = case["shape"][0]
         q = np.frombuffer(O.turboshake128(b"q" + seed, 4 * K), dtype="<u4")
         assert hashlib.sha256(srv.respond(O.matrix_to_bytes(q[None, :]))).hexdigest() == case["response_sha256"]
+
+
+# ------------------------------------------------------------------ host-pipelined A expansion (chpir_setup_opts.a_expand)
+@pytest.mark.parametrize("K,N,b,lwe,chunk", [(3000, 100, 9, 200, 0), (1001, 37, 10, 300, 7), (4099, 64, 9, 129, 128), (517, 20, 14, 128, 1)])
+def test_host_pipelined_setup_gives_identical_hint(K, N, b, lwe, chunk):
+    """Same seed, same D: the hint is byte-identical whether the XOF chain is walked by a GPU warp or by a host core
+    (4K is never a multiple of the 168-byte XOF rate here, chunks end mid-block, panels are ragged)."""
+    rng = np.random.default_rng(K + N)
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    srv_h, hint_h = cp.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe, a_expand="host", host_chunk_rows=chunk)
+    srv_d, hint_d = cp.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe, a_expand="device")
+    assert hint_h == hint_d
+    assert hint_h == O.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe, want_server=False)[1]
+    t = srv_h.setup_timing()
+    assert t["xof_host_busy_s"] > 0 and srv_d.setup_timing()["xof_host_busy_s"] == 0
+    q = rand_u32(rng, (1, K))
+    assert srv_h.respond(O.matrix_to_bytes(q)) == srv_d.respond(O.matrix_to_bytes(q))
+
+
+def test_host_pipelined_full_setup_end_to_end():
+    db = make_db(2000, seed=77, val_len=(1, 200))
+    seed = bytes(random.Random(9).randbytes(32))
+    srv, hint, fbytes = cp.Server.setup(seed, db, 3, filter_seed_rng=5, a_expand="host")
+    b = cp.find_mat_elem_bit_len(len(db))
+    D, _ = cp.encode_kv_database(db, b, 3, filter_seed_rng=5)
+    assert hint == O.Server.setup_from_matrix(seed, D, b, want_server=False)[1]
+    client = O.Client.setup(seed, hint, fbytes)
+    done = 0
+    for key in list(db)[:6]:
+        try:
+            q = client.query(key)
+        except O.OracleError:
+            continue
+        assert client.process_response(key, srv.respond(q)) == db[key]
+        done += 1
+    assert done >= 4
+
+
+def test_device_and_host_expanders_agree_deep_in_the_stream():
+    rows, cols = 1774, 20000
+    got = cp.generate_from_seed(rows, cols, SEED, row_begin=rows - 2, row_count=2)
+    assert np.array_equal(got, cp.host_generate_from_seed(rows, cols, SEED, row_begin=rows - 2, row_count=2))
