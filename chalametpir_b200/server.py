@@ -143,6 +143,39 @@ class Server:
         return Server(h, device), hint[: hl.value].tobytes(), fbytes.tobytes()
 
     @staticmethod
+    def setup_from_arrays(seed_mu: bytes, keys: np.ndarray, values: np.ndarray, arity: int = 3, *, device: int = 0,
+                          filter_seed_rng: Optional[int] = None, **opts) -> Tuple["Server", bytes, bytes]:
+        """Server::setup::<ARITY> for a database given as two 2-D uint8 arrays (n x key_len, n x value_len): the same call as
+        :meth:`setup` without materialising a million-entry Python dict (keys must be distinct, as HashMap keys are)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint8)
+        values = np.ascontiguousarray(values, dtype=np.uint8)
+        n = keys.shape[0]
+        if n == 0:
+            raise ChalametPIRError(5)
+        if arity not in (3, 4):
+            raise ChalametPIRError(14)
+        seed = _seed_arr(seed_mu)
+        b = find_mat_elem_bit_len(n)
+        K, N = db_matrix_shape(arity, n, values.shape[1], b)
+        o = Server._opts(**opts)
+        m = o.lwe_rows or LWE_DIMENSION
+        nc = o.col_count or (N - o.col_begin)
+        hint = np.empty(8 + 4 * m * nc, dtype=np.uint8)
+        fbytes = np.empty(FILTER_PARAM_BYTE_LEN, dtype=np.uint8)
+        ko = np.arange(n + 1, dtype=np.uint64) * np.uint64(keys.shape[1])
+        vo = np.arange(n + 1, dtype=np.uint64) * np.uint64(values.shape[1])
+        rng = C.c_uint64(filter_seed_rng) if filter_seed_rng is not None else None
+        h = C.c_void_p()
+        hl = C.c_size_t()
+        check(
+            lib.chpir_server_setup_from_db(
+                get_ctx(device), arity, seed.ctypes.data, n, keys.ctypes.data, ko.ctypes.data, values.ctypes.data, vo.ctypes.data,
+                C.byref(rng) if rng is not None else None, C.byref(o), hint.ctypes.data, hint.nbytes, C.byref(hl), fbytes.ctypes.data, C.byref(h),
+            )
+        )
+        return Server(h, device), hint[: hl.value].tobytes(), fbytes.tobytes()
+
+    @staticmethod
     def setup_from_matrix(seed_mu: bytes, D: np.ndarray, mat_elem_bit_len: int, *, device: int = 0, **opts) -> Tuple["Server", Optional[bytes]]:
         """The device half of setup for an already-encoded D (K x N uint32, host): A expansion, hint GEMM, pack."""
         seed = _seed_arr(seed_mu)

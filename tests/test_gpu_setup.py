@@ -175,3 +175,15 @@ def test_device_and_host_expanders_agree_deep_in_the_stream():
     rows, cols = 1774, 20000
     got = cp.generate_from_seed(rows, cols, SEED, row_begin=rows - 2, row_count=2)
     assert np.array_equal(got, cp.host_generate_from_seed(rows, cols, SEED, row_begin=rows - 2, row_count=2))
+
+
+def test_setup_from_arrays_equals_setup_from_dict():
+    rng = np.random.default_rng(4)
+    n = 1500
+    keys = rng.integers(0, 256, size=(n, 24), dtype=np.uint8)
+    keys[:, :4] = np.arange(n, dtype="<u4").view(np.uint8).reshape(n, 4)
+    vals = rng.integers(0, 256, size=(n, 64), dtype=np.uint8)
+    db = {keys[i].tobytes(): vals[i].tobytes() for i in range(n)}
+    _, h1, f1 = cp.Server.setup(SEED, db, 3, filter_seed_rng=3, lwe_rows=160, a_expand="host", host_chunk_rows=16)
+    _, h2, f2 = cp.Server.setup_from_arrays(SEED, keys, vals, 3, filter_seed_rng=3, lwe_rows=160)
+    assert h1 == h2 and f1 == f2
