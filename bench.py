@@ -45,6 +45,15 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when 
 FALLBACK_BF16_TFLOPS = 1590.0
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def shape_of(log2n: int, arity: int, use_oracle: bool = False):
     """(b, K, N) from the reference's formulas (server.rs:193-218, binary_fuse_filter.rs:52-67/:261-276, matrix.rs:699-700)."""
     n = 1 << log2n
@@ -218,7 +227,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "CPU restatement (oracle/chalamet_oracle.c) of the reference's Server::respond; the Rust reference cannot be built here (no cargo/rustc)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, b, K, N):
@@ -319,6 +328,8 @@ def run_b200(args):
         # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
         from chalametpir_b200 import sharding
 
+        dist.all_reduce(torch.zeros(1, device=dev))  # communicator set-up is not part of the gather
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         H = torch.from_numpy(np.frombuffer(hint, dtype=np.uint8)[8:].view(np.int32).reshape(LWE, nc).copy()).to(dev)
         padw = max(sharding.slice_counts(N, world))
@@ -568,7 +579,7 @@ def run_b200(args):
         "parity": parity,
         "published_reference": {"server_respond_2^20_3wise_ms": {"m8g.8xlarge": 10.06, "m7i.8xlarge": 14.06}, "server_setup_2^20_3wise_s": {"m8g": 577, "m7i": 1282, "g6e(L40S offload)": 25.58}},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -593,6 +604,11 @@ def main():
     ap.add_argument("--cpu-sample-frac", type=int, default=8)
     ap.add_argument("--ref-sample-frac", type=int, default=4)
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints to fd 1 (e.g. NCCL's version banner) goes to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <thread>
@@ -731,6 +732,10 @@ static int server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPI
              CHPIR_ERR_CUDA_TRANSFER_FAILED);
   CHPIR_CUDA(cudaStreamSynchronize(ctx->stream), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   const double t1 = now_s();
+  {
+    double tt = t0;
+    trace_phase("D upload", tt);
+  }
   chpir_server *srv = new chpir_server();
   int rc = setup_core(ctx, seed, d.as<uint32_t>(), rows_k, nc, 0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv, pipe);
   if (rc != CHPIR_OK) {
@@ -777,17 +782,17 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
     if (int rc = pipe.start(ctx->device, seed, m, K, opts->host_chunk_rows, (m + 127) / 128); rc != CHPIR_OK) return rc;
     pipe_p = &pipe;
   }
-  // pinned so the upload is a straight DMA
-  uint32_t *D = nullptr;
-  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMallocHost(&D, K * N * 4) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return CHPIR_ERR_HOST_ALLOCATION_FAILED;
-  }
+  // D lives in pageable memory: pinning 4.4 GB costs ~2 s in cudaMallocHost + cudaFreeHost at 2^20 entries and holds the driver
+  // lock the XOF uploader needs meanwhile; the staged pageable upload is a few tenths of a second
+  std::unique_ptr<uint32_t[]> d_store(new (std::nothrow) uint32_t[K * N]);
+  uint32_t *D = d_store.get();
+  if (!D) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+  if (pipe_p) set_encode_threads(std::max(1u, std::thread::hardware_concurrency()) > 3 ? std::thread::hardware_concurrency() - 2 : 1);
   int rc = encode_kv_database(arity, n, key_blob, key_offsets, value_blob, value_offsets, b, CHPIR_SERVER_SETUP_MAX_ATTEMPT_COUNT,
                               filter_seed_rng, D, filter_params_out);
+  set_encode_threads(0);
   const double t1 = now_s();
   if (rc == CHPIR_OK) rc = server_setup_from_host_matrix(ctx, seed, D, K, uint32_t(N), b, opts, hint_out, hint_cap, hint_len, out, pipe_p);
-  cudaFreeHost(D);
   if (rc == CHPIR_OK) {
     (*out)->timing.host_encode_s = t1 - t0;
     (*out)->timing.total_s += t1 - t0;

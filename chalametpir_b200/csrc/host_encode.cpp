@@ -14,7 +14,10 @@
 // runs in reverse peel order.  The peel itself is the reference's serial stack algorithm.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <random>
@@ -24,6 +27,19 @@
 #include "host_encode.hpp"
 
 namespace chpir {
+
+// CHPIR_TRACE=1 prints the phase split of the host encode to stderr (diagnostics only).
+double trace_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+void trace_phase(const char *name, double &t) {
+  static const bool on = [] {
+    const char *e = std::getenv("CHPIR_TRACE");
+    return e && *e && *e != '0';
+  }();
+  const double now = trace_now();
+  if (on) std::fprintf(stderr, "[chpir] setup(host): %-28s %8.3f ms\n", name, (now - t) * 1e3);
+  t = now;
+}
+
 
 // ------------------------------------------------------------------------------------------------------------
 // TurboSHAKE128 (RFC 9861) for short messages: what the `turboshake` crate =0.4.1 computes at the reference's
@@ -214,9 +230,15 @@ void FilterParams::to_bytes(uint8_t out[68]) const {
 // ------------------------------------------------------------------------------------------------------------
 // parallel helper
 // ------------------------------------------------------------------------------------------------------------
+// worker-thread cap for the calling thread's parallel_for calls (0 = one per hardware thread); Server::setup lowers it while
+// the host XOF producer is running beside the encode so that the serial chain keeps a core to itself
+static thread_local unsigned t_max_threads = 0;
+void set_encode_threads(unsigned n) { t_max_threads = n; }
+
 template <class F>
 static void parallel_for(uint64_t n, uint64_t grain, F &&fn) {
   unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  if (t_max_threads) nt = std::min(nt, t_max_threads);
   nt = static_cast<unsigned>(std::min<uint64_t>(nt, (n + grain - 1) / std::max<uint64_t>(grain, 1)));
   if (nt <= 1) {
     fn(0, n);
@@ -407,6 +429,7 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
   if (b < 4 || b > 14) return CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH;
   if (n > 0xffffffffULL) return CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE;
 
+  double tt = trace_now();
   std::vector<uint8_t> digests(32 * n);
   uint64_t max_vlen = 0;
   for (uint64_t i = 0; i < n; i++) max_vlen = std::max<uint64_t>(max_vlen, val_off[i + 1] - val_off[i]);
@@ -414,8 +437,10 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
     for (uint64_t i = lo; i < hi; i++) key_digest(key_blob + key_off[i], key_off[i + 1] - key_off[i], &digests[32 * i]);
   });
 
+  trace_phase("key digests", tt);
   PeelResult pr;
   if (int rc = peel(arity, digests, n, b, max_attempts, seed_rng, &pr); rc != CHPIR_OK) return rc;
+  trace_phase("peel", tt);
 
   uint64_t K = 0, N = 0;
   db_matrix_shape(arity, n, max_vlen, b, &K, &N);
@@ -431,6 +456,7 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
       encode_row(&digests[32 * key], val_blob + val_off[key], val_off[key + 1] - val_off[key], b, D + uint64_t(s.h[pr.found[i]]) * N, N);
     }
   });
+  trace_phase("zero + own rows", tt);
   // 2. dependent pass in reverse peel order (matrix.rs:707-746 / :839-885).  A slot read here is either final
   //    (its key was peeled later, i.e. handled earlier in this loop) or never owned by any key (all zero), because a
   //    key is peeled only when it is the last one left on its own slot.
@@ -448,6 +474,7 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
       for (uint64_t e = 0; e < N; e++) own[e] = (own[e] - o1[e] - o2[e] - o3[e] - static_cast<uint32_t>(mix(hash, e))) & mask;
     }
   }
+  trace_phase("dependent row fill", tt);
   fp.to_bytes(filter_bytes);
   return CHPIR_OK;
 }

@@ -38,6 +38,10 @@ struct PeelResult {
   std::vector<uint32_t> key_of_order;  // index of the key behind order[i]
 };
 
+// CHPIR_TRACE=1: phase split of the host side of setup on stderr (diagnostics only); t is advanced to now
+double trace_now();
+void trace_phase(const char *name, double &t);
+void set_encode_threads(unsigned n);  // cap on worker threads for this thread's encode calls; 0 = all hardware threads
 void key_digest(const uint8_t *key, size_t len, uint8_t out[32]);
 uint64_t mix(uint64_t key, uint64_t seed);
 uint64_t mix256(const uint8_t digest[32], const uint8_t seed[32]);
