@@ -156,9 +156,10 @@ def test_respond_device_pointers_and_batch():
         assert np.array_equal(got[i], O.matrix_from_bytes(oracle_respond(D, b, Q[i]))[0])
 
 
-@pytest.mark.parametrize("arity,n_log2", [(3, 20), (4, 20)])
+@pytest.mark.parametrize("arity,n_log2", [(3, 18), (3, 20), (4, 20), (3, 22)])
 def test_full_size_respond_properties(arity, n_log2):
-    """BASELINE.json configs 3/4 shapes (2^20 entries, 1 kB values): the oracle cannot stream 4.4 GB in seconds, so the
+    """BASELINE.json configs 2/3/4/5 shapes (2^18, 2^20, 2^22 entries, 1 kB values; at 2^22 K*N = 4.4e9 elements exceeds the
+    reference's own u32 index arithmetic): the oracle cannot stream 4.4 GB in seconds, so the
     full-size run is checked through size-independent properties: unit-vector queries read rows back, an all-ones query
     gives the column sums, a sparse random query equals the hand-computed combination, and respond is linear."""
     import torch
@@ -179,7 +180,10 @@ def test_full_size_respond_properties(arity, n_log2):
         e = np.zeros(K, np.uint32)
         e[k] = 1
         assert np.array_equal(respond(e), D[k].cpu().numpy().view(np.uint32))
-    colsum = (D.to(torch.int64).sum(dim=0) & 0xFFFFFFFF).cpu().numpy().astype(np.uint32)
+    colsum = torch.zeros(N, dtype=torch.int64, device="cuda")
+    for r0 in range(0, K, 1 << 20):  # chunked: an int64 copy of the 2^22 matrix would be 35 GB
+        colsum += D[r0 : r0 + (1 << 20)].sum(dim=0, dtype=torch.int64)
+    colsum = (colsum & 0xFFFFFFFF).cpu().numpy().astype(np.uint32)
     assert np.array_equal(respond(np.ones(K, np.uint32)), colsum)
     idx = rng.choice(K, size=2000, replace=False)
     vals = rand_u32(rng, 2000)
@@ -190,6 +194,36 @@ def test_full_size_respond_properties(arity, n_log2):
     assert np.array_equal(respond(qs), want)
     q1, q2 = rand_u32(rng, K), rand_u32(rng, K)
     assert np.array_equal(respond(q1 + q2), respond(q1) + respond(q2))
+    srv.close()
+
+
+def test_full_size_batched_tensor_core_respond():
+    """BASELINE.json configs[3]: 2^20 entries, 4-wise filter, 64 queries per batch through the int8-limb GEMM.  Checked against
+    the streaming GEMV for every query and, independently of both, through unit-vector and all-ones queries inside the batch."""
+    import torch
+
+    arity, n, nq = 4, 1 << 20, 64
+    b = cp.find_mat_elem_bit_len(n)
+    K, N = cp.db_matrix_shape(arity, n, 1024, b)
+    g = torch.Generator(device="cuda").manual_seed(44)
+    D = torch.randint(0, 1 << b, (K, N), dtype=torch.int32, device="cuda", generator=g)
+    srv, _ = cp.Server.setup_from_device_matrix(SEED, D.data_ptr(), K, N, b, skip_hint=True, batch_tc=1)
+    Q = torch.randint(-(2**31), 2**31, (nq, K), dtype=torch.int32, device="cuda", generator=g)
+    Q[0] = 0
+    Q[0, K - 1] = 1            # unit vector: the response is the last row of D
+    Q[1] = 1                   # all ones: column sums
+    Q[2] = -1                  # all 0xFFFFFFFF: every limb saturated
+    r_tc = torch.empty((nq, N), dtype=torch.int32, device="cuda")
+    r_gv = torch.empty((nq, N), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    srv.respond_device_tc(Q.data_ptr(), nq, r_tc.data_ptr(), st)
+    srv.respond_device(Q.data_ptr(), nq, r_gv.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(r_tc, r_gv)
+    assert torch.equal(r_tc[0], D[K - 1])
+    colsum = D.sum(dim=0, dtype=torch.int64)
+    assert torch.equal(r_tc[1].to(torch.int64) & 0xFFFFFFFF, colsum & 0xFFFFFFFF)
+    assert torch.equal(r_tc[2].to(torch.int64) & 0xFFFFFFFF, (-colsum) & 0xFFFFFFFF)
     srv.close()
 
 

@@ -187,3 +187,29 @@ def test_setup_from_arrays_equals_setup_from_dict():
     _, h1, f1 = cp.Server.setup(SEED, db, 3, filter_seed_rng=3, lwe_rows=160, a_expand="host", host_chunk_rows=16)
     _, h2, f2 = cp.Server.setup_from_arrays(SEED, keys, vals, 3, filter_seed_rng=3, lwe_rows=160)
     assert h1 == h2 and f1 == f2
+
+
+def test_full_size_setup_hint_rows():
+    """BASELINE.json configs[2] (2^20 entries, 3-wise): the whole Server::setup on the full shape, host-pipelined A.  The oracle
+    cannot multiply 1774 x 1.18M x 940 in seconds, so the hint is checked on its first two and its LAST row (the tail of the
+    8.4 GB XOF stream, walked independently by the oracle) against exact dot products on sampled columns."""
+    import torch
+
+    n, arity = 1 << 20, 3
+    b = cp.find_mat_elem_bit_len(n)
+    K, N = cp.db_matrix_shape(arity, n, 1024, b)
+    g = torch.Generator(device="cuda").manual_seed(20)
+    D = torch.randint(0, 1 << b, (K, N), dtype=torch.int32, device="cuda", generator=g)
+    srv, hint = cp.Server.setup_from_device_matrix(SEED, D.data_ptr(), K, N, b, a_expand="host", batch_tc=2)
+    H = O.matrix_from_bytes(hint)
+    assert H.shape == (cp.LWE_DIMENSION, N)
+    cols = [0, 1, 7, N // 2, N - 2, N - 1]
+    Dc = D[:, cols].cpu().numpy().astype(np.uint64)
+    for r0, nr in ((0, 2), (cp.LWE_DIMENSION - 1, 1)):
+        a = O.generate_rows_from_seed(K, SEED, r0, nr).astype(np.uint64)
+        lo, hi = a & 0xFFFF, a >> 16
+        want = ((lo @ Dc) + (((hi @ Dc) & 0xFFFF) << 16)) & 0xFFFFFFFF
+        assert np.array_equal(H[r0 : r0 + nr][:, cols].astype(np.uint64), want), r0
+    t = srv.setup_timing()
+    assert t["expand_a_s"] < 60
+    srv.close()
