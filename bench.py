@@ -322,11 +322,22 @@ def run_b200(args):
         srv_e, hint_e, fb_e = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=7, batch_tc=2, a_expand="host")
         wall_e = time.perf_counter() - t0
         te = srv_e.setup_timing()
+        # the same with the row encoding + dependent fill on the GPU (values uploaded instead of D): identical hint and filter bytes
+        del srv_e
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        srv_g, hint_g, fb_g = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=7, batch_tc=2, a_expand="host",
+                                                          db_encode="device")
+        wall_g = time.perf_counter() - t0
+        tg = srv_g.setup_timing()
+        assert hint_g == hint_e and fb_g == fb_e, "device row fill changed the hint or the filter parameters"
+        del srv_g, hint_g
         # spot check on the real D: rows 0..1 of the hint against the exact product with the head of the XOF stream
         setup["e2e_from_db"] = {"api": "chpir_server_setup_from_db (keys + values in host memory -> resident server + hint + filter params)",
                                 "wall_s": wall_e, **{k: round(v, 6) for k, v in te.items()}, "a_expand": "host", "db_entries": n_db, "key_bytes": 32,
-                                "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e)}
-        del srv_e, hint_e, keys, vals
+                                "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e),
+                                "with_device_row_fill": {"wall_s": wall_g, **{k: round(v, 6) for k, v in tg.items()}, "identical_hint_and_filter_bytes": True}}
+        del hint_e, keys, vals
     if world > 1 and hint is not None:
         # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
         from chalametpir_b200 import sharding

@@ -11,6 +11,7 @@ from .server import (
     db_matrix_shape,
     device_count,
     encode_kv_database,
+    encode_kv_database_device,
     find_mat_elem_bit_len,
     generate_from_seed,
     get_ctx,
@@ -30,6 +31,7 @@ __all__ = [
     "db_matrix_shape",
     "device_count",
     "encode_kv_database",
+    "encode_kv_database_device",
     "find_mat_elem_bit_len",
     "generate_from_seed",
     "get_ctx",

@@ -27,6 +27,7 @@ class SetupOpts(C.Structure):
         ("batch_tc", C.c_uint32),
         ("a_expand", C.c_uint32),
         ("host_chunk_rows", C.c_uint32),
+        ("db_encode", C.c_uint32),
     ]
 
 
@@ -35,7 +36,7 @@ A_EXPAND_HOST_PIPELINED = 1
 
 
 class SetupTiming(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("host_encode_s", "h2d_s", "pack_s", "expand_a_s", "gemm_s", "d2h_s", "total_s", "xof_host_busy_s")]
+    _fields_ = [(n, C.c_double) for n in ("host_encode_s", "h2d_s", "pack_s", "expand_a_s", "gemm_s", "d2h_s", "total_s", "device_encode_s", "xof_host_busy_s")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,6 +64,7 @@ EXPORTS = [
     "chpir_find_mat_elem_bit_len",
     "chpir_db_matrix_shape",
     "chpir_encode_kv_database",
+    "chpir_encode_kv_database_device",
     "chpir_server_setup",
     "chpir_server_setup_device",
     "chpir_server_setup_from_db",
@@ -102,6 +104,7 @@ lib.chpir_ctx_destroy.argtypes = [_vp]
 lib.chpir_find_mat_elem_bit_len.argtypes = [C.c_uint64, C.POINTER(C.c_uint32)]
 lib.chpir_db_matrix_shape.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 lib.chpir_encode_kv_database.argtypes = [C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), _vp, _vp]
+lib.chpir_encode_kv_database_device.argtypes = [_vp, C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), _vp, _vp]
 lib.chpir_server_setup.argtypes = [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(SetupOpts), _vp, C.c_size_t, _szp, C.POINTER(_vp)]
 lib.chpir_server_setup_device.argtypes = lib.chpir_server_setup.argtypes
 lib.chpir_server_setup_from_db.argtypes = [

@@ -561,6 +561,67 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   return CHPIR_OK;
 }
 
+// Matrix::from_kv_database::<ARITY> with the row fill on the GPU: host = key digests + filter construction + wave plan, device =
+// row encoding + dependent fill.  d_out receives the K x N u32 matrix in HBM (the caller's stream `st` is synchronised on return).
+int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off,
+                              const uint8_t *val_blob, const uint64_t *val_off, uint32_t b, uint32_t max_attempts, const uint64_t *seed_rng,
+                              uint64_t K, uint64_t N, DevBuf *d_out, uint8_t filter_bytes[68], double *host_s, double *device_s) {
+  cudaStream_t st = ctx->stream;
+  const double t0 = now_s();
+  // D is allocated and cleared first so the memset runs under the host-side filter construction
+  if (int rc = d_out->alloc(K * N * 4); rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemsetAsync(d_out->p, 0, K * N * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  DevBuf d_values, d_valoff;
+  const uint64_t val_bytes = val_off[n];
+  if (int rc = d_values.alloc(val_bytes); rc != CHPIR_OK) return rc;
+  if (int rc = d_valoff.alloc((n + 1) * 8); rc != CHPIR_OK) return rc;
+  // values do not depend on the filter: their upload (pageable memory, staged by the driver) also precedes the peeling
+  CHPIR_CUDA(cudaMemcpyAsync(d_valoff.p, val_off, (n + 1) * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  if (val_bytes) CHPIR_CUDA(cudaMemcpyAsync(d_values.p, val_blob, val_bytes, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  double tt = trace_now();
+  trace_phase("values upload (enqueue)", tt);
+  std::vector<uint8_t> digests;
+  PeelResult pr;
+  if (int rc = digest_and_peel(arity, n, key_blob, key_off, b, max_attempts, seed_rng, &digests, &pr); rc != CHPIR_OK) return rc;
+  tt = trace_now();
+  FillPlan plan;
+  plan_fill_levels(arity, pr, &plan);
+  trace_phase("fill wave plan", tt);
+  const uint32_t waves = uint32_t(plan.level_start.size() - 1);
+  DevBuf d_members, d_order, d_found, d_koo, d_digests;
+  if (int rc = d_members.alloc(n * 4); rc != CHPIR_OK) return rc;
+  if (int rc = d_order.alloc(n * 8); rc != CHPIR_OK) return rc;
+  if (int rc = d_found.alloc(n); rc != CHPIR_OK) return rc;
+  if (int rc = d_koo.alloc(n * 4); rc != CHPIR_OK) return rc;
+  if (int rc = d_digests.alloc(n * 32); rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemcpyAsync(d_members.p, plan.members.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_order.p, pr.order.data(), n * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_found.p, pr.found.data(), n, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_koo.p, pr.key_of_order.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_digests.p, digests.data(), n * 32, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  const double t1 = now_s();
+  EventTimer t_fill;
+  t_fill.start(st);
+  if (int rc = launch_device_row_fill(arity, d_members.as<uint32_t>(), plan.level_start.data(), waves, d_order.as<uint64_t>(),
+                                      d_found.as<uint8_t>(), d_koo.as<uint32_t>(), d_digests.as<uint8_t>(), d_values.as<uint8_t>(),
+                                      d_valoff.as<uint64_t>(), d_out->as<uint32_t>(), N, b, pr.params.segment_length,
+                                      pr.params.segment_count_length, st);
+      rc != CHPIR_OK)
+    return rc;
+  t_fill.stop(st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "device row fill");
+    return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+  }
+  trace_phase("device row fill (waves)", tt);
+  pr.params.to_bytes(filter_bytes);
+  if (host_s) *host_s = t1 - t0;
+  if (device_s) *device_s = t_fill.ms() * 1e-3;
+  (void)waves;
+  return CHPIR_OK;
+}
+
 int resolve_slice(const chpir_setup_opts &o, uint32_t N, uint32_t *c0, uint32_t *nc) {
   *c0 = o.col_begin;
   *nc = o.col_count ? o.col_count : (N > o.col_begin ? N - o.col_begin : 0);
@@ -681,6 +742,27 @@ int chpir_encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob
   CHPIR_GUARD_END
 }
 
+int chpir_encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_offsets,
+                                    const uint8_t *value_blob, const uint64_t *value_offsets, uint32_t b, uint32_t max_attempt_count,
+                                    const uint64_t *filter_seed_rng, uint32_t *d_out, uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN]) {
+  CHPIR_GUARD_BEGIN
+  if (n == 0) return CHPIR_ERR_EMPTY_KV_DATABASE;
+  if (!ctx || !key_blob || !key_offsets || !value_blob || !value_offsets || !d_out || !filter_params_out) return CHPIR_ERR_INVALID_ARGUMENT;
+  uint64_t max_vlen = 0, K = 0, N = 0;
+  for (uint64_t i = 0; i < n; i++) max_vlen = std::max<uint64_t>(max_vlen, value_offsets[i + 1] - value_offsets[i]);
+  if (int rc = db_matrix_shape(arity, n, max_vlen, b, &K, &N); rc != CHPIR_OK) return rc;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  DevBuf d;
+  if (int rc = encode_kv_database_device(ctx, arity, n, key_blob, key_offsets, value_blob, value_offsets, b, max_attempt_count, filter_seed_rng, K, N,
+                                         &d, filter_params_out, nullptr, nullptr);
+      rc != CHPIR_OK)
+    return rc;
+  CHPIR_CUDA(cudaMemcpy(d_out, d.p, K * N * 4, cudaMemcpyDeviceToHost), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
 int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k,
                               uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
                               size_t *hint_len, chpir_server **out) {
@@ -781,6 +863,33 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
     const uint32_t m = opts->lwe_rows ? opts->lwe_rows : CHPIR_LWE_DIMENSION;
     if (int rc = pipe.start(ctx->device, seed, m, K, opts->host_chunk_rows, (m + 127) / 128); rc != CHPIR_OK) return rc;
     pipe_p = &pipe;
+  }
+  if (opts && opts->db_encode == CHPIR_DB_ENCODE_DEVICE) {
+    // row encoding + dependent fill on the GPU: D is born in HBM, the host never holds it
+    chpir_setup_opts o = *opts;
+    uint32_t c0, nc;
+    if (int rc = resolve_slice(o, uint32_t(N), &c0, &nc); rc != CHPIR_OK) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    if (pipe_p) set_encode_threads(std::max(1u, std::thread::hardware_concurrency()) > 3 ? std::thread::hardware_concurrency() - 2 : 1);
+    DevBuf d;
+    double enc_host_s = 0, enc_dev_s = 0;
+    int rc = encode_kv_database_device(ctx, arity, n, key_blob, key_offsets, value_blob, value_offsets, b, CHPIR_SERVER_SETUP_MAX_ATTEMPT_COUNT,
+                                       filter_seed_rng, K, N, &d, filter_params_out, &enc_host_s, &enc_dev_s);
+    set_encode_threads(0);
+    if (rc != CHPIR_OK) return rc;
+    const double t1 = now_s();
+    chpir_server *srv = new chpir_server();
+    rc = setup_core(ctx, seed, d.as<uint32_t>(), K, uint32_t(N), c0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv, pipe_p);
+    if (rc != CHPIR_OK) {
+      delete srv;
+      return rc;
+    }
+    srv->timing.host_encode_s = t1 - t0;
+    srv->timing.device_encode_s = enc_dev_s;
+    srv->timing.total_s = now_s() - t0;
+    *out = srv;
+    return CHPIR_OK;
   }
   // D lives in pageable memory: pinning 4.4 GB costs ~2 s in cudaMallocHost + cudaFreeHost at 2^20 entries and holds the driver
   // lock the XOF uploader needs meanwhile; the staged pageable upload is a few tenths of a second

@@ -386,6 +386,37 @@ int peel(uint32_t arity, const std::vector<uint8_t> &digests, uint64_t n, uint32
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// dependency levels of the row fill (matrix.rs:707-746 / :839-885 walk the keys in reverse peel order)
+// ------------------------------------------------------------------------------------------------------------
+// Key i's row is  own = enc(i) - sum(rows of its other slots) - mix(hash, e).  A slot it reads is either never owned (all zero)
+// or owned by a key that was peeled LATER (a key is peeled only when it is alone on its slot), so the reverse peel order is one
+// valid schedule -- but not the only one: level(i) = 1 + max(level of the owners of i's other slots) groups the keys into waves
+// whose members are independent of each other.  The waves are what a parallel (GPU) row fill executes.
+void plan_fill_levels(uint32_t arity, const PeelResult &pr, FillPlan *plan) {
+  const FilterParams &fp = pr.params;
+  const uint64_t n = pr.order.size();
+  std::vector<uint32_t> slot_level(fp.num_fingerprints, 0);  // level of the key that owns the slot, 0 = not owned (yet)
+  std::vector<uint32_t> level(n);
+  uint32_t max_level = 0;
+  for (uint64_t i = n; i-- > 0;) {
+    const Slots s = slots_of(arity, pr.order[i], fp.segment_length, fp.segment_count_length);
+    const uint32_t which = pr.found[i];
+    uint32_t l = 0;
+    for (uint32_t step = 1; step < arity; step++) l = std::max(l, slot_level[s.h[(which + step) % arity]]);
+    level[i] = l + 1;
+    slot_level[s.h[which]] = l + 1;
+    max_level = std::max(max_level, l + 1);
+  }
+  std::vector<uint32_t> counts(size_t(max_level) + 1, 0);
+  for (uint64_t i = 0; i < n; i++) counts[level[i]]++;
+  plan->level_start.assign(size_t(max_level) + 1, 0);
+  for (uint32_t l = 1; l <= max_level; l++) plan->level_start[l] = plan->level_start[l - 1] + counts[l];
+  plan->members.resize(n);
+  std::vector<uint32_t> cursor(plan->level_start.begin(), plan->level_start.end() - 1);
+  for (uint64_t i = 0; i < n; i++) plan->members[cursor[level[i] - 1]++] = static_cast<uint32_t>(i);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // row codec (serialization.rs:22-116): digest || value || 0x81, LSB-first b-bit fields
 // ------------------------------------------------------------------------------------------------------------
 namespace {
@@ -421,6 +452,25 @@ void encode_row(const uint8_t digest[32], const uint8_t *value, size_t vlen, uin
 // ------------------------------------------------------------------------------------------------------------
 // Matrix::from_kv_database
 // ------------------------------------------------------------------------------------------------------------
+// key digests (serialization.rs:24-29 / binary_fuse_filter.rs:569-574) + filter construction: the part of the encode that
+// stays on the host in every mode
+int digest_and_peel(uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off, uint32_t b, uint32_t max_attempts,
+                    const uint64_t *seed_rng, std::vector<uint8_t> *digests, PeelResult *pr) {
+  if (arity != 3 && arity != 4) return CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER;
+  if (n == 0) return CHPIR_ERR_EMPTY_KV_DATABASE;
+  if (b < 4 || b > 14) return CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH;
+  if (n > 0xffffffffULL) return CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE;
+  double tt = trace_now();
+  digests->resize(32 * n);
+  parallel_for(n, 1 << 12, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) key_digest(key_blob + key_off[i], key_off[i + 1] - key_off[i], &(*digests)[32 * i]);
+  });
+  trace_phase("key digests", tt);
+  const int rc = peel(arity, *digests, n, b, max_attempts, seed_rng, pr);
+  trace_phase("peel", tt);
+  return rc;
+}
+
 int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off, const uint8_t *val_blob,
                        const uint64_t *val_off, uint32_t b, uint32_t max_attempts, const uint64_t *seed_rng, uint32_t *D,
                        uint8_t filter_bytes[68]) {
@@ -430,17 +480,11 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
   if (n > 0xffffffffULL) return CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE;
 
   double tt = trace_now();
-  std::vector<uint8_t> digests(32 * n);
+  std::vector<uint8_t> digests;
   uint64_t max_vlen = 0;
   for (uint64_t i = 0; i < n; i++) max_vlen = std::max<uint64_t>(max_vlen, val_off[i + 1] - val_off[i]);
-  parallel_for(n, 1 << 12, [&](uint64_t lo, uint64_t hi) {
-    for (uint64_t i = lo; i < hi; i++) key_digest(key_blob + key_off[i], key_off[i + 1] - key_off[i], &digests[32 * i]);
-  });
-
-  trace_phase("key digests", tt);
   PeelResult pr;
-  if (int rc = peel(arity, digests, n, b, max_attempts, seed_rng, &pr); rc != CHPIR_OK) return rc;
-  trace_phase("peel", tt);
+  if (int rc = digest_and_peel(arity, n, key_blob, key_off, b, max_attempts, seed_rng, &digests, &pr); rc != CHPIR_OK) return rc;
 
   uint64_t K = 0, N = 0;
   db_matrix_shape(arity, n, max_vlen, b, &K, &N);
@@ -475,6 +519,15 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
     }
   }
   trace_phase("dependent row fill", tt);
+  if (std::getenv("CHPIR_TRACE_LEVELS")) {
+    FillPlan plan;
+    plan_fill_levels(arity, pr, &plan);
+    trace_phase("plan_fill_levels", tt);
+    const size_t L = plan.level_start.size() - 1;
+    uint32_t big = 0;
+    for (size_t l = 0; l < L; l++) big = std::max(big, plan.level_start[l + 1] - plan.level_start[l]);
+    std::fprintf(stderr, "[chpir] fill waves: %zu, largest %u, mean %.1f\n", L, big, double(n) / double(L));
+  }
   fp.to_bytes(filter_bytes);
   return CHPIR_OK;
 }

@@ -41,6 +41,15 @@ struct PeelResult {
 // CHPIR_TRACE=1: phase split of the host side of setup on stderr (diagnostics only); t is advanced to now
 double trace_now();
 void trace_phase(const char *name, double &t);
+// Waves of mutually independent keys for the dependent row fill: members[level_start[l] .. level_start[l+1]) are the peel-order
+// indices i of wave l (0-based); wave l only reads rows written by waves < l.
+struct FillPlan {
+  std::vector<uint32_t> level_start;
+  std::vector<uint32_t> members;
+};
+void plan_fill_levels(uint32_t arity, const PeelResult &pr, FillPlan *plan);
+int digest_and_peel(uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off, uint32_t b, uint32_t max_attempts,
+                    const uint64_t *seed_rng, std::vector<uint8_t> *digests, PeelResult *pr);
 void set_encode_threads(unsigned n);  // cap on worker threads for this thread's encode calls; 0 = all hardware threads
 void key_digest(const uint8_t *key, size_t len, uint8_t out[32]);
 uint64_t mix(uint64_t key, uint64_t seed);

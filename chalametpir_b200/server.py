@@ -89,6 +89,28 @@ def encode_kv_database(db: Mapping[bytes, bytes], mat_elem_bit_len: int, arity: 
     return D, fbytes.tobytes()
 
 
+def encode_kv_database_device(db: Mapping[bytes, bytes], mat_elem_bit_len: int, arity: int = 3, max_attempt_count: int = 100,
+                              filter_seed_rng: Optional[int] = None, device: int = 0):
+    """Matrix::from_kv_database::<ARITY> with the row encoding and the dependent fill on the GPU (csrc/encode_dev.cu); returns the
+    downloaded (D, filter_param_bytes) so that it can be compared with :func:`encode_kv_database` byte for byte."""
+    if len(db) == 0:
+        raise ChalametPIRError(5)
+    keys, vals = list(db.keys()), list(db.values())
+    K, N = db_matrix_shape(arity, len(keys), max(len(v) for v in vals), mat_elem_bit_len)
+    kb, ko = _flatten(keys)
+    vb, vo = _flatten(vals)
+    D = np.empty((K, N), dtype=np.uint32)
+    fbytes = np.empty(FILTER_PARAM_BYTE_LEN, dtype=np.uint8)
+    rng = C.c_uint64(filter_seed_rng) if filter_seed_rng is not None else None
+    check(
+        lib.chpir_encode_kv_database_device(
+            get_ctx(device), arity, len(keys), kb.ctypes.data, ko.ctypes.data, vb.ctypes.data, vo.ctypes.data, mat_elem_bit_len, max_attempt_count,
+            C.byref(rng) if rng is not None else None, D.ctypes.data, fbytes.ctypes.data,
+        )
+    )
+    return D, fbytes.tobytes()
+
+
 class Server:
     """The PIR server: bit-packed D resident in HBM on one GPU (optionally a column slice of it)."""
 
@@ -106,11 +128,13 @@ class Server:
 
     # ------------------------------------------------------------------ setup
     @staticmethod
-    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0, a_expand="device", host_chunk_rows=0) -> SetupOpts:
+    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0, a_expand="device", host_chunk_rows=0,
+              db_encode="host") -> SetupOpts:
         """a_expand: "device" (default; TurboSHAKE128 chain on one GPU warp) or "host" (one host core squeezes the chain and the
         uploads + panel GEMMs are pipelined behind it -- same bytes, several times lower setup latency)."""
         mode = {"device": 0, "host": 1, 0: 0, 1: 1}[a_expand]
-        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc, mode, host_chunk_rows)
+        enc = {"host": 0, "device": 1, 0: 0, 1: 1}[db_encode]  # setup / setup_from_arrays only: where the rows of D are encoded and filled
+        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc, mode, host_chunk_rows, enc)
 
     @staticmethod
     def setup(seed_mu: bytes, db: Mapping[bytes, bytes], arity: int = 3, *, device: int = 0, filter_seed_rng: Optional[int] = None,

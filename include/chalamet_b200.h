@@ -94,6 +94,13 @@ CHPIR_API int chpir_encode_kv_database(uint32_t arity, uint64_t db_entry_count, 
                              uint32_t max_attempt_count, const uint64_t *filter_seed_rng, uint32_t *d_out,
                              uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN]);
 
+/* The same matrix and filter parameters with the row encoding and the dependent fill done on the GPU (csrc/encode_dev.cu); D is
+ * downloaded into d_out so that the two encoders can be compared byte for byte. */
+CHPIR_API int chpir_encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t db_entry_count, const uint8_t *key_blob,
+                                    const uint64_t *key_offsets, const uint8_t *value_blob, const uint64_t *value_offsets,
+                                    uint32_t mat_elem_bit_len, uint32_t max_attempt_count, const uint64_t *filter_seed_rng, uint32_t *d_out,
+                                    uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN]);
+
 /* ---- setup: replaces generate_from_seed + transfer_mat_to_device + mat_x_mat + mat_transpose + row_wise_compress
  *      (server.rs:115-156, gpu_utils.rs:81-281, shaders/mat_x_mat.glsl, shaders/mat_transpose.glsl,
  *      matrix.rs:98-205, :517-558, :1040-1059) ------------------------------------------------------------- */
@@ -109,7 +116,17 @@ typedef struct chpir_setup_opts {
   uint32_t a_expand;     /* where the LWE matrix A = generate_from_seed(lwe_rows, K, seed) (matrix.rs:541-558) is squeezed out of
                             TurboSHAKE128: CHPIR_A_EXPAND_DEVICE (default) or CHPIR_A_EXPAND_HOST_PIPELINED            */
   uint32_t host_chunk_rows; /* host-pipelined mode: rows of A per pinned upload chunk; 0 = about 32 MB worth (tests shrink it) */
+  uint32_t db_encode;    /* chpir_server_setup_from_db only: where the rows of D are encoded and filled, CHPIR_DB_ENCODE_HOST
+                            (default, north_star) or CHPIR_DB_ENCODE_DEVICE                                            */
 } chpir_setup_opts;
+
+/* chpir_setup_opts.db_encode.  Key digests and filter construction (peeling) always run on the host.
+ *   HOST:   encode_kv_as_row + the dependent row fill of Matrix::from_kv_database run on the host (csrc/host_encode.cpp) and the
+ *           K x N u32 matrix D (4.4 GB at 2^20 entries) is uploaded;
+ *   DEVICE: the raw values (1.1 GB) are uploaded and D is built in HBM by csrc/encode_dev.cu, wave by wave in the dependency
+ *           order the peeling implies -- the same D, byte for byte. */
+#define CHPIR_DB_ENCODE_HOST 0u
+#define CHPIR_DB_ENCODE_DEVICE 1u
 
 /* chpir_setup_opts.a_expand.  The squeeze is ONE serial chain of Keccak-p[1600,12] permutations (49.8 M of them at
  * 2^20 entries); neither mode changes a single byte of A or of the hint.
@@ -148,6 +165,7 @@ typedef struct chpir_setup_timing {
   double gemm_s;        /* hint GEMM                                                   */
   double d2h_s;         /* hint download                                               */
   double total_s;
+  double device_encode_s; /* db_encode = DEVICE: device time of the row-fill waves (part of host_encode_s's wall time) */
   double xof_host_busy_s; /* host-pipelined mode: time the producer core spent inside the XOF (0 in device mode); expand_a_s is the
                              wall time of the whole expansion phase in either mode            */
 } chpir_setup_timing;

@@ -213,3 +213,42 @@ def test_full_size_setup_hint_rows():
     t = srv.setup_timing()
     assert t["expand_a_s"] < 60
     srv.close()
+
+
+# ------------------------------------------------------------------ row encoding + dependent fill on the GPU (db_encode = "device")
+@pytest.mark.parametrize("arity", [3, 4])
+@pytest.mark.parametrize("n,val_len", [(1, (5, 5)), (2, (0, 3)), (7, (1, 40)), (300, (0, 120)), (5000, (1, 64)), (20000, (900, 1024))])
+def test_device_row_fill_is_byte_identical_to_host_encode(arity, n, val_len):
+    """Matrix::from_kv_database (matrix.rs:687-755 / :819-894): D built in HBM wave by wave == D built by the host encoder ==
+    the oracle's, for every legal element width, ragged and empty values included; filter parameters identical."""
+    db = make_db(n, seed=n + arity, val_len=val_len)
+    for b in sorted({4, 9, 10, 14, O.find_mat_elem_bit_len(n)}):
+        Dd, fd = cp.encode_kv_database_device(db, b, arity, filter_seed_rng=n)
+        Dh, fh = cp.encode_kv_database(db, b, arity, filter_seed_rng=n)
+        assert fd == fh
+        assert np.array_equal(Dd, Dh), (arity, n, b)
+    if n <= 5000:
+        Do, fo = O.from_kv_database(db, b, arity, rng_seed=n)
+        assert fd == fo.to_bytes() and np.array_equal(Dd, Do)
+
+
+@pytest.mark.parametrize("arity", [3, 4])
+def test_setup_with_device_row_fill_end_to_end(arity):
+    db = make_db(4000, seed=arity + 100, val_len=(1, 256))
+    seed = bytes(random.Random(arity + 5).randbytes(32))
+    srv, hint, fbytes = cp.Server.setup(seed, db, arity, filter_seed_rng=8, db_encode="device", a_expand="host")
+    srv2, hint2, fbytes2 = cp.Server.setup(seed, db, arity, filter_seed_rng=8)
+    assert hint == hint2 and fbytes == fbytes2
+    client = O.Client.setup(seed, hint, fbytes)
+    done = 0
+    for key in list(db)[:8]:
+        try:
+            q = client.query(key)
+        except O.OracleError:
+            continue
+        r = srv.respond(q)
+        assert r == srv2.respond(q)
+        assert client.process_response(key, r) == db[key]
+        done += 1
+    assert done >= 5
+    assert srv.setup_timing()["device_encode_s"] > 0
