@@ -277,7 +277,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     srv, hint = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, skip_hint=args.skip_hint,
-                                                   batch_tc=0 if args.no_batch_tc else 1, a_expand="host" if args.a_expand == "host" else "device")
+                                                   batch_tc=0 if args.no_batch_tc else 1, a_expand="host" if args.a_expand == "host" else "device",
+                                                   respond_coalesce=not args.no_coalesce)
     setup_wall = time.perf_counter() - t0
     tm = srv.setup_timing()
     km = srv.last_kernel_ms()
@@ -459,8 +460,11 @@ def run_b200(args):
 
     # ---------------- e2e: C ABI with host (pinned) buffers, `--e2e-threads` concurrent callers as Arc<Server> sharing allows
     qlen, rlen = 8 + 4 * K, 8 + 4 * nc
-    q_host = torch.empty((Q, qlen), dtype=torch.uint8).pin_memory()
-    r_host = torch.empty((Q, rlen), dtype=torch.uint8).pin_memory()
+    # page-locked through the library (cudaHostAlloc): on this box copies from torch's pin_memory() buffers ran at 16-28 GB/s for
+    # 5-75 MB transfers against 52-55 GB/s from cudaHostAlloc memory (tools/h2d_probe.*)
+    q_pin, r_pin = cp.PinnedBuffer(Q * qlen), cp.PinnedBuffer(Q * rlen)
+    q_host = torch.from_numpy(q_pin.array).view(Q, qlen)
+    r_host = torch.from_numpy(r_pin.array).view(Q, rlen)
     qh_np = q_host.numpy()
     hdr = np.array([1, K], dtype="<u4").view(np.uint8)
     qcpu = q_dev.cpu().numpy().view(np.uint8).reshape(Q, 4 * K)
@@ -468,13 +472,16 @@ def run_b200(args):
         qh_np[i, :8] = hdr
         qh_np[i, 8:] = qcpu[i]
 
-    def e2e_step():
-        nthreads = max(1, min(args.e2e_threads, Q))
+    def e2e_steps_single(n):
+        """n steps = n*Q calls of chpir_server_respond from `--e2e-threads` concurrent callers (the reference shares Arc<Server>
+        across tasks the same way, examples/server.rs:45-85); caller t answers queries t, t+T, t+2T, ... of the n*Q."""
+        nthreads = max(1, min(args.e2e_threads, n * Q))
         errs = []
 
         def work(tid):
             try:
-                for i in range(tid, Q, nthreads):
+                for j in range(tid, n * Q, nthreads):
+                    i = j % Q
                     srv.respond_into(q_host[i].data_ptr(), qlen, r_host[i].data_ptr(), rlen)
             except Exception as ex:  # pragma: no cover
                 errs.append(ex)
@@ -541,9 +548,7 @@ def run_b200(args):
                         r_all_host[p].copy_(gather_bufs[p], non_blocking=True)
             torch.cuda.synchronize()
     else:
-        def e2e_steps(n):
-            for _ in range(n):
-                e2e_step()
+        e2e_steps = e2e_steps_single
 
     e2e_steps(max(args.warmup, 3))
     barrier()
@@ -636,7 +641,13 @@ def run_b200(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, b, K, N),
         "e2e": ({"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * qlen, "d2h_bytes_per_step": Q * rlen,
-                 "threads": max(1, min(args.e2e_threads, Q)), "api": "chpir_server_respond (C ABI, pinned host buffers)"} if world == 1 else
+                 "threads": max(1, min(args.e2e_threads, args.steps * Q)), "coalesced": not args.no_coalesce,
+                 "pcie_bound_queries_per_s": 52.0e9 / qlen,
+                 "note": "with coalescing, whoever arrives while a batch is on the GPU shares ONE tensor-core pass over D (6..128 queries), so e2e is "
+                         "bounded by the H2D of 4.7 MB per query (52 GB/s measured, tools/h2d_probe.cu), not by `value`, which streams D once "
+                         "PER query (the HBM-roofline GEMV north_star names)",
+                 "api": "chpir_server_respond (C ABI, pinned host buffers), concurrent callers" +
+                        ("" if args.no_coalesce else " coalesced into shared launches (respond_coalesce = 1)")} if world == 1 else
                 {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * 4 * K, "d2h_bytes_per_step": world * Q * pad * 4, "threads": 1,
                  "api": "pinned host queries -> per-rank H2D of a K/N slice -> NCCL all-gather -> chpir_server_respond_device -> NCCL gather -> D2H on rank 0",
                  "h2d_bytes_per_step_per_rank": Q * 4 * (-(-K // world))}),
@@ -664,7 +675,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--arity", type=int, default=3, choices=[3, 4])
     ap.add_argument("--queries-per-step", type=int, default=16)
-    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--e2e-threads", type=int, default=32, help="concurrent callers of chpir_server_respond in the e2e leg (N = 1)")
+    ap.add_argument("--no-coalesce", action="store_true", help="e2e leg: do not coalesce concurrent respond calls into shared launches")
     ap.add_argument("--skip-hint", action="store_true", help="make D resident only (no A expansion / hint GEMM) -- development shortcut")
     ap.add_argument("--a-expand", default="both", choices=["device", "host", "both"],
                     help="where Server::setup walks the TurboSHAKE128 chain of A: GPU warp, host core (pipelined), or both one after the other")

@@ -7,6 +7,7 @@ byte layouts are unchanged.  The compute lives in ``libchalamet_b200.so`` (hand-
 from ._lib import FILTER_PARAM_BYTE_LEN, LIB_PATH, LWE_DIMENSION, SEED_BYTE_LEN, SERVER_SETUP_MAX_ATTEMPT_COUNT
 from .errors import ChalametPIRError
 from .server import (
+    PinnedBuffer,
     Server,
     db_matrix_shape,
     device_count,
@@ -22,6 +23,7 @@ from .server import (
 
 __all__ = [
     "Server",
+    "PinnedBuffer",
     "ChalametPIRError",
     "LWE_DIMENSION",
     "SEED_BYTE_LEN",

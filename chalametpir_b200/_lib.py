@@ -27,6 +27,7 @@ class SetupOpts(C.Structure):
         ("batch_tc", C.c_uint32),
         ("a_expand", C.c_uint32),
         ("host_chunk_rows", C.c_uint32),
+        ("respond_coalesce", C.c_uint32),
         ("db_encode", C.c_uint32),
     ]
 
@@ -61,6 +62,8 @@ EXPORTS = [
     "chpir_device_count",
     "chpir_ctx_create",
     "chpir_ctx_destroy",
+    "chpir_host_alloc",
+    "chpir_host_free",
     "chpir_find_mat_elem_bit_len",
     "chpir_db_matrix_shape",
     "chpir_encode_kv_database",
@@ -101,6 +104,9 @@ lib.chpir_device_count.argtypes = [C.POINTER(C.c_int)]
 lib.chpir_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
 lib.chpir_ctx_destroy.restype = None
 lib.chpir_ctx_destroy.argtypes = [_vp]
+lib.chpir_host_alloc.argtypes = [C.c_size_t, C.POINTER(_vp)]
+lib.chpir_host_free.restype = None
+lib.chpir_host_free.argtypes = [_vp]
 lib.chpir_find_mat_elem_bit_len.argtypes = [C.c_uint64, C.POINTER(C.c_uint32)]
 lib.chpir_db_matrix_shape.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 lib.chpir_encode_kv_database.argtypes = [C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), _vp, _vp]

@@ -32,6 +32,34 @@ struct RespondSlot {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
+// Transparent coalescing of concurrent chpir_server_respond calls (chpir_setup_opts.respond_coalesce).  Callers join the open
+// batch, each uploading its own query straight into its row of the batch's device buffer; the first caller of a batch is its
+// leader: it waits for the previous batch to leave the GPU (that wait IS the batching window -- an idle GPU means a batch of
+// one and no added latency), closes the batch, runs one launch for all of it (grid.y GEMV for a handful of queries, the
+// tensor-core limb GEMM beyond that, where one pass over D serves up to 128 queries) and reads the responses back.  Two batches
+// ping-pong, so the uploads of the next batch overlap the compute of the current one.
+struct CoalesceBatch {
+  uint32_t *d_q = nullptr, *d_resp = nullptr, *h_resp = nullptr;
+  cudaStream_t copy = nullptr;
+  cudaEvent_t uploaded = nullptr;
+  uint32_t count = 0, issued = 0, picked = 0;
+  bool closed = false, done = false;
+  int rc = CHPIR_OK;
+};
+
+struct Coalescer {
+  static constexpr uint32_t kMaxBatch = 128;
+  static constexpr uint32_t kTensorCoreFrom = 6;  // a tensor-core pass costs about as much as five streaming GEMVs
+  std::mutex mu;
+  std::condition_variable cv;
+  std::mutex exec_mu;  // one batch on the GPU at a time
+  CoalesceBatch b[2];
+  int open = 0;
+  cudaStream_t compute = nullptr;
+  bool ready = false;
+  uint64_t batches = 0, queries = 0, tc_batches = 0;  // statistics
+};
+
 }  // namespace chpir
 
 using namespace chpir;
@@ -46,6 +74,8 @@ struct chpir_server {
   uint64_t packed_bytes = 0;
   GemmTcB *gemm = nullptr;  // D's byte-limb planes + operand ring, kept for the tensor-core batched respond
   std::mutex gemm_mu;
+  bool coalesce = false;
+  Coalescer co;
   chpir_setup_timing timing{};
   float last_respond_ms = 0.f, last_gemm_ms = 0.f, last_expand_ms = 0.f;
   std::mutex pool_mu;
@@ -78,6 +108,36 @@ struct chpir_server {
     if (batch_h_resp) cudaFreeHost(batch_h_resp);
     if (d_packed) cudaFree(d_packed);
     if (gemm) gemm_tc_free(gemm);
+    for (CoalesceBatch &cb : co.b) {
+      if (cb.copy) {
+        cudaStreamSynchronize(cb.copy);
+        cudaStreamDestroy(cb.copy);
+      }
+      if (cb.uploaded) cudaEventDestroy(cb.uploaded);
+      if (cb.d_q) cudaFree(cb.d_q);
+      if (cb.d_resp) cudaFree(cb.d_resp);
+      if (cb.h_resp) cudaFreeHost(cb.h_resp);
+    }
+    if (co.compute) {
+      cudaStreamSynchronize(co.compute);
+      cudaStreamDestroy(co.compute);
+    }
+  }
+
+  int init_coalescer() {
+    for (CoalesceBatch &cb : co.b) {
+      if (cudaMalloc(&cb.d_q, size_t(Coalescer::kMaxBatch) * K * 4) != cudaSuccess ||
+          cudaMalloc(&cb.d_resp, size_t(Coalescer::kMaxBatch) * ncols * 4) != cudaSuccess ||
+          cudaMallocHost(&cb.h_resp, size_t(Coalescer::kMaxBatch) * ncols * 4) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&cb.copy, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&cb.uploaded, cudaEventDisableTiming) != cudaSuccess) {
+        set_last_cuda_error(cudaGetLastError(), "respond coalescer allocation");
+        return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+      }
+    }
+    if (cudaStreamCreateWithFlags(&co.compute, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    co.ready = true;
+    return CHPIR_OK;
   }
 
   int reserve_batch(uint32_t nq) {
@@ -304,6 +364,10 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
   }
   srv->timing.pack_s = t_pack.ms() * 1e-3;
+  if (o.respond_coalesce) {
+    if (int rc = srv->init_coalescer(); rc != CHPIR_OK) return rc;
+    srv->coalesce = true;
+  }
   return CHPIR_OK;
 }
 
@@ -465,6 +529,20 @@ void chpir_ctx_destroy(chpir_ctx *ctx) {
     cudaStreamDestroy(ctx->stream);
   }
   delete ctx;
+}
+
+int chpir_host_alloc(size_t bytes, void **out) {
+  if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    set_last_cuda_error(cudaGetLastError(), "cudaHostAlloc");
+    return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+  }
+  return CHPIR_OK;
+}
+
+void chpir_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 int chpir_find_mat_elem_bit_len(uint64_t n, uint32_t *b) {
@@ -690,6 +768,92 @@ static int validate_query(const chpir_server *srv, const uint8_t *query, size_t 
   return CHPIR_OK;
 }
 
+// One caller's share of a coalesced batch (see Coalescer).  query has been validated; resp_out holds 8 + 4*ncols bytes.
+static int respond_coalesced(chpir_server *srv, const uint8_t *query, uint8_t *resp_out) {
+  Coalescer &co = srv->co;
+  CoalesceBatch *B = nullptr;
+  uint32_t row = 0;
+  {
+    std::unique_lock<std::mutex> lk(co.mu);
+    co.cv.wait(lk, [&] { return !co.b[co.open].closed && co.b[co.open].count < Coalescer::kMaxBatch; });
+    B = &co.b[co.open];
+    row = B->count++;
+  }
+  const bool leader = row == 0;
+  const bool sent = cudaMemcpyAsync(B->d_q + size_t(row) * srv->K, query + 8, srv->K * 4, cudaMemcpyHostToDevice, B->copy) == cudaSuccess;
+  {
+    std::lock_guard<std::mutex> lk(co.mu);
+    B->issued++;
+    if (!sent && B->rc == CHPIR_OK) B->rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+  }
+  co.cv.notify_all();
+  if (leader) {
+    std::lock_guard<std::mutex> ex(co.exec_mu);  // the previous batch leaves the GPU: everyone who arrived meanwhile is in this one
+    uint32_t n = 0;
+    int rc = CHPIR_OK;
+    {
+      std::unique_lock<std::mutex> lk(co.mu);
+      B->closed = true;
+      n = B->count;
+      co.cv.wait(lk, [&] { return B->issued == n; });  // every member has enqueued its upload
+      rc = B->rc;
+      // the other batch becomes the open one as soon as its previous members have all collected their responses
+      co.cv.wait(lk, [&] { return co.b[co.open ^ 1].count == 0 && !co.b[co.open ^ 1].closed; });
+      co.open ^= 1;
+    }
+    co.cv.notify_all();
+    if (rc == CHPIR_OK) {
+      const bool tc = srv->gemm && n >= Coalescer::kTensorCoreFrom;
+      cudaEventRecord(B->uploaded, B->copy);
+      cudaStreamWaitEvent(co.compute, B->uploaded, 0);
+      if (tc) {
+        rc = chpir_server_respond_device_tc(srv, B->d_q, n, B->d_resp, co.compute);
+      } else {
+        if (cudaMemsetAsync(B->d_resp, 0, size_t(n) * srv->ncols * 4, co.compute) != cudaSuccess) rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+        if (rc == CHPIR_OK) rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, B->d_q, B->d_resp, n, co.compute);
+      }
+      if (rc == CHPIR_OK &&
+          cudaMemcpyAsync(B->h_resp, B->d_resp, size_t(n) * srv->ncols * 4, cudaMemcpyDeviceToHost, co.compute) != cudaSuccess)
+        rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+      cudaError_t e = cudaStreamSynchronize(co.compute);
+      if (rc == CHPIR_OK && e != cudaSuccess) {
+        set_last_cuda_error(e, "coalesced respond");
+        rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+      }
+      co.batches++, co.queries += n, co.tc_batches += tc ? 1 : 0;
+    } else {
+      cudaStreamSynchronize(B->copy);
+    }
+    {
+      std::lock_guard<std::mutex> lk(co.mu);
+      B->rc = rc;
+      B->done = true;
+    }
+    co.cv.notify_all();
+  }
+  int rc = CHPIR_OK;
+  {
+    std::unique_lock<std::mutex> lk(co.mu);
+    co.cv.wait(lk, [&] { return B->done; });
+    rc = B->rc;
+  }
+  if (rc == CHPIR_OK) {
+    const uint32_t hdr[2] = {1u, srv->ncols};
+    std::memcpy(resp_out, hdr, 8);
+    std::memcpy(resp_out + 8, B->h_resp + size_t(row) * srv->ncols, size_t(srv->ncols) * 4);
+  }
+  {
+    std::lock_guard<std::mutex> lk(co.mu);
+    if (++B->picked == B->count) {  // last one out resets the batch for reuse
+      B->count = B->issued = B->picked = 0;
+      B->closed = B->done = false;
+      B->rc = CHPIR_OK;
+    }
+  }
+  co.cv.notify_all();
+  return rc;
+}
+
 int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_len, uint8_t *resp_out, size_t resp_cap, size_t *resp_len) {
   CHPIR_GUARD_BEGIN
   if (!srv) return CHPIR_ERR_INVALID_ARGUMENT;
@@ -697,6 +861,11 @@ int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_l
   const size_t need = 8 + size_t(srv->ncols) * 4;
   if (!resp_out || resp_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
   CHPIR_CUDA(cudaSetDevice(srv->ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  if (srv->coalesce && srv->co.ready) {
+    const int rc = respond_coalesced(srv, query, resp_out);
+    if (rc == CHPIR_OK && resp_len) *resp_len = need;
+    return rc;
+  }
   RespondSlot *s = nullptr;
   if (int rc = srv->acquire(&s); rc != CHPIR_OK) return rc;
   int rc = CHPIR_OK;

@@ -39,6 +39,30 @@ def get_ctx(device: int = 0):
         return ctx
 
 
+class PinnedBuffer:
+    """Page-locked host memory from chpir_host_alloc, viewed as a numpy uint8 array (``.array``); freed on close / GC.
+    Queries and responses handed to :meth:`Server.respond_into` from such buffers move at the full PCIe rate."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(lib.chpir_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib.chpir_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def find_mat_elem_bit_len(db_entry_count: int) -> int:
     """server.rs:193-218"""
     b = C.c_uint32()
@@ -129,12 +153,13 @@ class Server:
     # ------------------------------------------------------------------ setup
     @staticmethod
     def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0, a_expand="device", host_chunk_rows=0,
-              db_encode="host") -> SetupOpts:
+              db_encode="host", respond_coalesce=False) -> SetupOpts:
         """a_expand: "device" (default; TurboSHAKE128 chain on one GPU warp) or "host" (one host core squeezes the chain and the
         uploads + panel GEMMs are pipelined behind it -- same bytes, several times lower setup latency)."""
         mode = {"device": 0, "host": 1, 0: 0, 1: 1}[a_expand]
         enc = {"host": 0, "device": 1, 0: 0, 1: 1}[db_encode]  # setup / setup_from_arrays only: where the rows of D are encoded and filled
-        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc, mode, host_chunk_rows, enc)
+        return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc, mode, host_chunk_rows,
+                         1 if respond_coalesce else 0, enc)
 
     @staticmethod
     def setup(seed_mu: bytes, db: Mapping[bytes, bytes], arity: int = 3, *, device: int = 0, filter_seed_rng: Optional[int] = None,

@@ -138,6 +138,42 @@ def test_respond_is_reentrant_across_threads():  # Arc<Server> shared across tas
     assert [r for r in srv.respond_batch([qbytes(q) for q in qs])] == want
 
 
+@pytest.mark.parametrize("batch_tc", [1, 2])
+def test_coalesced_respond_across_threads(batch_tc):
+    """chpir_setup_opts.respond_coalesce: concurrent Server::respond calls are answered by shared launches (grid.y GEMV for small
+    batches, the tensor-core limb GEMM from 6 queries up when the limb planes are resident) -- every caller still gets exactly
+    the bytes the oracle's Server::respond produces, and the error behaviour of a lone call is unchanged."""
+    rng = np.random.default_rng(12)
+    K, N, b = 20011, 301, 10
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    srv, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True, batch_tc=batch_tc, respond_coalesce=True)
+    nthreads, per = 24, 12
+    qs = [rand_u32(rng, K) for _ in range(nthreads)]
+    qs[0][:] = 0xFFFFFFFF
+    want = [oracle_respond(D, b, q) for q in qs]
+    assert srv.respond(qbytes(qs[3])) == want[3]  # a lone caller: batch of one
+    errs = []
+    barrier = threading.Barrier(nthreads)
+
+    def worker(i):
+        try:
+            barrier.wait()
+            for _ in range(per):
+                if srv.respond(qbytes(qs[i])) != want[i]:
+                    errs.append(i)
+        except Exception as ex:  # pragma: no cover
+            errs.append(repr(ex))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(nthreads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    with pytest.raises(cp.ChalametPIRError) as e:
+        srv.respond(qbytes(qs[0])[:-4])
+    assert e.value.variant == "FailedToDeserializeMatrixFromBytes"
+    srv.close()
+
+
 def test_respond_device_pointers_and_batch():
     import torch
 
