@@ -5,6 +5,7 @@ byte layouts are unchanged.  The compute lives in ``libchalamet_b200.so`` (hand-
 ``include/chalamet_b200.h``); importing this package fails if that library has not been built.
 """
 from ._lib import FILTER_PARAM_BYTE_LEN, LIB_PATH, LWE_DIMENSION, SEED_BYTE_LEN, SERVER_SETUP_MAX_ATTEMPT_COUNT
+from .client import Client
 from .errors import ChalametPIRError
 from .server import (
     PinnedBuffer,
@@ -23,6 +24,7 @@ from .server import (
 
 __all__ = [
     "Server",
+    "Client",
     "PinnedBuffer",
     "ChalametPIRError",
     "LWE_DIMENSION",

@@ -55,6 +55,23 @@ class ServerInfo(C.Structure):
     ]
 
 
+class ClientOpts(C.Structure):
+    _fields_ = [("lwe_rows", C.c_uint32), ("a_expand", C.c_uint32), ("host_chunk_rows", C.c_uint32)]
+
+
+class ClientInfo(C.Structure):
+    _fields_ = [
+        ("rows_k", C.c_uint64),
+        ("cols_n", C.c_uint32),
+        ("lwe_rows", C.c_uint32),
+        ("mat_elem_bit_len", C.c_uint32),
+        ("arity", C.c_uint32),
+        ("pub_mat_a_bytes", C.c_uint64),
+        ("setup_expand_s", C.c_double),
+        ("last_query_kernel_ms", C.c_float),
+    ]
+
+
 # every symbol include/chalamet_b200.h declares
 EXPORTS = [
     "chpir_strerror",
@@ -83,6 +100,12 @@ EXPORTS = [
     "chpir_server_last_kernel_ms",
     "chpir_host_generate_from_seed",
     "chpir_host_xof_impl",
+    "chpir_client_setup",
+    "chpir_client_destroy",
+    "chpir_client_query",
+    "chpir_client_query_with",
+    "chpir_client_process_response",
+    "chpir_client_get_info",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -129,4 +152,11 @@ lib.chpir_matmul.argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, 
 lib.chpir_host_generate_from_seed.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _vp]
 lib.chpir_host_xof_impl.restype = C.c_char_p
 lib.chpir_host_xof_impl.argtypes = []
+lib.chpir_client_setup.argtypes = [_vp, _vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(ClientOpts), C.POINTER(_vp)]
+lib.chpir_client_destroy.restype = None
+lib.chpir_client_destroy.argtypes = [_vp]
+lib.chpir_client_query.argtypes = [_vp, _vp, C.c_size_t, C.POINTER(C.c_uint64), _vp, C.c_size_t, _szp]
+lib.chpir_client_query_with.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_size_t, _szp]
+lib.chpir_client_process_response.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _szp]
+lib.chpir_client_get_info.argtypes = [_vp, C.POINTER(ClientInfo)]
 lib.chpir_server_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]

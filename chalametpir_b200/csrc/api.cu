@@ -464,7 +464,15 @@ const char *chpir_strerror(int status) {
     case CHPIR_ERR_EMPTY_KV_DATABASE: return "EmptyKVDatabase";
     case CHPIR_ERR_EXHAUSTED_ALL_ATTEMPTS_TO_BUILD_3_WISE_XOR_FILTER: return "ExhaustedAllAttemptsToBuild3WiseXorFilter";
     case CHPIR_ERR_EXHAUSTED_ALL_ATTEMPTS_TO_BUILD_4_WISE_XOR_FILTER: return "ExhaustedAllAttemptsToBuild4WiseXorFilter";
+    case CHPIR_ERR_ROW_NOT_DECODABLE: return "RowNotDecodable";
+    case CHPIR_ERR_DECODED_ROW_NOT_PREPENDED_WITH_DIGEST_OF_KEY: return "DecodedRowNotPrependedWithDigestOfKey";
+    case CHPIR_ERR_FAILED_TO_DESERIALIZE_FILTER_FROM_BYTES: return "FailedToDeserializeFilterFromBytes";
     case CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE: return "KVDatabaseSizeTooLarge";
+    case CHPIR_ERR_INVALID_HINT_MATRIX: return "InvalidHintMatrix";
+    case CHPIR_ERR_ARITHMETIC_OVERFLOW_ADDING_QUERY_INDICATOR: return "ArithmeticOverflowAddingQueryIndicator";
+    case CHPIR_ERR_INVALID_RESPONSE_VECTOR: return "InvalidResponseVector";
+    case CHPIR_ERR_PENDING_QUERY_EXISTS_FOR_KEY: return "PendingQueryExistsForKey";
+    case CHPIR_ERR_PENDING_QUERY_DOES_NOT_EXIST_FOR_KEY: return "PendingQueryDoesNotExistForKey";
     case CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER: return "UnsupportedArityForBinaryFuseFilter";
     case CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH: return "ImpossibleEncodedDBMatrixElementBitLength";
     case CHPIR_ERR_INVALID_ARGUMENT: return "InvalidArgument";
@@ -918,8 +926,13 @@ int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries,
   // all uploads, one launch over the whole batch (grid.y = query), one download
   for (uint32_t i = 0; i < nq; i++)
     CHPIR_CUDA(cudaMemcpyAsync(srv->batch_q + size_t(i) * srv->K, queries[i] + 8, srv->K * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  CHPIR_CUDA(cudaMemsetAsync(srv->batch_resp, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  if (int rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, srv->batch_q, srv->batch_resp, nq, st); rc != CHPIR_OK) return rc;
+  if (srv->gemm && nq >= Coalescer::kTensorCoreFrom) {
+    // one pass over D's limb planes per 128 queries beats nq passes over the packed D from about six queries up
+    if (int rc = chpir_server_respond_device_tc(srv, srv->batch_q, nq, srv->batch_resp, st); rc != CHPIR_OK) return rc;
+  } else {
+    CHPIR_CUDA(cudaMemsetAsync(srv->batch_resp, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    if (int rc = launch_respond(srv->d_packed, srv->layout, srv->K, srv->plan, srv->batch_q, srv->batch_resp, nq, st); rc != CHPIR_OK) return rc;
+  }
   CHPIR_CUDA(cudaMemcpyAsync(srv->batch_h_resp, srv->batch_resp, size_t(nq) * srv->ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {

@@ -1,0 +1,395 @@
+// client.cu -- chalametpir_client::Client (chalametpir_client/src/client.rs:21-283) with the heavy half on the GPU
+// (SURVEY.md section 8f, rank 2).  Not part of the server hot path: it exists so that a complete PIR round -- query, respond,
+// recover -- can be run and checked at the full 2^20-entry shape, where the reference client spends 8-9 s in setup and
+// 0.3-2 s per query on the CPU (README.md:55-56).
+//
+//   setup            A = generate_from_seed(1774, K, seed) (matrix.rs:541-558) made RESIDENT in HBM as row-major u32 (8.4 GB at
+//                    2^20 entries), through either expander (GPU warp, or a host core with pipelined uploads); hint M and the
+//                    filter parameters are parsed and kept on the host (client.rs:39-57)
+//   query            b = s*A + e (+ indicator at the key's filter slots), c = s*M   (client.rs:95-194): s*A streams all of A
+//                    once -- vec_x_mat_kernel, HBM-bound (8.4 GB, ~1.3 ms) -- everything else is small and stays on the host
+//   process_response round((r - c) / (2^32 / 2^b)), unmask, decode the row, compare the digest (client.rs:209-275): host
+#include <map>
+#include <random>
+#include <string>
+
+#include "common.cuh"
+#include "host_encode.hpp"
+#include "host_pipe.cuh"
+
+namespace chpir {
+namespace {
+
+constexpr int kVxmThreads = 256;
+constexpr int kVxmRowsPerPass = 8;  // independent 16-byte loads in flight per thread
+
+// y[k] (+)= sum_{r in this block's row range} s[r] * A[r][k] mod 2^32; thread = 4 consecutive columns (one 16-byte load per row),
+// blockIdx.y splits the rows so that small K still fills the GPU (partial sums are combined with u32 atomics: exact).
+__global__ void __launch_bounds__(kVxmThreads) vec_x_mat_kernel(const uint32_t *__restrict__ A, const uint32_t *__restrict__ s,
+                                                                uint32_t *__restrict__ y, uint32_t rows, uint64_t cols,
+                                                                uint32_t rows_per_block) {
+  extern __shared__ uint32_t s_sh[];
+  const uint32_t r0 = blockIdx.y * rows_per_block;
+  const uint32_t r1 = min(rows, r0 + rows_per_block);
+  for (uint32_t i = threadIdx.x; i < r1 - r0; i += kVxmThreads) s_sh[i] = s[r0 + i];
+  __syncthreads();
+  const uint64_t c = (uint64_t(blockIdx.x) * kVxmThreads + threadIdx.x) * 4;
+  if (c >= cols) return;
+  uint32_t acc[4] = {0, 0, 0, 0};
+  if (c + 4 <= cols && (cols & 3) == 0) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(A + uint64_t(r0) * cols + c);
+    const uint64_t pitch = cols / 4;
+    uint32_t r = r0;
+    for (; r + kVxmRowsPerPass <= r1; r += kVxmRowsPerPass) {
+      uint4 v[kVxmRowsPerPass];
+#pragma unroll
+      for (int j = 0; j < kVxmRowsPerPass; j++) v[j] = __ldcs(p + uint64_t(j) * pitch);
+#pragma unroll
+      for (int j = 0; j < kVxmRowsPerPass; j++) {
+        const uint32_t sv = s_sh[r - r0 + j];
+        acc[0] += sv * v[j].x, acc[1] += sv * v[j].y, acc[2] += sv * v[j].z, acc[3] += sv * v[j].w;
+      }
+      p += uint64_t(kVxmRowsPerPass) * pitch;
+    }
+    for (; r < r1; r++) {
+      const uint4 v = __ldcs(p);
+      const uint32_t sv = s_sh[r - r0];
+      acc[0] += sv * v.x, acc[1] += sv * v.y, acc[2] += sv * v.z, acc[3] += sv * v.w;
+      p += pitch;
+    }
+  } else {  // ragged K: scalar loads
+    const int n = cols - c < 4 ? int(cols - c) : 4;
+    for (uint32_t r = r0; r < r1; r++) {
+      const uint32_t sv = s_sh[r - r0];
+      for (int j = 0; j < n; j++) acc[j] += sv * A[uint64_t(r) * cols + c + j];
+    }
+  }
+  for (int j = 0; j < 4; j++)
+    if (c + j < cols) {
+      if (gridDim.y == 1)
+        y[c + j] += acc[j];
+      else
+        atomicAdd(y + c + j, acc[j]);
+    }
+}
+
+// y (pre-loaded with the error vector e) += s * A
+int launch_vec_x_mat(const uint32_t *A, const uint32_t *s, uint32_t *y, uint32_t rows, uint64_t cols, int sm_count, cudaStream_t st) {
+  const uint64_t col_blocks = (cols + 4ull * kVxmThreads - 1) / (4ull * kVxmThreads);
+  // enough CTAs for ~8 per SM; never split finer than 64 rows
+  uint32_t splits = 1;
+  while (col_blocks * splits < uint64_t(sm_count) * 8 && rows / (splits * 2) >= 64) splits *= 2;
+  const uint32_t rpb = (rows + splits - 1) / splits;
+  dim3 grid(static_cast<unsigned>(col_blocks), (rows + rpb - 1) / rpb);
+  vec_x_mat_kernel<<<grid, kVxmThreads, rpb * sizeof(uint32_t), st>>>(A, s, y, rows, cols, rpb);
+  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+// matrix.rs:572-619 sample_from_uniform_ternary_dist: rejection above 3*floor((2^32-3)/3), thirds -> 0 / 1 / 2^32-1.  The reference
+// draws from ChaCha8 seeded by the OS; the values are not meant to be reproducible, so any generator serves.
+struct TernarySampler {
+  std::mt19937_64 gen;
+  uint64_t buf = 0;
+  int have = 0;
+  explicit TernarySampler(const uint64_t *seed) {
+    if (seed) {
+      gen.seed(*seed);
+    } else {
+      std::random_device rd;
+      std::seed_seq sq{rd(), rd(), rd(), rd(), rd(), rd(), rd(), rd()};
+      gen.seed(sq);
+    }
+  }
+  uint32_t next_u32() {
+    if (!have) buf = gen(), have = 2;
+    const uint32_t v = uint32_t(buf);
+    buf >>= 32, have--;
+    return v;
+  }
+  void fill(uint32_t *out, uint64_t n) {
+    constexpr uint32_t interval = (0xffffffffu - 2) / 3, max_ok = interval * 3;
+    for (uint64_t i = 0; i < n; i++) {
+      uint32_t v = next_u32();
+      while (v > max_ok) v = next_u32();
+      out[i] = v <= interval ? 0u : (v <= 2 * interval ? 1u : 0xffffffffu);
+    }
+  }
+};
+
+// serialization.rs:132-183 decode_kv_from_row
+int decode_kv_from_row(const uint32_t *row, uint64_t n, uint32_t b, std::vector<uint8_t> *kv) {
+  const uint64_t bits = (n * b) & ~7ull, nbytes = bits / 8;
+  kv->assign(nbytes, 0);
+  const uint32_t mask = (1u << b) - 1;
+  uint64_t buffer = 0, have = 0, off = 0;
+  for (uint64_t r = 0; r < n; r++) {
+    const uint64_t remaining = bits - (off * 8 + have);
+    buffer |= uint64_t(row[r] & mask) << have;
+    have += std::min<uint64_t>(b, remaining);
+    const uint64_t dec_bits = have & ~7ull, dec_bytes = dec_bits / 8;
+    for (uint64_t i = 0; i < dec_bytes; i++) (*kv)[off + i] = uint8_t(buffer >> (8 * i));
+    buffer = dec_bits >= 64 ? 0 : buffer >> dec_bits;
+    have -= dec_bits;
+    off += dec_bytes;
+  }
+  uint64_t i = nbytes;
+  while (i > 0 && (*kv)[i - 1] != 0x81) i--;
+  if (i == 0) return CHPIR_ERR_ROW_NOT_DECODABLE;
+  const uint64_t boundary = i - 1;
+  for (uint64_t j = boundary + 1; j < nbytes; j++)
+    if ((*kv)[j] != 0) return CHPIR_ERR_ROW_NOT_DECODABLE;
+  if (!(boundary > 32)) return CHPIR_ERR_ROW_NOT_DECODABLE;
+  kv->resize(boundary);
+  return CHPIR_OK;
+}
+
+}  // namespace
+}  // namespace chpir
+
+using namespace chpir;
+
+struct chpir_client {
+  chpir_ctx *ctx = nullptr;
+  uint32_t lwe = 0, N = 0, b = 0;
+  uint64_t K = 0;
+  FilterParams fp{};
+  DevBuf a;                    // lwe x K u32, row-major: the reference's pub_mat_a
+  HostAPipe *pipe = nullptr;   // owns A instead when it was expanded on the host
+  const uint32_t *d_a = nullptr;
+  std::vector<uint32_t> hint;  // lwe x N
+  std::mutex mu;               // pending_queries + the per-client device scratch
+  std::map<std::string, std::vector<uint32_t>> pending;  // key -> c = s*M   (client.rs:12-14 Query { vec_c })
+  DevBuf d_s, d_y;
+  uint32_t *h_y = nullptr;     // pinned K words
+  cudaStream_t stream = nullptr;
+  double setup_expand_s = 0;
+  float last_query_kernel_ms = 0.f;
+  ~chpir_client() {
+    if (ctx) cudaSetDevice(ctx->device);
+    if (stream) {
+      cudaStreamSynchronize(stream);
+      cudaStreamDestroy(stream);
+    }
+    if (h_y) cudaFreeHost(h_y);
+    delete pipe;
+  }
+};
+
+static int client_hash_slots(const chpir_client *c, const uint8_t *key, size_t klen, uint8_t digest[32], uint64_t *hash, Slots *slots) {
+  key_digest(key, klen, digest);
+  *hash = mix256(digest, c->fp.seed);
+  *slots = slots_of(c->fp.arity, *hash, c->fp.segment_length, c->fp.segment_count_length);
+  return CHPIR_OK;
+}
+
+#define CHPIR_GUARD_BEGIN try {
+#define CHPIR_GUARD_END                          \
+  }                                              \
+  catch (const std::bad_alloc &) {               \
+    return CHPIR_ERR_HOST_ALLOCATION_FAILED;     \
+  }                                              \
+  catch (...) {                                  \
+    return CHPIR_ERR_INVALID_ARGUMENT;           \
+  }
+
+extern "C" {
+
+int chpir_client_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint8_t *hint, size_t hint_len, const uint8_t *filter_params,
+                       size_t filter_len, const chpir_client_opts *opts, chpir_client **out) {
+  CHPIR_GUARD_BEGIN
+  if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (!ctx || !seed || !hint || !filter_params) return CHPIR_ERR_INVALID_ARGUMENT;
+  // BinaryFuseFilter::from_bytes (binary_fuse_filter.rs:488-517), then Matrix::from_bytes (matrix.rs:973-1010), in the reference's order
+  if (filter_len != CHPIR_FILTER_PARAM_BYTE_LEN) return CHPIR_ERR_FAILED_TO_DESERIALIZE_FILTER_FROM_BYTES;
+  chpir_client_opts o{};
+  if (opts) o = *opts;
+  std::unique_ptr<chpir_client> c(new chpir_client());
+  c->ctx = ctx;
+  std::memcpy(c->fp.seed, filter_params, 32);
+  std::memcpy(&c->fp.arity, filter_params + 32, 4);
+  std::memcpy(&c->fp.segment_length, filter_params + 36, 4);
+  std::memcpy(&c->fp.segment_count_length, filter_params + 40, 4);
+  std::memcpy(&c->fp.num_fingerprints, filter_params + 44, 8);
+  std::memcpy(&c->fp.filter_size, filter_params + 52, 8);
+  std::memcpy(&c->fp.mat_elem_bit_len, filter_params + 60, 8);
+  c->lwe = o.lwe_rows ? o.lwe_rows : CHPIR_LWE_DIMENSION;
+  c->K = c->fp.num_fingerprints;
+  c->b = uint32_t(c->fp.mat_elem_bit_len);
+  if (c->K == 0 || c->K > 0xffffffffull) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;  // generate_from_seed: Matrix::new rejects empty
+  if (c->b < 1 || c->b > 31) return CHPIR_ERR_FAILED_TO_DESERIALIZE_FILTER_FROM_BYTES;
+  if (hint_len <= 8) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  uint32_t hr = 0, hc = 0;
+  std::memcpy(&hr, hint, 4);
+  std::memcpy(&hc, hint + 4, 4);
+  if (uint64_t(hr) * hc == 0 || hint_len != 8 + 4ull * hr * hc) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  if (hr != c->lwe) return CHPIR_ERR_INVALID_HINT_MATRIX;
+  c->N = hc;
+  c->hint.resize(size_t(hr) * hc);
+  std::memcpy(c->hint.data(), hint + 8, size_t(hr) * hc * 4);
+
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  const double t0 = now_s();
+  if (o.a_expand == CHPIR_A_EXPAND_HOST_PIPELINED) {
+    // a panel ring as deep as A is A itself, row-major and contiguous
+    c->pipe = new HostAPipe();
+    const uint32_t panels = (c->lwe + 127) / 128;
+    if (int rc = c->pipe->start(ctx->device, seed, c->lwe, c->K, o.host_chunk_rows, panels); rc != CHPIR_OK) return rc;
+    if (c->pipe->depth() != panels) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    const uint32_t *rows = nullptr;
+    for (uint32_t p = 0; p < panels; p++)
+      if (int rc = c->pipe->acquire_panel(p, ctx->stream, &rows); rc != CHPIR_OK) return rc;
+    CHPIR_CUDA(cudaStreamSynchronize(ctx->stream), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    c->pipe->shutdown();
+    c->d_a = c->pipe->base();
+  } else {
+    DevBuf scratch;
+    if (int rc = scratch.alloc(512); rc != CHPIR_OK) return rc;
+    if (int rc = c->a.alloc(uint64_t(c->lwe) * c->K * 4); rc != CHPIR_OK) return rc;
+    if (int rc = launch_expand(seed, c->a.as<uint8_t>(), uint64_t(c->lwe) * c->K * 4, scratch.as<uint8_t>(), ctx->stream); rc != CHPIR_OK) return rc;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e, "client setup: expand A");
+      return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+    }
+    c->d_a = c->a.as<uint32_t>();
+  }
+  c->setup_expand_s = now_s() - t0;
+  if (int rc = c->d_s.alloc(size_t(c->lwe) * 4); rc != CHPIR_OK) return rc;
+  if (int rc = c->d_y.alloc(c->K * 4); rc != CHPIR_OK) return rc;
+  if (cudaMallocHost(&c->h_y, c->K * 4) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_last_cuda_error(cudaGetLastError(), "client scratch");
+    return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+  }
+  *out = c.release();
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+void chpir_client_destroy(chpir_client *c) { delete c; }
+
+// client.rs:95-194 with the randomness supplied by the caller (s: lwe_rows words, e: K words, every word in {0, 1, 2^32-1} for a
+// real query -- any words are accepted, the arithmetic is the same): the deterministic core both public entry points share.
+int chpir_client_query_with(chpir_client *c, const uint8_t *key, size_t key_len, const uint32_t *secret_s, const uint32_t *error_e,
+                            uint8_t *query_out, size_t query_cap, size_t *query_len) {
+  CHPIR_GUARD_BEGIN
+  if (!c || (!key && key_len) || !secret_s || !error_e || !query_out) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (c->fp.arity != 3 && c->fp.arity != 4) return CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER;
+  const size_t need = 8 + c->K * 4;
+  if (query_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
+  const std::string k(reinterpret_cast<const char *>(key), key_len);
+  std::lock_guard<std::mutex> g(c->mu);
+  if (c->pending.count(k)) return CHPIR_ERR_PENDING_QUERY_EXISTS_FOR_KEY;
+  CHPIR_CUDA(cudaSetDevice(c->ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  cudaStream_t st = c->stream;
+  // b = s*A + e on the device (y starts as e)
+  CHPIR_CUDA(cudaMemcpyAsync(c->d_s.p, secret_s, size_t(c->lwe) * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(c->d_y.p, error_e, c->K * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  EventTimer t;
+  t.start(st);
+  if (int rc = launch_vec_x_mat(c->d_a, c->d_s.as<uint32_t>(), c->d_y.as<uint32_t>(), c->lwe, c->K, c->ctx->sm_count, st); rc != CHPIR_OK) return rc;
+  t.stop(st);
+  CHPIR_CUDA(cudaMemcpyAsync(c->h_y, c->d_y.p, c->K * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  // c = s*M on the host meanwhile (1774 x N words)
+  std::vector<uint32_t> vec_c(c->N, 0);
+  for (uint32_t r = 0; r < c->lwe; r++) {
+    const uint32_t sv = secret_s[r];
+    if (!sv) continue;
+    const uint32_t *m = c->hint.data() + size_t(r) * c->N;
+    for (uint32_t j = 0; j < c->N; j++) vec_c[j] += sv * m[j];
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "client query: s*A");
+    return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+  }
+  c->last_query_kernel_ms = t.ms();
+  uint8_t digest[32];
+  uint64_t hash = 0;
+  Slots sl{};
+  client_hash_slots(c, key, key_len, digest, &hash, &sl);
+  const uint32_t indicator = uint32_t((1ull << 32) / (1ull << c->b));  // client.rs:277-282
+  for (uint32_t j = 0; j < c->fp.arity; j++) {
+    if (sl.h[j] >= c->K) return CHPIR_ERR_INVALID_ARGUMENT;  // filter parameters inconsistent with K
+    const uint32_t old = c->h_y[sl.h[j]], nw = old + indicator;
+    if (nw < old) return CHPIR_ERR_ARITHMETIC_OVERFLOW_ADDING_QUERY_INDICATOR;  // the caller retries with fresh randomness (test_pir.rs:66-70)
+    c->h_y[sl.h[j]] = nw;
+  }
+  const uint32_t hdr[2] = {1u, uint32_t(c->K)};
+  std::memcpy(query_out, hdr, 8);
+  std::memcpy(query_out + 8, c->h_y, c->K * 4);
+  if (query_len) *query_len = need;
+  c->pending.emplace(k, std::move(vec_c));
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_client_query(chpir_client *c, const uint8_t *key, size_t key_len, const uint64_t *rng_seed, uint8_t *query_out, size_t query_cap,
+                       size_t *query_len) {
+  CHPIR_GUARD_BEGIN
+  if (!c) return CHPIR_ERR_INVALID_ARGUMENT;
+  TernarySampler rng(rng_seed);
+  std::vector<uint32_t> s(c->lwe), e(c->K);
+  rng.fill(s.data(), s.size());
+  rng.fill(e.data(), e.size());
+  return chpir_client_query_with(c, key, key_len, s.data(), e.data(), query_out, query_cap, query_len);
+  CHPIR_GUARD_END
+}
+
+int chpir_client_process_response(chpir_client *c, const uint8_t *key, size_t key_len, const uint8_t *resp, size_t resp_len, uint8_t *value_out,
+                                  size_t value_cap, size_t *value_len) {
+  CHPIR_GUARD_BEGIN
+  if (!c || (!key && key_len) || !value_len) return CHPIR_ERR_INVALID_ARGUMENT;
+  const std::string k(reinterpret_cast<const char *>(key), key_len);
+  std::lock_guard<std::mutex> g(c->mu);
+  auto it = c->pending.find(k);
+  if (it == c->pending.end()) return CHPIR_ERR_PENDING_QUERY_DOES_NOT_EXIST_FOR_KEY;
+  const std::vector<uint32_t> &vec_c = it->second;
+  // Matrix::from_bytes, then the shape check (client.rs:214-217)
+  if (!resp || resp_len <= 8) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  uint32_t rr = 0, rc_ = 0;
+  std::memcpy(&rr, resp, 4);
+  std::memcpy(&rc_, resp + 4, 4);
+  if (uint64_t(rr) * rc_ == 0 || resp_len != 8 + 4ull * rr * rc_) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
+  if (!(rr == 1 && rc_ == c->N)) return CHPIR_ERR_INVALID_RESPONSE_VECTOR;
+  const uint32_t factor = uint32_t((1ull << 32) / (1ull << c->b)), half = factor / 2, mask = (1u << c->b) - 1;
+  uint8_t digest[32];
+  uint64_t hash = 0;
+  Slots sl{};
+  client_hash_slots(c, key, key_len, digest, &hash, &sl);
+  std::vector<uint32_t> row(c->N);
+  for (uint32_t i = 0; i < c->N; i++) {
+    uint32_t rv;
+    std::memcpy(&rv, resp + 8 + 4ull * i, 4);
+    const uint32_t un = rv - vec_c[i];
+    uint32_t sc = un / factor;
+    if (un % factor > half) sc++;
+    row[i] = ((sc & mask) + uint32_t(mix(hash, i))) & mask;
+  }
+  std::vector<uint8_t> kv;
+  int rc = decode_kv_from_row(row.data(), c->N, c->b, &kv);
+  if (rc == CHPIR_OK && std::memcmp(kv.data(), digest, 32) != 0) rc = CHPIR_ERR_DECODED_ROW_NOT_PREPENDED_WITH_DIGEST_OF_KEY;
+  if (rc == CHPIR_OK && value_cap < kv.size() - 32) return CHPIR_ERR_BUFFER_TOO_SMALL;  // the query stays pending: call again with room
+  c->pending.erase(it);  // client.rs:269: removed whether or not decoding succeeded
+  if (rc != CHPIR_OK) return rc;
+  if (kv.size() > 32 && value_out) std::memcpy(value_out, kv.data() + 32, kv.size() - 32);
+  *value_len = kv.size() - 32;
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_client_get_info(const chpir_client *c, chpir_client_info *out) {
+  if (!c || !out) return CHPIR_ERR_INVALID_ARGUMENT;
+  out->rows_k = c->K;
+  out->cols_n = c->N;
+  out->lwe_rows = c->lwe;
+  out->mat_elem_bit_len = c->b;
+  out->arity = c->fp.arity;
+  out->pub_mat_a_bytes = uint64_t(c->lwe) * c->K * 4;
+  out->setup_expand_s = c->setup_expand_s;
+  out->last_query_kernel_ms = c->last_query_kernel_ms;
+  return CHPIR_OK;
+}
+
+}  // extern "C"

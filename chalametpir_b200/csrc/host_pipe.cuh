@@ -173,6 +173,9 @@ class HostAPipe {
   }
   double busy_s() const { return busy_; }            // time the producer core spent inside the XOF
   uint32_t panels() const { return panels_; }
+  uint32_t depth() const { return depth_; }
+  // the panel ring; with depth() == panels() this is A itself, row-major u32
+  const uint32_t *base() const { return panels_dev_.as<uint32_t>(); }
 
  private:
   static constexpr int kBufs = 4;

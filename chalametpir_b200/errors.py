@@ -1,4 +1,4 @@
-"""ChalametPIRError -- mirrors chalametpir_common/src/error.rs:8-50 for the variants reachable on the server path."""
+"""ChalametPIRError -- mirrors chalametpir_common/src/error.rs:8-50 for the variants reachable on the server and client paths."""
 from __future__ import annotations
 
 from ._lib import lib
@@ -12,9 +12,17 @@ VARIANTS = {
     5: "EmptyKVDatabase",
     6: "ExhaustedAllAttemptsToBuild3WiseXorFilter",
     7: "ExhaustedAllAttemptsToBuild4WiseXorFilter",
+    8: "RowNotDecodable",
+    9: "DecodedRowNotPrependedWithDigestOfKey",
+    10: "FailedToDeserializeFilterFromBytes",
     11: "KVDatabaseSizeTooLarge",
+    12: "InvalidHintMatrix",
+    13: "ArithmeticOverflowAddingQueryIndicator",
     14: "UnsupportedArityForBinaryFuseFilter",
+    15: "InvalidResponseVector",
     16: "ImpossibleEncodedDBMatrixElementBitLength",
+    17: "PendingQueryExistsForKey",
+    18: "PendingQueryDoesNotExistForKey",
     50: "InvalidArgument",
     51: "BufferTooSmall",
     100: "CudaDeviceNotFound",

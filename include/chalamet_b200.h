@@ -52,9 +52,17 @@ typedef enum chpir_status {
   CHPIR_ERR_EMPTY_KV_DATABASE = 5,
   CHPIR_ERR_EXHAUSTED_ALL_ATTEMPTS_TO_BUILD_3_WISE_XOR_FILTER = 6,
   CHPIR_ERR_EXHAUSTED_ALL_ATTEMPTS_TO_BUILD_4_WISE_XOR_FILTER = 7,
+  CHPIR_ERR_ROW_NOT_DECODABLE = 8,
+  CHPIR_ERR_DECODED_ROW_NOT_PREPENDED_WITH_DIGEST_OF_KEY = 9,
+  CHPIR_ERR_FAILED_TO_DESERIALIZE_FILTER_FROM_BYTES = 10,
   CHPIR_ERR_KV_DATABASE_SIZE_TOO_LARGE = 11,
+  CHPIR_ERR_INVALID_HINT_MATRIX = 12,
+  CHPIR_ERR_ARITHMETIC_OVERFLOW_ADDING_QUERY_INDICATOR = 13,
   CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER = 14,
+  CHPIR_ERR_INVALID_RESPONSE_VECTOR = 15,
   CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH = 16,
+  CHPIR_ERR_PENDING_QUERY_EXISTS_FOR_KEY = 17,
+  CHPIR_ERR_PENDING_QUERY_DOES_NOT_EXIST_FOR_KEY = 18,
   CHPIR_ERR_INVALID_ARGUMENT = 50,
   CHPIR_ERR_BUFFER_TOO_SMALL = 51,
   CHPIR_ERR_CUDA_DEVICE_NOT_FOUND = 100,
@@ -197,7 +205,9 @@ CHPIR_API int chpir_server_get_info(const chpir_server *srv, chpir_server_info *
 /* query: wire format 1 x K.  resp_out: wire format 1 x col_count (3768 B at N=940). */
 CHPIR_API int chpir_server_respond(chpir_server *srv, const uint8_t *query, size_t query_len, uint8_t *resp_out, size_t resp_cap,
                          size_t *resp_len);
-/* nq queries, each wire format 1 x K, concatenated responses each of `resp_stride` bytes. */
+/* nq queries, each wire format 1 x K, concatenated responses each of `resp_stride` bytes.  One launch for the whole batch: the
+ * streaming GEMV with grid.y = query, or -- from 6 queries up when the limb planes are resident (batch_tc) -- the tensor-core
+ * limb GEMM, which passes over D once per 128 queries. */
 CHPIR_API int chpir_server_respond_batch(chpir_server *srv, const uint8_t *const *queries, const size_t *query_lens, uint32_t nq,
                                uint8_t *resp_out, size_t resp_stride);
 /* Device-resident variants (inputs already in HBM): q_device = nq x K u32, resp_device = nq x col_count u32,
@@ -210,6 +220,39 @@ CHPIR_API int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_d
  * Calls on one server must be stream-ordered with respect to each other (they share the operand staging ring).
  * Returns CHPIR_ERR_INVALID_ARGUMENT if the server was set up without limb planes (chpir_setup_opts.batch_tc). */
 CHPIR_API int chpir_server_respond_device_tc(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream);
+
+/* ---- client: chalametpir_client::Client (chalametpir_client/src/client.rs:21-283) with the public
+ *      matrix A resident in HBM and b = s*A + e computed there.  Not on the server hot path; it lets a complete PIR round be run and
+ *      checked at the full 2^20-entry shape. ------------------------------------------------------------------------------------ */
+typedef struct chpir_client chpir_client;
+typedef struct chpir_client_opts {
+  uint32_t lwe_rows;        /* 0 = CHPIR_LWE_DIMENSION; must equal the hint's row count (else InvalidHintMatrix) */
+  uint32_t a_expand;        /* CHPIR_A_EXPAND_DEVICE / CHPIR_A_EXPAND_HOST_PIPELINED, as in chpir_setup_opts       */
+  uint32_t host_chunk_rows; /* as in chpir_setup_opts                                                              */
+} chpir_client_opts;
+typedef struct chpir_client_info {
+  uint64_t rows_k;
+  uint32_t cols_n, lwe_rows, mat_elem_bit_len, arity;
+  uint64_t pub_mat_a_bytes;   /* resident A: lwe_rows * K * 4 */
+  double setup_expand_s;      /* wall time of the A expansion in chpir_client_setup */
+  float last_query_kernel_ms; /* device time of the s*A kernel of the last query */
+} chpir_client_info;
+/* Client::setup (client.rs:39-57).  filter_params: BinaryFuseFilter::to_bytes (68 bytes), hint: Matrix::to_bytes of 1774 x N. */
+CHPIR_API int chpir_client_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint8_t *hint, size_t hint_len,
+                       const uint8_t *filter_params, size_t filter_params_len, const chpir_client_opts *opts, chpir_client **out);
+CHPIR_API void chpir_client_destroy(chpir_client *client);
+/* Client::query (client.rs:95-194): query_out receives the wire-format 1 x K query (8 + 4K bytes).  rng_seed NULL = OS entropy
+ * (reference behaviour), otherwise a reproducible stream.  ArithmeticOverflowAddingQueryIndicator: retry (fresh randomness). */
+CHPIR_API int chpir_client_query(chpir_client *client, const uint8_t *key, size_t key_len, const uint64_t *rng_seed, uint8_t *query_out,
+                       size_t query_cap, size_t *query_len);
+/* The same with the secret vector s (lwe_rows words) and the error vector e (K words) supplied: the deterministic core, used
+ * to check the device arithmetic against the oracle word for word. */
+CHPIR_API int chpir_client_query_with(chpir_client *client, const uint8_t *key, size_t key_len, const uint32_t *secret_s,
+                            const uint32_t *error_e, uint8_t *query_out, size_t query_cap, size_t *query_len);
+/* Client::process_response (client.rs:209-275): value_out receives the value bytes (at most N*b/8 - 33). */
+CHPIR_API int chpir_client_process_response(chpir_client *client, const uint8_t *key, size_t key_len, const uint8_t *response,
+                                  size_t response_len, uint8_t *value_out, size_t value_cap, size_t *value_len);
+CHPIR_API int chpir_client_get_info(const chpir_client *client, chpir_client_info *out);
 
 /* ---- building blocks exposed for parity tests and for composing other paths ------------------------ */
 /* Matrix::generate_from_seed (matrix.rs:541-558) on device; rows [row_begin, row_begin+row_count) of the rows x cols

@@ -976,18 +976,29 @@ static void sample_ternary(orc_rng_t *rng, uint32_t *out, uint64_t n) {
 
 /* client.rs:95-194 query: b = s*A + e, + indicator at h0..h{arity-1}; c = s*M.
  * query_out: 8 + 4K bytes; c_out: N words (the pending-query secret). */
+ORC_EXPORT int orc_client_query_with(const orc_client_t *c, const uint8_t *key, size_t klen, const uint32_t *s, const uint32_t *e,
+                                     uint8_t *query_out, uint32_t *c_out);
+
 ORC_EXPORT int orc_client_query(orc_client_t *c, const uint8_t *key, size_t klen, uint8_t *query_out, uint32_t *c_out) {
   if (c->filter.arity != 3 && c->filter.arity != 4) return ORC_ERR_UNSUPPORTED_ARITY;
   uint32_t *s = (uint32_t *)malloc(c->lwe * 4);
   uint32_t *e = (uint32_t *)malloc(c->K * 4);
-  uint32_t *bq = (uint32_t *)(query_out + 8);
   sample_ternary(&c->rng, s, c->lwe);
   sample_ternary(&c->rng, e, c->K);
+  const int rc = orc_client_query_with(c, key, klen, s, e, query_out, c_out);
+  free(s);
+  free(e);
+  return rc;
+}
+
+/* The deterministic core of client.rs:95-194 for a given secret vector s (lwe words) and error vector e (K words). */
+ORC_EXPORT int orc_client_query_with(const orc_client_t *c, const uint8_t *key, size_t klen, const uint32_t *s, const uint32_t *e,
+                                     uint8_t *query_out, uint32_t *c_out) {
+  if (c->filter.arity != 3 && c->filter.arity != 4) return ORC_ERR_UNSUPPORTED_ARITY;
+  uint32_t *bq = (uint32_t *)(query_out + 8);
   orc_matmul_fast(s, 1, c->lwe, c->A, c->lwe, c->K, bq);
   for (uint64_t i = 0; i < c->K; i++) bq[i] += e[i];
   orc_matmul_fast(s, 1, c->lwe, c->M, c->lwe, c->N, c_out);
-  free(s);
-  free(e);
   uint64_t hk[4];
   hash_of_key(key, klen, hk);
   const uint64_t hash = mix256(hk, c->filter.seed);

@@ -382,6 +382,19 @@ class Client:
         self.pending[key] = c
         return q.tobytes()
 
+    def query_with(self, key: bytes, secret_s: np.ndarray, error_e: np.ndarray) -> bytes:
+        """client.rs:95-194 with the secret vector s and the error vector e supplied (the deterministic core of query)."""
+        if key in self.pending:
+            raise OracleError(-1)
+        q = np.empty(8 + 4 * self.K, dtype=np.uint8)
+        c = np.empty(self.N, dtype=np.uint32)
+        k = _u8(key)
+        s = np.ascontiguousarray(secret_s, dtype=np.uint32)
+        e = np.ascontiguousarray(error_e, dtype=np.uint32)
+        _chk(lib().orc_client_query_with(self._h, _p(k), C.c_size_t(len(k)), _p(s), _p(e), _p(q), _p(c)))
+        self.pending[key] = c
+        return q.tobytes()
+
     def process_response(self, key: bytes, resp: bytes) -> bytes:
         c = self.pending[key]
         out = np.zeros((self.N * self.b) // 8 + 8, dtype=np.uint8)

@@ -168,6 +168,9 @@ def test_coalesced_respond_across_threads(batch_tc):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs
+    # the host batch entry point takes the same two routes (tensor cores from 6 queries up when the planes are resident)
+    assert srv.respond_batch([qbytes(q) for q in qs]) == want
+    assert srv.respond_batch([qbytes(q) for q in qs[:3]]) == want[:3]
     with pytest.raises(cp.ChalametPIRError) as e:
         srv.respond(qbytes(qs[0])[:-4])
     assert e.value.variant == "FailedToDeserializeMatrixFromBytes"
