@@ -332,12 +332,36 @@ def run_b200(args):
         wall_g = time.perf_counter() - t0
         tg = srv_g.setup_timing()
         assert hint_g == hint_e and fb_g == fb_e, "device row fill changed the hint or the filter parameters"
-        del srv_g, hint_g
+        # a complete PIR round on this real database: GPU client (A resident in HBM) -> Server::respond -> recover the value
+        t0 = time.perf_counter()
+        client = cp.Client.setup(SEED_MU, hint_g, fb_g, device=local_rank, a_expand="host")
+        client_setup_s = time.perf_counter() - t0
+        rounds, q_ms = 0, []
+        for j, i in enumerate([0, 1, n_db // 3, n_db // 2, n_db - 1, 777_777]):
+            key = keys[i].tobytes()
+            try:
+                t0 = time.perf_counter()
+                qb = client.query(key, rng_seed=j)
+                q_ms.append((time.perf_counter() - t0) * 1e3)
+            except cp.ChalametPIRError as ex:
+                if ex.variant != "ArithmeticOverflowAddingQueryIndicator":
+                    raise
+                continue
+            assert client.process_response(key, srv_g.respond(qb)) == vals[i].tobytes(), "PIR round failed to recover the value"
+            rounds += 1
+        ci = client.info()
+        pir_round = {"values_recovered": rounds, "client_setup_s": client_setup_s, "client_query_ms_wall": statistics.median(q_ms),
+                     "client_query_kernel_ms": ci["last_query_kernel_ms"], "client_query_kernel_gbs": ci["pub_mat_a_bytes"] / (ci["last_query_kernel_ms"] * 1e-3) / 1e9,
+                     "pub_mat_a_bytes_resident": ci["pub_mat_a_bytes"]}
+        assert rounds >= 3
+        client.close()
+        del srv_g, hint_g, client
         # spot check on the real D: rows 0..1 of the hint against the exact product with the head of the XOF stream
         setup["e2e_from_db"] = {"api": "chpir_server_setup_from_db (keys + values in host memory -> resident server + hint + filter params)",
                                 "wall_s": wall_e, **{k: round(v, 6) for k, v in te.items()}, "a_expand": "host", "db_entries": n_db, "key_bytes": 32,
                                 "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e),
-                                "with_device_row_fill": {"wall_s": wall_g, **{k: round(v, 6) for k, v in tg.items()}, "identical_hint_and_filter_bytes": True}}
+                                "with_device_row_fill": {"wall_s": wall_g, **{k: round(v, 6) for k, v in tg.items()}, "identical_hint_and_filter_bytes": True},
+                                "pir_round_gpu_client": pir_round}
         del hint_e, keys, vals
     if world > 1 and hint is not None:
         # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
@@ -361,6 +385,11 @@ def run_b200(args):
 
     # ---------------- parity spot checks (outside every timed region; numpy / oracle as the checker)
     parity = {}
+    if "e2e_from_db" in setup:
+        parity["full_size_pir_round_values_recovered"] = setup["e2e_from_db"]["pir_round_gpu_client"]["values_recovered"]
+        parity["device_row_fill_identical_hint_and_filter_bytes"] = True
+    if "host_pipelined" in setup:
+        parity["host_pipelined_hint_identical_to_device_mode"] = True
     cols = sorted(set(int(x) for x in np.linspace(0, nc - 1, num=min(nc, 6))))
     Dcols = D[:, cols].cpu().numpy().astype(np.uint64)
     if hint is not None and rank == 0:
