@@ -232,7 +232,9 @@ def run_reference(args):
 
 def workload_config(args, b, K, N):
     return {
-        "workload": f"2^{args.log2n} entries x 32B keys x {VALUE_BYTES}B values, {args.arity}-wise XOR filter (BASELINE.json configs[2])",
+        "workload": f"2^{args.log2n} entries x 32B keys x {VALUE_BYTES}B values, {args.arity}-wise XOR filter (BASELINE.json " +
+                    {(16, 3): "configs[0]", (18, 3): "configs[1]", (20, 3): "configs[2]", (20, 4): "configs[3] shape", (22, 3): "configs[4]"}.get(
+                        (args.log2n, args.arity), "shape outside configs") + ")",
         "K": K, "N": N, "mat_elem_bit_len": b, "lwe_dimension": LWE, "queries_per_step": args.queries_per_step,
         "sharding": f"columns/{args.gpus}" if args.gpus > 1 else "none",
         "l2": "inputs larger than L2 (resident packed D per GPU >> 126 MB at N<=4; every query streams all of it)",

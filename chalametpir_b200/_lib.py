@@ -89,6 +89,8 @@ EXPORTS = [
     "chpir_server_setup_device",
     "chpir_server_setup_from_db",
     "chpir_server_destroy",
+    "chpir_server_save",
+    "chpir_server_load",
     "chpir_server_setup_timing",
     "chpir_server_get_info",
     "chpir_server_respond",
@@ -141,6 +143,8 @@ lib.chpir_server_setup_from_db.argtypes = [
 ]
 lib.chpir_server_destroy.restype = None
 lib.chpir_server_destroy.argtypes = [_vp]
+lib.chpir_server_save.argtypes = [_vp, C.c_char_p]
+lib.chpir_server_load.argtypes = [_vp, C.c_char_p, C.POINTER(SetupOpts), C.POINTER(_vp)]
 lib.chpir_server_setup_timing.argtypes = [_vp, C.POINTER(SetupTiming)]
 lib.chpir_server_get_info.argtypes = [_vp, C.POINTER(ServerInfo)]
 lib.chpir_server_respond.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp]

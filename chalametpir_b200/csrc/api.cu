@@ -4,6 +4,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -476,6 +477,8 @@ const char *chpir_strerror(int status) {
     case CHPIR_ERR_UNSUPPORTED_ARITY_FOR_BINARY_FUSE_FILTER: return "UnsupportedArityForBinaryFuseFilter";
     case CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH: return "ImpossibleEncodedDBMatrixElementBitLength";
     case CHPIR_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+    case CHPIR_ERR_IO_FAILED: return "IoFailed";
+    case CHPIR_ERR_INVALID_SAVED_SERVER: return "InvalidSavedServer";
     case CHPIR_ERR_BUFFER_TOO_SMALL: return "BufferTooSmall";
     case CHPIR_ERR_CUDA_DEVICE_NOT_FOUND: return "CudaDeviceNotFound";
     case CHPIR_ERR_CUDA_ALLOCATION_FAILED: return "CudaAllocationFailed";
@@ -743,6 +746,140 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
 }
 
 void chpir_server_destroy(chpir_server *srv) { delete srv; }
+
+// ---- persisted server state (the reference's Server lives in memory only, server.rs:16-21) ----
+namespace {
+struct SavedHeader {
+  char magic[8];  // "CHPIRSV1"
+  uint32_t version, b;
+  uint64_t K;
+  uint32_t ncols, col_begin, fpw, units;
+  uint64_t packed_bytes, checksum;
+  uint8_t reserved[8];
+};
+static_assert(sizeof(SavedHeader) == 64, "on-disk header is 64 bytes");
+constexpr char kSavedMagic[8] = {'C', 'H', 'P', 'I', 'R', 'S', 'V', '1'};
+constexpr size_t kIoChunk = 64ull << 20;
+
+// FNV-1a over 64-bit words (the payload is a whole number of 16-byte units)
+inline uint64_t fnv1a64(uint64_t h, const uint8_t *p, size_t n) {
+  for (size_t i = 0; i + 8 <= n; i += 8) {
+    uint64_t w;
+    std::memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x100000001b3ull;
+  }
+  return h;
+}
+struct FileCloser {
+  void operator()(FILE *f) const {
+    if (f) std::fclose(f);
+  }
+};
+struct PinnedPair {
+  uint8_t *p[2] = {nullptr, nullptr};
+  ~PinnedPair() {
+    for (auto q : p)
+      if (q) cudaFreeHost(q);
+  }
+};
+}  // namespace
+
+int chpir_server_save(chpir_server *srv, const char *path) {
+  CHPIR_GUARD_BEGIN
+  if (!srv || !path) return CHPIR_ERR_INVALID_ARGUMENT;
+  CHPIR_CUDA(cudaSetDevice(srv->ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  std::unique_ptr<FILE, FileCloser> f(std::fopen(path, "wb"));
+  if (!f) return CHPIR_ERR_IO_FAILED;
+  SavedHeader h{};
+  std::memcpy(h.magic, kSavedMagic, 8);
+  h.version = 1, h.b = srv->b, h.K = srv->K, h.ncols = srv->ncols, h.col_begin = srv->col_begin;
+  h.fpw = srv->layout.fpw, h.units = srv->layout.units, h.packed_bytes = srv->packed_bytes;
+  if (std::fwrite(&h, sizeof h, 1, f.get()) != 1) return CHPIR_ERR_IO_FAILED;
+  PinnedPair buf;
+  if (cudaMallocHost(&buf.p[0], kIoChunk) != cudaSuccess) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+  uint64_t sum = 0xcbf29ce484222325ull;
+  std::lock_guard<std::mutex> g(srv->ctx->mu);
+  for (uint64_t off = 0; off < srv->packed_bytes; off += kIoChunk) {
+    const size_t n = size_t(std::min<uint64_t>(kIoChunk, srv->packed_bytes - off));
+    CHPIR_CUDA(cudaMemcpy(buf.p[0], srv->d_packed + off, n, cudaMemcpyDeviceToHost), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    sum = fnv1a64(sum, buf.p[0], n);
+    if (std::fwrite(buf.p[0], 1, n, f.get()) != n) return CHPIR_ERR_IO_FAILED;
+  }
+  h.checksum = sum;
+  if (std::fseek(f.get(), 0, SEEK_SET) != 0 || std::fwrite(&h, sizeof h, 1, f.get()) != 1 || std::fflush(f.get()) != 0) return CHPIR_ERR_IO_FAILED;
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
+int chpir_server_load(chpir_ctx *ctx, const char *path, const chpir_setup_opts *opts, chpir_server **out) {
+  CHPIR_GUARD_BEGIN
+  if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (!ctx || !path) return CHPIR_ERR_INVALID_ARGUMENT;
+  chpir_setup_opts o{};
+  if (opts) o = *opts;
+  std::unique_ptr<FILE, FileCloser> f(std::fopen(path, "rb"));
+  if (!f) return CHPIR_ERR_IO_FAILED;
+  SavedHeader h{};
+  if (std::fread(&h, sizeof h, 1, f.get()) != 1) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  if (std::memcmp(h.magic, kSavedMagic, 8) != 0 || h.version != 1) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  if (validate_bits(h.b) != CHPIR_OK || h.K == 0 || h.ncols == 0) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  const PackedLayout L = make_layout(h.b, h.ncols);
+  if (L.fpw != h.fpw || L.units != h.units || h.packed_bytes != h.K * L.pitch_bytes()) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  const double t0 = now_s();
+  std::unique_ptr<chpir_server> srv(new chpir_server());
+  srv->ctx = ctx, srv->K = h.K, srv->ncols = h.ncols, srv->col_begin = h.col_begin, srv->b = h.b;
+  srv->layout = L, srv->packed_bytes = h.packed_bytes;
+  {
+    void *p = nullptr;
+    CHPIR_CUDA(cudaMalloc(&p, srv->packed_bytes), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+    srv->d_packed = static_cast<uint8_t *>(p);
+  }
+  PinnedPair buf;
+  if (cudaMallocHost(&buf.p[0], kIoChunk) != cudaSuccess || cudaMallocHost(&buf.p[1], kIoChunk) != cudaSuccess) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  struct EvGuard {
+    cudaEvent_t *e;
+    ~EvGuard() {
+      for (int i = 0; i < 2; i++)
+        if (e[i]) cudaEventDestroy(e[i]);
+    }
+  } evg{ev};
+  for (auto &e : ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+  uint64_t sum = 0xcbf29ce484222325ull;
+  int i = 0;
+  for (uint64_t off = 0; off < srv->packed_bytes; off += kIoChunk, i ^= 1) {
+    const size_t n = size_t(std::min<uint64_t>(kIoChunk, srv->packed_bytes - off));
+    cudaEventSynchronize(ev[i]);  // the upload that last used this buffer (no-op the first time round)
+    if (std::fread(buf.p[i], 1, n, f.get()) != n) return CHPIR_ERR_INVALID_SAVED_SERVER;  // truncated
+    sum = fnv1a64(sum, buf.p[i], n);
+    CHPIR_CUDA(cudaMemcpyAsync(srv->d_packed + off, buf.p[i], n, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    cudaEventRecord(ev[i], st);
+  }
+  CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  if (sum != h.checksum || std::fgetc(f.get()) != EOF) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  srv->plan = plan_respond(srv->layout, srv->K, ctx->sm_count);
+  if (o.batch_tc == 1) {
+    // the limb planes are derived data: rebuild them from the packed rows
+    DevBuf d;
+    if (int rc = d.alloc(srv->K * srv->ncols * 4); rc != CHPIR_OK) return rc;
+    if (int rc = launch_unpack(srv->d_packed, srv->layout, srv->K, d.as<uint32_t>(), st); rc != CHPIR_OK) return rc;
+    if (int rc = gemm_tc_prepare(d.as<uint32_t>(), srv->ncols, srv->K, srv->ncols, srv->b, ctx->sm_count, st, &srv->gemm); rc != CHPIR_OK) return rc;
+    CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
+  }
+  if (o.respond_coalesce) {
+    if (int rc = srv->init_coalescer(); rc != CHPIR_OK) return rc;
+    srv->coalesce = true;
+  }
+  srv->timing.total_s = now_s() - t0;
+  *out = srv.release();
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
 
 int chpir_server_setup_timing(const chpir_server *srv, chpir_setup_timing *out) {
   if (!srv || !out) return CHPIR_ERR_INVALID_ARGUMENT;

@@ -38,6 +38,8 @@ PackedLayout make_layout(uint32_t b, uint32_t ncols);
 // D (u32, K x ld, columns [col_begin, col_begin+ncols)) -> packed rows.
 int launch_pack(const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col_begin, const PackedLayout &L, uint8_t *packed,
                 cudaStream_t s);
+// packed rows -> K x ncols u32 row-major (inverse of launch_pack for a whole slice)
+int launch_unpack(const uint8_t *packed, const PackedLayout &L, uint64_t K, uint32_t *d_dev, cudaStream_t s);
 struct RespondPlan {
   // register-pipelined kernel (respond_kernel): generic shapes
   uint32_t threads;         // block size = rows_per_iter * units (+ idle lanes)

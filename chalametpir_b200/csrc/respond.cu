@@ -341,6 +341,39 @@ __global__ void pack_kernel(const uint32_t *__restrict__ d, uint64_t K, uint32_t
   }
 }
 
+// packed rows -> K x ncols u32 (the inverse of pack_kernel; used to rebuild the GEMM's limb planes for a server loaded from disk)
+template <int B>
+__global__ void unpack_kernel(const uint4 *__restrict__ packed, uint64_t K, uint32_t ncols, uint32_t units, uint32_t *__restrict__ d) {
+  constexpr int FPW = 64 / B;
+  constexpr uint32_t MASK = (1u << B) - 1u;
+  const uint64_t total = K * units;
+  for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < total; idx += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t k = idx / units;
+    const uint32_t u = uint32_t(idx - k * units);
+    const uint4 v = packed[idx];
+    const uint64_t w[2] = {uint64_t(v.x) | uint64_t(v.y) << 32, uint64_t(v.z) | uint64_t(v.w) << 32};
+    uint32_t *row = d + k * ncols;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int f = 0; f < FPW; f++) {
+        const uint32_t col = (2 * u + h) * FPW + f;
+        if (col < ncols) row[col] = uint32_t(w[h] >> (f * B)) & MASK;
+      }
+    }
+  }
+}
+
+template <int B>
+int unpack_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, uint32_t *d, cudaStream_t s) {
+  const uint64_t total = K * L.units;
+  const int block = 256;
+  const uint64_t want = (total + block - 1) / block;
+  const int grid = int(want < 148ull * 32 ? (want ? want : 1) : 148ull * 32);
+  unpack_kernel<B><<<grid, block, 0, s>>>(reinterpret_cast<const uint4 *>(packed), K, L.ncols, L.units, d);
+  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
 template <int B>
 int respond_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q, uint32_t *resp,
                      cudaStream_t s) {
@@ -519,6 +552,12 @@ int launch_pack(const uint32_t *d_dev, uint64_t K, uint32_t ld, uint32_t col_beg
 #define CHPIR_PACK(B) pack_dispatch<B>(d_dev, K, ld, col_begin, L, packed, s)
   CHPIR_DISPATCH_B(L.b, CHPIR_PACK)
 #undef CHPIR_PACK
+}
+
+int launch_unpack(const uint8_t *packed, const PackedLayout &L, uint64_t K, uint32_t *d_dev, cudaStream_t s) {
+#define CHPIR_UNPACK(B) unpack_dispatch<B>(packed, L, K, d_dev, s)
+  CHPIR_DISPATCH_B(L.b, CHPIR_UNPACK)
+#undef CHPIR_UNPACK
 }
 
 }  // namespace chpir

@@ -25,6 +25,8 @@ VARIANTS = {
     18: "PendingQueryDoesNotExistForKey",
     50: "InvalidArgument",
     51: "BufferTooSmall",
+    52: "IoFailed",
+    53: "InvalidSavedServer",
     100: "CudaDeviceNotFound",
     101: "CudaAllocationFailed",
     102: "CudaTransferFailed",

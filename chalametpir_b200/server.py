@@ -263,6 +263,19 @@ class Server:
         )
         return Server(h, device), (hint[: hl.value].tobytes() if hint is not None else None)
 
+    # ------------------------------------------------------------------ persisted state
+    def save(self, path: str) -> None:
+        """Write the resident packed column slice to ``path`` (chpir_server_save); hint and filter bytes stay with the caller."""
+        check(lib.chpir_server_save(self._h, str(path).encode()))
+
+    @staticmethod
+    def load(path: str, *, device: int = 0, batch_tc: int = 0, respond_coalesce: bool = False) -> "Server":
+        """A server that answers queries straight from a file written by :meth:`save`, without re-running setup."""
+        o = Server._opts(batch_tc=batch_tc, respond_coalesce=respond_coalesce)
+        h = C.c_void_p()
+        check(lib.chpir_server_load(get_ctx(device), str(path).encode(), C.byref(o), C.byref(h)))
+        return Server(h, device)
+
     # ------------------------------------------------------------------ respond
     def respond(self, query: bytes) -> bytes:
         """Server::respond(&self, query) -> response bytes   [server.rs:184-190]"""

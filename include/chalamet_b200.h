@@ -65,6 +65,8 @@ typedef enum chpir_status {
   CHPIR_ERR_PENDING_QUERY_DOES_NOT_EXIST_FOR_KEY = 18,
   CHPIR_ERR_INVALID_ARGUMENT = 50,
   CHPIR_ERR_BUFFER_TOO_SMALL = 51,
+  CHPIR_ERR_IO_FAILED = 52,
+  CHPIR_ERR_INVALID_SAVED_SERVER = 53,
   CHPIR_ERR_CUDA_DEVICE_NOT_FOUND = 100,
   CHPIR_ERR_CUDA_ALLOCATION_FAILED = 101,
   CHPIR_ERR_CUDA_TRANSFER_FAILED = 102,
@@ -172,6 +174,15 @@ CHPIR_API int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const u
                                uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
                                uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN], chpir_server **out);
 CHPIR_API void chpir_server_destroy(chpir_server *srv);
+
+/* Persisted server state (the reference's Server exists in memory only, server.rs:16-21): the resident
+ * packed column slice with its shape, so that respond can start without re-running setup -- one file per rank under column
+ * sharding.  64-byte header (magic "CHPIRSV1", version, b, K, columns, first column, layout, payload bytes, FNV-1a checksum) followed
+ * by the packed rows exactly as they sit in HBM.  The hint and the filter parameters are the caller's bytes already (setup returned
+ * them); derived data (the limb planes of batch_tc = 1) is rebuilt on load.  chpir_server_load honours opts->batch_tc and
+ * opts->respond_coalesce and ignores the setup-only fields. */
+CHPIR_API int chpir_server_save(chpir_server *srv, const char *path);
+CHPIR_API int chpir_server_load(chpir_ctx *ctx, const char *path, const chpir_setup_opts *opts, chpir_server **out);
 
 /* Phase split of the last setup on this server, seconds. */
 typedef struct chpir_setup_timing {

@@ -301,3 +301,36 @@ def test_respond_tensor_core_batch_needs_planes():
     with pytest.raises(cp.ChalametPIRError) as e:
         srv.respond_device_tc(dq.data_ptr(), 1, dr.data_ptr(), 0)
     assert e.value.variant == "InvalidArgument"
+
+
+# ------------------------------------------------------------------ persisted server state (chpir_server_save / chpir_server_load)
+@pytest.mark.parametrize("b,K,N", [(9, 5003, 941), (10, 20000, 300), (4, 777, 17), (14, 1024, 64)])
+def test_saved_server_answers_identically_after_load(tmp_path, b, K, N):
+    rng = np.random.default_rng(b + K)
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    srv, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True, col_begin=3 if N > 20 else 0)
+    path = tmp_path / "server.chpir"
+    srv.save(path)
+    assert path.stat().st_size == 64 + srv.packed_bytes
+    qs = [rand_u32(rng, K) for _ in range(7)]
+    want = [srv.respond(qbytes(q)) for q in qs]
+    assert want[0] == oracle_respond(D[:, srv.col_begin :], b, qs[0])
+    for batch_tc, coalesce in ((0, False), (1, True)):
+        ld = cp.Server.load(path, batch_tc=batch_tc, respond_coalesce=coalesce)
+        assert (ld.rows_k, ld.cols_n, ld.col_begin, ld.mat_elem_bit_len, ld.packed_bytes) == (srv.rows_k, srv.cols_n, srv.col_begin, b, srv.packed_bytes)
+        assert [ld.respond(qbytes(q)) for q in qs] == want
+        assert ld.respond_batch([qbytes(q) for q in qs]) == want  # 7 queries: the tensor-core route when the planes were rebuilt
+        ld.close()
+    # damaged files are rejected, not served
+    raw = bytearray(path.read_bytes())
+    raw[64 + len(raw) // 2] ^= 1
+    (tmp_path / "flipped").write_bytes(raw)
+    (tmp_path / "short").write_bytes(path.read_bytes()[:-16])
+    (tmp_path / "magic").write_bytes(b"X" + path.read_bytes()[1:])
+    for name in ("flipped", "short", "magic"):
+        with pytest.raises(cp.ChalametPIRError) as e:
+            cp.Server.load(tmp_path / name)
+        assert e.value.variant == "InvalidSavedServer", name
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.Server.load(tmp_path / "does-not-exist")
+    assert e.value.variant == "IoFailed"
