@@ -529,9 +529,9 @@ def run_b200(args):
         # Sharded e2e: the query batch sits in pinned HOST memory; rank r uploads only rows' K/world slice
         # over its own PCIe link, the slices are all-gathered over NVLink, every rank answers for its column slice through the
         # C ABI's device entry point, the response slices are gathered and rank 0 reads them back to the host.
-        ks = -(-K // world)
-        k0 = min(K, rank * ks)
-        k1 = min(K, k0 + ks)
+        from chalametpir_b200 import sharding
+
+        k0, k1, ks = sharding.query_slice(K, rank, world)
         q_words = q_host[:, 8:].view(torch.int32)  # Q x K, pinned
         q_slice = [torch.zeros((Q, ks), dtype=torch.int32, device=dev) for _ in range(2)]
         q_all = [torch.empty((world, Q, ks), dtype=torch.int32, device=dev) for _ in range(2)]
@@ -553,8 +553,7 @@ def run_b200(args):
                         s_in.wait_event(done[p])
                     for j in range(Q):  # one contiguous pinned -> device DMA per query (a strided 2-D copy_ would be staged through the host)
                         q_slice[p][j, : k1 - k0].copy_(q_words[j, k0:k1], non_blocking=True)
-                    dist.all_gather_into_tensor(q_all[p].view(-1), q_slice[p].view(-1))
-                    q_rows[p].copy_(q_all[p].permute(1, 0, 2).reshape(Q, world * ks)[:, :K])
+                    sharding.allgather_query_slices(dist, torch, q_slice[p], q_all[p], q_rows[p])
                     ready[p] = torch.cuda.Event()
                     ready[p].record(s_in)
 

@@ -40,6 +40,24 @@ def unpad_gathered(torch, gathered: "torch.Tensor", counts: Sequence[int]) -> "t
     return torch.cat([gathered[r, :, :c] for r, c in enumerate(counts)], dim=1)
 
 
+def query_slice(K: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """(k0, k1, ks): rank `rank` uploads words [k0, k1) of every query over its own PCIe link; ks = ceil(K / world) is the padded
+    slice length every rank contributes to the all-gather (H2D-scatter + all-gather instead of a full upload
+    per rank)."""
+    ks = -(-K // world)
+    k0 = min(K, rank * ks)
+    return k0, min(K, k0 + ks), ks
+
+
+def allgather_query_slices(dist, torch, q_slice: "torch.Tensor", q_all: "torch.Tensor", q_rows: "torch.Tensor", group=None) -> "torch.Tensor":
+    """q_slice: (Q, ks) this rank's words of Q queries (zero padded) -> q_rows: (Q, K) whole queries on every rank.
+    q_all is the (world, Q, ks) all-gather landing buffer; the rank-major result is re-laid out query-major into q_rows."""
+    world, Q, ks = q_all.shape
+    dist.all_gather_into_tensor(q_all.view(-1), q_slice.view(-1), group=group)
+    q_rows.copy_(q_all.permute(1, 0, 2).reshape(Q, world * ks)[:, : q_rows.shape[1]])
+    return q_rows
+
+
 def response_bytes(row: np.ndarray) -> bytes:
     """Matrix::to_bytes of a 1 x N response (matrix.rs:947-971)."""
     row = np.ascontiguousarray(row, dtype="<u4").reshape(-1)

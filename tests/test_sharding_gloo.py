@@ -25,6 +25,15 @@ def test_slice_of_partitions_exactly():
             assert max(c for _, c in got) - min(c for _, c in got) <= 1
 
 
+def test_query_slices_cover_the_query_exactly():
+    for K in (1, 5, 997, 1179648, 1130496):
+        for world in (1, 2, 3, 8):
+            parts = [sharding.query_slice(K, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == K
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert all(p[1] - p[0] <= p[2] for p in parts) and len({p[2] for p in parts}) == 1
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -44,6 +53,12 @@ def _worker(rank, world, port, K, N, b, lwe, out_dir):
             qt.zero_()
         dist.broadcast(qt, 0)  # the query batch reaches every rank
         q_here = qt.numpy().view(np.uint32)
+        # the e2e route: every rank holds only its K/world words of each query, the slices are all-gathered and re-laid out
+        k0, k1, ks = sharding.query_slice(K, rank, world)
+        q_slice = torch.zeros((Q, ks), dtype=torch.int32)
+        q_slice[:, : k1 - k0] = torch.from_numpy(q.view(np.int32)[:, k0:k1].copy())
+        q_rows = sharding.allgather_query_slices(dist, torch, q_slice, torch.empty((world, Q, ks), dtype=torch.int32), torch.empty((Q, K), dtype=torch.int32))
+        assert np.array_equal(q_rows.numpy().view(np.uint32), q)
         c0, nc = sharding.slice_of(N, rank, world)
         srv, hint = O.Server.setup_from_matrix(SEED, np.ascontiguousarray(D[:, c0 : c0 + nc]), b, lwe_rows=lwe)
         local = np.stack([O.matrix_from_bytes(srv.respond(O.matrix_to_bytes(q_here[i : i + 1])))[0] for i in range(Q)])
