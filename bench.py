@@ -263,6 +263,8 @@ def run_b200(args):
         # NCCL's kernels run on a high-priority stream: the respond kernel fills every SM (one 175 KB-smem CTA each), and without
         # priority the query broadcast of the next batch only gets SMs once the current batch has drained (no overlap)
         pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        if os.environ.get("CHPIR_NCCL_MAX_CTAS"):  # experiment knob: fewer NCCL CTAs leave more SMs to the respond kernel
+            pg_opts.config.max_ctas = int(os.environ["CHPIR_NCCL_MAX_CTAS"])
         dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
 
     def barrier():

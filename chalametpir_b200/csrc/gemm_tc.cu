@@ -25,8 +25,17 @@ namespace {
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BN_MAX = 128;    // accumulator columns per shift; 4 * 128 = all 512 TMEM columns
-constexpr int BK = 128;        // bytes of K per stage row = one 128B swizzle row = 4 UMMA k-steps of 32
-constexpr int STAGES = 2;
+// Bytes of K per stage row = one swizzle row, and pipeline depth.  A stage holds 4 A limbs + up to 2 B limbs of 128 rows each:
+// 96 KB at BK = 128 (two stages fit), 48 KB at BK = 64 (four stages).  The two-stage pipeline leaves the tensor pipe 70 % active
+// (ncu, round 1): each SM has to take in 96 KB per 1728 MMA cycles, 57 B/clk, which is about what one SM can pull from L2.
+// Four half-size stages (-DCHPIR_GEMM_BK=64, 64B swizzle) were measured and are SLOWER (19.9 ms against 11.3 ms for the 2^20
+// hint GEMM), so 128 stays the default; the switch is kept for experiments.
+#ifndef CHPIR_GEMM_BK
+#define CHPIR_GEMM_BK 128
+#endif
+constexpr int BK = CHPIR_GEMM_BK;
+static_assert(BK == 128 || BK == 64, "BK is one 128B- or 64B-swizzle row");
+constexpr int STAGES = BK == 128 ? 2 : 4;
 constexpr int A_TILE = BM * BK;      // 16 KB per limb
 constexpr int B_TILE = BN_MAX * BK;  // 16 KB per limb
 constexpr int kThreads = 192;
@@ -60,14 +69,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// K-major, swizzled operand tile: rows of BK bytes (128B or 64B swizzle), 8-row groups 8*BK bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFF) >> 4);  // start address
   d |= uint64_t(1) << 16;                     // leading byte offset (ignored for swizzled K-major), canonical value 1
-  d |= uint64_t(1024 >> 4) << 32;             // stride byte offset: 8 rows * 128 B
+  d |= uint64_t((8 * BK) >> 4) << 32;         // stride byte offset: 8 rows * BK bytes
   d |= uint64_t(1) << 46;                     // descriptor version (sm_100)
-  d |= uint64_t(2) << 61;                     // SWIZZLE_128B
+  d |= uint64_t(BK == 128 ? 2 : 4) << 61;     // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -314,7 +323,7 @@ int make_map(CUtensorMap *map, void *base, uint64_t k, uint64_t kp, uint64_t row
   const cuuint32_t box[3] = {BK, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
 }
 
@@ -372,7 +381,7 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
     // one launch = one 128-row panel: split K so that tiles_n * splits fills whole waves of sm_count CTAs
     uint32_t best_splits = 1;
     double best_eff = 0.0;
-    uint32_t max_splits = g->kblocks / 8;  // every split keeps >= 8 k-blocks (1024 k) of mainloop per epilogue
+    uint32_t max_splits = g->kblocks / (1024 / BK);  // every split keeps >= 1024 k of mainloop per epilogue
     if (max_splits < 1) max_splits = 1;
     if (max_splits > 148) max_splits = 148;
     for (uint32_t sp = 1; sp <= max_splits; sp++) {
