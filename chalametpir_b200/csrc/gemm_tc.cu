@@ -27,9 +27,12 @@ constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BN_MAX = 128;    // accumulator columns per shift; 4 * 128 = all 512 TMEM columns
 // Bytes of K per stage row = one swizzle row, and pipeline depth.  A stage holds 4 A limbs + up to 2 B limbs of 128 rows each:
 // 96 KB at BK = 128 (two stages fit), 48 KB at BK = 64 (four stages).  The two-stage pipeline leaves the tensor pipe 70 % active
-// (ncu, round 1): each SM has to take in 96 KB per 1728 MMA cycles, 57 B/clk, which is about what one SM can pull from L2.
-// Four half-size stages (-DCHPIR_GEMM_BK=64, 64B swizzle) were measured and are SLOWER (19.9 ms against 11.3 ms for the 2^20
-// hint GEMM), so 128 stays the default; the switch is kept for experiments.
+// (ncu, round 1).  What bounds it is the rate at which TMA fills shared memory, not latency: a k-block takes ~3100 cycles for 768
+// 128-byte rows (32 B/clk per SM, 4700 B/clk chip-wide) where its MMAs need 1728.  Doubling the TMA work per byte of K makes the
+// kernel proportionally slower: four half-size stages (-DCHPIR_GEMM_BK=64, 64B swizzle, 12 loads per 128 B of K) 19.9 ms against
+// 11.4 ms for the 2^20 hint GEMM; L2 prefetches (cp.async.bulk.prefetch.tensor) of A and B ahead of the loads 19.9 ms, of B alone
+// 14.0 ms.  So 128 B x 2 stages stays, and the next step for this kernel is fewer L2 reads per MAC (A multicast across a cluster
+// of N-tile CTAs), not a deeper pipeline.
 #ifndef CHPIR_GEMM_BK
 #define CHPIR_GEMM_BK 128
 #endif
