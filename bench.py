@@ -482,7 +482,6 @@ def run_b200(args):
         srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
     k1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
     ms_kernel = k0.elapsed_time(k1) / (args.steps * Q)
     t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
     if world > 1:
@@ -588,6 +587,8 @@ def run_b200(args):
     e2e_steps(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # one nvidia-smi sampler (100 ms period) spans all three timed respond regions: device-resident steps, kernel-only, e2e
+    clocks = sampler.stop() if rank == 0 else None
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -701,7 +702,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20)

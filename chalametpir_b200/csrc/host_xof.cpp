@@ -7,9 +7,10 @@
 // implementations, picked at run time:
 //   * AVX-512 (F + VL): one 64-bit lane per qword slot, a plane A[0..4][y] per zmm register; theta and chi are three-input
 //     vpternlogq, rho is vprolvq, pi is the slot permutation that makes chi register-wise, and the only cross-register data
-//     movement per round is one 5x5 qword transposition;
+//     movement per round is one 5x5 qword transposition (two shuffle levels + one trip through the store buffer);
 //   * scalar 64-bit code (two rounds unrolled, lanes in locals), built twice: baseline x86-64 and BMI2 (rorx / andn).
-// impl 0 times each available variant once (~1 ms) and keeps the fastest.
+// impl 0 times each available variant (a few ms, after a warm-up long enough for the core's 512-bit frequency licence to settle)
+// and keeps the fastest.
 #include "host_xof.hpp"
 
 #include <algorithm>
@@ -73,34 +74,37 @@ __attribute__((target("bmi,bmi2"))) void squeeze_bmi2(uint64_t s[25], uint8_t *o
 #endif
 
 #if defined(__x86_64__)
-// ---- AVX-512.  Plane representation: register P[y], qword slot x holds A[x][y] (slots 5..7 are don't-care).
+// ---- AVX-512.  Plane representation: register P[y] holds A[0..4][y], lane x in qword slot kTau[x] (slots 3, 6, 7 are don't-care).
+// Per round: theta is two three-input XORs, two slot permutes of the parity vector and five vpternlogq; rho is vprolvq; pi is one
+// slot permute per plane, after which chi is register-wise (R[X] slot Y = A'[X][Y]).  The 5x5 transposition back to planes is
+// two levels of two-source shuffles (in-lane unpack, then 128-bit lane select) for X = 0..3; the fifth source R[4] goes through
+// memory: one 64-byte store and five merge-masked 8-byte broadcast loads, which run on the load ports instead of the one
+// shuffle port every vpermq needs (16 shuffle uops per round instead of 21, and a shorter dependent chain).
+constexpr unsigned kRho[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+constexpr int kTau[5] = {0, 1, 4, 5, 2};  // slot of lane x: what unpack + lane select produce for x = 0..3; x = 4 is merged into slot 2
+
 struct Avx512Consts {
-  alignas(64) uint64_t rho[5][8];      // rho[y][x] = rotation of lane (x, y)
-  alignas(64) uint64_t pi[5][8];       // pi[X][Y] = (3Y + X) % 5: slot of old plane X that lands at new position (X, Y)
-  alignas(64) uint64_t rot_m1[8], rot_p1[8];
-  alignas(64) uint64_t t_ab[8];  // first-level transposition index vector (see squeeze_avx512)
+  alignas(64) uint64_t rho[5][8];  // rho[y][kTau[x]] = rotation of lane (x, y)
+  alignas(64) uint64_t pi[5][8];   // pi[X][Y] = kTau[(3Y + X) % 5]: slot of plane X that lands at position (X, Y) after pi
+  alignas(64) uint64_t rot_m1[8], rot_p1[8];  // parity vector C -> C[x-1], C[x+1] in plane slot order
+  alignas(64) uint64_t natural[8];            // plane slot order -> x = 0..4 in slots 0..4 (for the 168-byte output)
   alignas(64) uint64_t rc[12][8];
 };
-
-constexpr unsigned kRho[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
 
 const Avx512Consts &avx512_consts() {
   static const Avx512Consts c = [] {
     Avx512Consts k{};
     for (int y = 0; y < 5; y++)
-      for (int x = 0; x < 8; x++) k.rho[y][x] = x < 5 ? kRho[x + 5 * y] : 0;
+      for (int x = 0; x < 5; x++) k.rho[y][kTau[x]] = kRho[x + 5 * y];
     for (int X = 0; X < 5; X++)
-      for (int Y = 0; Y < 8; Y++) k.pi[X][Y] = Y < 5 ? uint64_t((3 * Y + X) % 5) : uint64_t(Y);
-    for (int x = 0; x < 8; x++) {
-      k.rot_m1[x] = x < 5 ? uint64_t((x + 4) % 5) : uint64_t(x);
-      k.rot_p1[x] = x < 5 ? uint64_t((x + 1) % 5) : uint64_t(x);
+      for (int Y = 0; Y < 5; Y++) k.pi[X][Y] = uint64_t(kTau[(3 * Y + X) % 5]);
+    for (int s = 0; s < 8; s++) k.rot_m1[s] = k.rot_p1[s] = uint64_t(s);
+    for (int x = 0; x < 5; x++) {
+      k.rot_m1[kTau[x]] = uint64_t(kTau[(x + 4) % 5]);
+      k.rot_p1[kTau[x]] = uint64_t(kTau[(x + 1) % 5]);
+      k.natural[x] = uint64_t(kTau[x]);
     }
-    // Transposition of the column representation R[X] (slot Y) into planes T[Y] (slot X).
-    //   W01 = permutex2var(R0, t_ab, R1): slots (2Y, 2Y+1) = (R0[Y], R1[Y]) for Y = 0..3;  W23 likewise from R2, R3.
-    //   T[Y] (Y < 4) = permutex2var(W01, t_cd + 2Y, W23) -> slots 0..3, then slot 4 <- R4[Y] by a masked permute.
-    //   T[4] is gathered on its own (4 two-source permutes).
-    for (int i = 0; i < 8; i++) k.t_ab[i] = uint64_t((i >> 1) + ((i & 1) ? 8 : 0));
-    for (int r = 0; r < 12; r++) k.rc[r][0] = kRC[r];
+    for (int r = 0; r < 12; r++) k.rc[r][kTau[0]] = kRC[r];
     return k;
   }();
   return c;
@@ -108,24 +112,21 @@ const Avx512Consts &avx512_consts() {
 
 __attribute__((target("avx512f,avx512vl"))) void squeeze_avx512(uint64_t s[25], uint8_t *out, uint64_t nblocks) {
   const Avx512Consts &k = avx512_consts();
-  const __mmask8 m5 = 0x1f;
-  __m512i P0 = _mm512_maskz_loadu_epi64(m5, s + 0), P1 = _mm512_maskz_loadu_epi64(m5, s + 5), P2 = _mm512_maskz_loadu_epi64(m5, s + 10),
-          P3 = _mm512_maskz_loadu_epi64(m5, s + 15), P4 = _mm512_maskz_loadu_epi64(m5, s + 20);
+  const __mmask8 m5 = 0x1f, mx4 = uint8_t(1u << kTau[4]);
+  alignas(64) uint64_t tmp[5][8] = {};
+  for (int y = 0; y < 5; y++)
+    for (int x = 0; x < 5; x++) tmp[y][kTau[x]] = s[x + 5 * y];
+  __m512i P0 = _mm512_load_si512(tmp[0]), P1 = _mm512_load_si512(tmp[1]), P2 = _mm512_load_si512(tmp[2]), P3 = _mm512_load_si512(tmp[3]),
+          P4 = _mm512_load_si512(tmp[4]);
   const __m512i rho0 = _mm512_load_si512(k.rho[0]), rho1 = _mm512_load_si512(k.rho[1]), rho2 = _mm512_load_si512(k.rho[2]),
                 rho3 = _mm512_load_si512(k.rho[3]), rho4 = _mm512_load_si512(k.rho[4]);
   const __m512i pi0 = _mm512_load_si512(k.pi[0]), pi1 = _mm512_load_si512(k.pi[1]), pi2 = _mm512_load_si512(k.pi[2]),
                 pi3 = _mm512_load_si512(k.pi[3]), pi4 = _mm512_load_si512(k.pi[4]);
-  const __m512i im1 = _mm512_load_si512(k.rot_m1), ip1 = _mm512_load_si512(k.rot_p1);
-  const __m512i tab = _mm512_load_si512(k.t_ab);
-  // second-level transposition indices: slots 0,1 from W01 pair Y, slots 2,3 from W23 pair Y (+8 selects the second source)
-  const __m512i tq0 = _mm512_setr_epi64(0, 1, 8, 9, 0, 0, 0, 0), tq1 = _mm512_setr_epi64(2, 3, 10, 11, 0, 0, 0, 0),
-                tq2 = _mm512_setr_epi64(4, 5, 12, 13, 0, 0, 0, 0), tq3 = _mm512_setr_epi64(6, 7, 14, 15, 0, 0, 0, 0);
-  const __m512i b0 = _mm512_set1_epi64(0), b1 = _mm512_set1_epi64(1), b2 = _mm512_set1_epi64(2), b3 = _mm512_set1_epi64(3);
-  // T[4]: slot X = R[X][4]
-  const __m512i t4a = _mm512_setr_epi64(4, 12, 0, 0, 0, 0, 0, 0);   // (R0, R1) -> slots 0, 1
-  const __m512i t4b = _mm512_setr_epi64(0, 0, 4, 12, 0, 0, 0, 0);   // (R2, R3) -> slots 2, 3
-  const __m512i t4c = _mm512_setr_epi64(0, 1, 10, 11, 0, 0, 0, 0);  // merge the two pairs
-  const __m512i t4d = _mm512_setr_epi64(0, 1, 2, 3, 12, 0, 0, 0);   // slot 4 <- R4[4]
+  const __m512i im1 = _mm512_load_si512(k.rot_m1), ip1 = _mm512_load_si512(k.rot_p1), nat = _mm512_load_si512(k.natural);
+  alignas(64) uint64_t r4[8];
+  // slot kTau[4] of plane P <- r4[Y], straight from memory (written as asm so that the compiler cannot turn the store + loads back
+  // into register shuffles, which is exactly the port pressure this avoids)
+#define CHPIR_MERGE_X4(P, Y) asm("vpbroadcastq %2, %0 %{%1%}" : "+v"(P) : "Yk"(mx4), "m"(r4[Y]), "m"(*(const __m512i *)r4))
   for (uint64_t blk = 0; blk < nblocks; blk++) {
     for (int r = 0; r < 12; r++) {
       // theta
@@ -143,34 +144,42 @@ __attribute__((target("avx512f,avx512vl"))) void squeeze_avx512(uint64_t s[25], 
       const __m512i Q2 = _mm512_permutexvar_epi64(pi2, _mm512_rolv_epi64(P2, rho2));
       const __m512i Q3 = _mm512_permutexvar_epi64(pi3, _mm512_rolv_epi64(P3, rho3));
       const __m512i Q4 = _mm512_permutexvar_epi64(pi4, _mm512_rolv_epi64(P4, rho4));
-      // chi is register-wise in this representation: R[X] slot Y = A'[X][Y]; iota on (0, 0)
-      const __m512i R0 = _mm512_xor_si512(_mm512_ternarylogic_epi64(Q0, Q1, Q2, 0xD2), _mm512_load_si512(k.rc[r]));
+      // chi is register-wise in this representation: R[X] slot Y = A'[X][Y]
+      const __m512i R4 = _mm512_ternarylogic_epi64(Q4, Q0, Q1, 0xD2);
+      asm("vmovdqa64 %1, %0" : "=m"(*(__m512i *)r4) : "v"(R4));
+      const __m512i R0 = _mm512_ternarylogic_epi64(Q0, Q1, Q2, 0xD2);
       const __m512i R1 = _mm512_ternarylogic_epi64(Q1, Q2, Q3, 0xD2);
       const __m512i R2 = _mm512_ternarylogic_epi64(Q2, Q3, Q4, 0xD2);
       const __m512i R3 = _mm512_ternarylogic_epi64(Q3, Q4, Q0, 0xD2);
-      const __m512i R4 = _mm512_ternarylogic_epi64(Q4, Q0, Q1, 0xD2);
-      // transpose back to planes
-      const __m512i W01 = _mm512_permutex2var_epi64(R0, tab, R1), W23 = _mm512_permutex2var_epi64(R2, tab, R3);
-      P0 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq0, W23), 0x10, b0, R4);
-      P1 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq1, W23), 0x10, b1, R4);
-      P2 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq2, W23), 0x10, b2, R4);
-      P3 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(W01, tq3, W23), 0x10, b3, R4);
-      const __m512i e01 = _mm512_permutex2var_epi64(R0, t4a, R1), e23 = _mm512_permutex2var_epi64(R2, t4b, R3);
-      P4 = _mm512_permutex2var_epi64(_mm512_permutex2var_epi64(e01, t4c, e23), t4d, R4);
+      // transpose back to planes: 128-bit lane j of lo = (R[even][2j], R[odd][2j]), of hi = (R[even][2j+1], R[odd][2j+1])
+      const __m512i lo01 = _mm512_unpacklo_epi64(R0, R1), hi01 = _mm512_unpackhi_epi64(R0, R1);
+      const __m512i lo23 = _mm512_unpacklo_epi64(R2, R3), hi23 = _mm512_unpackhi_epi64(R2, R3);
+      P0 = _mm512_shuffle_i64x2(lo01, lo23, 0x00);
+      P1 = _mm512_shuffle_i64x2(hi01, hi23, 0x00);
+      P2 = _mm512_shuffle_i64x2(lo01, lo23, 0x11);
+      P3 = _mm512_shuffle_i64x2(hi01, hi23, 0x11);
+      P4 = _mm512_shuffle_i64x2(lo01, lo23, 0x22);
+      CHPIR_MERGE_X4(P0, 0);
+      P0 = _mm512_xor_si512(P0, _mm512_load_si512(k.rc[r]));  // iota on lane (0, 0); P0 is the plane that is ready first
+      CHPIR_MERGE_X4(P1, 1);
+      CHPIR_MERGE_X4(P2, 2);
+      CHPIR_MERGE_X4(P3, 3);
+      CHPIR_MERGE_X4(P4, 4);
     }
-    // 168 bytes = lanes 0..20: planes 0..3 whole, lane (0, 4)
+    // 168 bytes = lanes 0..20: planes 0..3 whole, lane (0, 4) (slot kTau[0] = 0 of plane 4)
     uint8_t *o = out + blk * kXofRate;
-    _mm512_mask_storeu_epi64(o, m5, P0);
-    _mm512_mask_storeu_epi64(o + 40, m5, P1);
-    _mm512_mask_storeu_epi64(o + 80, m5, P2);
-    _mm512_mask_storeu_epi64(o + 120, m5, P3);
+    _mm512_mask_storeu_epi64(o, m5, _mm512_permutexvar_epi64(nat, P0));
+    _mm512_mask_storeu_epi64(o + 40, m5, _mm512_permutexvar_epi64(nat, P1));
+    _mm512_mask_storeu_epi64(o + 80, m5, _mm512_permutexvar_epi64(nat, P2));
+    _mm512_mask_storeu_epi64(o + 120, m5, _mm512_permutexvar_epi64(nat, P3));
     _mm512_mask_storeu_epi64(o + 160, 0x01, P4);
   }
-  _mm512_mask_storeu_epi64(s + 0, m5, P0);
-  _mm512_mask_storeu_epi64(s + 5, m5, P1);
-  _mm512_mask_storeu_epi64(s + 10, m5, P2);
-  _mm512_mask_storeu_epi64(s + 15, m5, P3);
-  _mm512_mask_storeu_epi64(s + 20, m5, P4);
+#undef CHPIR_MERGE_X4
+  _mm512_mask_storeu_epi64(s + 0, m5, _mm512_permutexvar_epi64(nat, P0));
+  _mm512_mask_storeu_epi64(s + 5, m5, _mm512_permutexvar_epi64(nat, P1));
+  _mm512_mask_storeu_epi64(s + 10, m5, _mm512_permutexvar_epi64(nat, P2));
+  _mm512_mask_storeu_epi64(s + 15, m5, _mm512_permutexvar_epi64(nat, P3));
+  _mm512_mask_storeu_epi64(s + 20, m5, _mm512_permutexvar_epi64(nat, P4));
 }
 
 bool have_avx512() {
@@ -208,14 +217,15 @@ int best_impl() {
   static const int best = [] {
     int win = kXofScalar;
     double win_t = 1e30;
-    std::vector<uint8_t> buf(2048 * kXofRate);
+    constexpr uint64_t kCal = 4096;
+    std::vector<uint8_t> buf(kCal * kXofRate);
     for (int impl : {kXofScalar, kXofBmi2, kXofAvx512}) {
       uint64_t st[25] = {1, 2, 3};
-      if (!run_impl(impl, st, buf.data(), 64)) continue;  // warm up / availability
+      if (!run_impl(impl, st, buf.data(), kCal)) continue;  // availability + warm-up (~0.5 ms: past the frequency-licence transition)
       double t = 1e30;
-      for (int rep = 0; rep < 3; rep++) {
+      for (int rep = 0; rep < 5; rep++) {
         const auto t0 = std::chrono::steady_clock::now();
-        run_impl(impl, st, buf.data(), 2048);
+        run_impl(impl, st, buf.data(), kCal);
         t = std::min(t, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
       }
       if (t < win_t) win_t = t, win = impl;
