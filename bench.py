@@ -332,10 +332,23 @@ def run_b200(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         srv_g, hint_g, fb_g = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=7, batch_tc=2, a_expand="host",
-                                                          db_encode="device")
+                                                          db_encode="device", a_cache=True)
         wall_g = time.perf_counter() - t0
         tg = srv_g.setup_timing()
         assert hint_g == hint_e and fb_g == fb_e, "device row fill changed the hint or the filter parameters"
+        # a database UPDATE: same seed, same keys, new values.  A depends on (seed, K) only and was left resident in HBM by the
+        # setup above (a_cache), so this Server::setup runs no XOF chain: filter + row fill + pack + the tensor-core hint GEMM.
+        # Its hint is checked end to end below: the client set up from it recovers the NEW values.
+        del srv_g
+        vals = vals[::-1].copy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        srv_g, hint_g, fb_g = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=8, batch_tc=2, a_expand="host",
+                                                          db_encode="device", a_cache=True)
+        wall_u = time.perf_counter() - t0
+        tu = srv_g.setup_timing()
+        assert tu["a_cache_hit"] == 1.0
+        cached_a_bytes = cp.drop_a_cache(local_rank)
         # a complete PIR round on this real database: GPU client (A resident in HBM) -> Server::respond -> recover the value
         t0 = time.perf_counter()
         client = cp.Client.setup(SEED_MU, hint_g, fb_g, device=local_rank, a_expand="host")
@@ -365,6 +378,10 @@ def run_b200(args):
                                 "wall_s": wall_e, **{k: round(v, 6) for k, v in te.items()}, "a_expand": "host", "db_entries": n_db, "key_bytes": 32,
                                 "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e),
                                 "with_device_row_fill": {"wall_s": wall_g, **{k: round(v, 6) for k, v in tg.items()}, "identical_hint_and_filter_bytes": True},
+                                "after_database_update_with_cached_a": {
+                                    "wall_s": wall_u, **{k: round(v, 6) for k, v in tu.items()}, "cached_a_bytes": cached_a_bytes,
+                                    "note": "same seed and keys, new values; A (seed- and K-dependent only) reused from HBM (chpir_setup_opts.a_cache), "
+                                            "device row fill; the PIR round below runs against THIS server and hint"},
                                 "pir_round_gpu_client": pir_round}
         del hint_e, keys, vals
     if world > 1 and hint is not None:

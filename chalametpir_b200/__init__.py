@@ -12,6 +12,7 @@ from .server import (
     Server,
     db_matrix_shape,
     device_count,
+    drop_a_cache,
     encode_kv_database,
     encode_kv_database_device,
     find_mat_elem_bit_len,
@@ -34,6 +35,7 @@ __all__ = [
     "LIB_PATH",
     "db_matrix_shape",
     "device_count",
+    "drop_a_cache",
     "encode_kv_database",
     "encode_kv_database_device",
     "find_mat_elem_bit_len",

@@ -29,6 +29,7 @@ class SetupOpts(C.Structure):
         ("host_chunk_rows", C.c_uint32),
         ("respond_coalesce", C.c_uint32),
         ("db_encode", C.c_uint32),
+        ("a_cache", C.c_uint32),
     ]
 
 
@@ -37,7 +38,7 @@ A_EXPAND_HOST_PIPELINED = 1
 
 
 class SetupTiming(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("host_encode_s", "h2d_s", "pack_s", "expand_a_s", "gemm_s", "d2h_s", "total_s", "device_encode_s", "xof_host_busy_s")]
+    _fields_ = [(n, C.c_double) for n in ("host_encode_s", "h2d_s", "pack_s", "expand_a_s", "gemm_s", "d2h_s", "total_s", "device_encode_s", "xof_host_busy_s", "a_cache_hit", "xof_host_wait_s")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -79,6 +80,7 @@ EXPORTS = [
     "chpir_device_count",
     "chpir_ctx_create",
     "chpir_ctx_destroy",
+    "chpir_ctx_drop_a_cache",
     "chpir_host_alloc",
     "chpir_host_free",
     "chpir_find_mat_elem_bit_len",
@@ -129,6 +131,8 @@ lib.chpir_device_count.argtypes = [C.POINTER(C.c_int)]
 lib.chpir_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
 lib.chpir_ctx_destroy.restype = None
 lib.chpir_ctx_destroy.argtypes = [_vp]
+lib.chpir_ctx_drop_a_cache.restype = C.c_int
+lib.chpir_ctx_drop_a_cache.argtypes = [_vp, C.POINTER(C.c_uint64)]
 lib.chpir_host_alloc.argtypes = [C.c_size_t, C.POINTER(_vp)]
 lib.chpir_host_free.restype = None
 lib.chpir_host_free.argtypes = [_vp]

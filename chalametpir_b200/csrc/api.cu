@@ -195,12 +195,13 @@ namespace {
 int validate_bits(uint32_t b) { return (b >= 4 && b <= 14) ? CHPIR_OK : CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH; }
 
 // Hint GEMM fed by a HostAPipe (started here with a two-panel ring unless the caller started one earlier).
+// keep_a: the ring is made as deep as A and handed to the ctx afterwards (chpir_setup_opts.a_cache).
 int hint_host_pipelined(chpir_ctx *ctx, const uint8_t *seed, const GemmTcB *g, uint32_t m, uint64_t K, uint32_t ncols, uint32_t *c_dev,
-                        uint32_t chunk_rows_opt, HostAPipe *pipe, cudaStream_t st, float *gemm_ms_out, double *xof_busy_s) {
+                        uint32_t chunk_rows_opt, HostAPipe *pipe, cudaStream_t st, float *gemm_ms_out, double *xof_busy_s, double *xof_wait_s, bool keep_a) {
   HostAPipe own;
   if (!pipe) {
     pipe = &own;
-    if (int rc = own.start(ctx->device, seed, m, K, chunk_rows_opt, 2); rc != CHPIR_OK) return rc;
+    if (int rc = own.start(ctx->device, seed, m, K, chunk_rows_opt, keep_a ? (m + 127) / 128 : 2); rc != CHPIR_OK) return rc;
   }
   const uint32_t panels = pipe->panels();
   struct Ev {
@@ -238,7 +239,48 @@ int hint_host_pipelined(chpir_ctx *ctx, const uint8_t *seed, const GemmTcB *g, u
     }
   *gemm_ms_out = gemm_ms;
   *xof_busy_s = pipe->busy_s();
+  *xof_wait_s = pipe->wait_s();
+  if (rc == CHPIR_OK && keep_a && pipe->depth() == panels) {  // the ring holds every panel: it IS A, row-major u32
+    if (ctx->a_cache.a) cudaFree(ctx->a_cache.a);
+    ctx->a_cache.a = pipe->take_panels();
+    ctx->a_cache.m = m, ctx->a_cache.K = K;
+    std::memcpy(ctx->a_cache.seed, seed, 32);
+  }
   return rc;
+}
+
+// Hint GEMM from the A a previous setup left resident in the ctx: per 128-row panel, split the u32 rows into byte planes and multiply.
+int hint_from_cached_a(chpir_ctx *ctx, const GemmTcB *g, uint32_t m, uint64_t K, uint32_t ncols, uint32_t *c_dev, cudaStream_t st, float *gemm_ms_out) {
+  const uint32_t panels = (m + 127) / 128;
+  struct Ev {
+    std::vector<cudaEvent_t> ev;
+    ~Ev() {
+      for (auto e : ev)
+        if (e) cudaEventDestroy(e);
+    }
+  } evs;
+  evs.ev.resize(2 * panels, nullptr);
+  for (auto &e : evs.ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+  for (uint32_t p = 0; p < panels; p++) {
+    const uint32_t rows = std::min(m, (p + 1) * 128) - p * 128;
+    if (int rc = gemm_tc_load_panel_u32(g, int(p & 1), ctx->a_cache.a + uint64_t(p) * 128u * K, rows, st); rc != CHPIR_OK) return rc;
+    cudaEventRecord(evs.ev[2 * p], st);
+    if (int rc = gemm_tc_panel(g, int(p & 1), rows, c_dev + size_t(p) * 128u * ncols, st); rc != CHPIR_OK) return rc;
+    cudaEventRecord(evs.ev[2 * p + 1], st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "setup: hint GEMM from the cached A");
+    return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+  }
+  float gemm_ms = 0.f;
+  for (uint32_t p = 0; p < panels; p++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, evs.ev[2 * p], evs.ev[2 * p + 1]) == cudaSuccess) gemm_ms += ms;
+  }
+  *gemm_ms_out = gemm_ms;
+  return CHPIR_OK;
 }
 
 // Core of setup once D (K x ld u32, device) is resident.  d_dev columns [col0, col0+ncols) form this server's slice.
@@ -265,6 +307,8 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   if (int rc = launch_pack(d_dev, K, ld, col0, srv->layout, srv->d_packed, st); rc != CHPIR_OK) return rc;
   t_pack.stop(st);
   srv->plan = plan_respond(srv->layout, K, ctx->sm_count);
+  double tt = trace_now();
+  trace_phase("core: plan_respond", tt);
 
   const uint32_t m = o.lwe_rows ? o.lwe_rows : CHPIR_LWE_DIMENSION;
   if (!o.skip_hint) {
@@ -293,7 +337,9 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
       // GEMM reads, into a two-buffer ring; each panel is multiplied as soon as it exists.  One stream: the XOF chain is
       // serial and ~1000x longer than a panel GEMM, so there is nothing to gain from overlapping them.
       GemmTcB *g = nullptr;
+      trace_phase("core: scratch + hint alloc", tt);
       if (int rc = gemm_tc_prepare(d_dev + col0, ld, K, ncols, b, ctx->sm_count, st, &g); rc != CHPIR_OK) return rc;
+      trace_phase("core: gemm_tc_prepare", tt);
       struct Guard {
         GemmTcB *g;
         std::vector<cudaEvent_t> ev;
@@ -308,9 +354,33 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
         if (cudaEventCreate(&e) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
       CHPIR_CUDA(cudaMemsetAsync(c.p, 0, size_t(m) * ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
       t_all.start(st);
-      if (o.a_expand == CHPIR_A_EXPAND_HOST_PIPELINED) {
+      bool a_filled_now = false;
+      if (o.a_cache && !ctx->a_cache.matches(seed, m, K) && o.a_expand != CHPIR_A_EXPAND_HOST_PIPELINED) {
+        a_filled_now = true;
+        // device expansion with a_cache: squeeze A once as row-major u32 (what the cache holds), then take the cached route below
+        if (ctx->a_cache.a) cudaFree(ctx->a_cache.a);
+        ctx->a_cache = chpir_ctx::ACache{};
+        DevBuf a;
+        if (int rc = a.alloc(size_t(m) * K * 4); rc != CHPIR_OK) return rc;
+        if (int rc = launch_expand(seed, a.as<uint8_t>(), uint64_t(m) * K * 4, scratch.as<uint8_t>(), st); rc != CHPIR_OK) return rc;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+          set_last_cuda_error(e, "setup: expand A for the cache");
+          return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+        }
+        ctx->a_cache.a = static_cast<uint32_t *>(a.release());
+        ctx->a_cache.m = m, ctx->a_cache.K = K;
+        std::memcpy(ctx->a_cache.seed, seed, 32);
+      }
+      if (o.a_cache && ctx->a_cache.matches(seed, m, K)) {
+        if (pipe) pipe->shutdown();  // started by the caller before it could know: not needed
+        if (int rc = hint_from_cached_a(ctx, g, m, K, ncols, c.as<uint32_t>(), st, &gemm_ms); rc != CHPIR_OK) return rc;
+        t_all.stop(st);
+        srv->timing.a_cache_hit = a_filled_now ? 0.0 : 1.0;
+      } else if (o.a_expand == CHPIR_A_EXPAND_HOST_PIPELINED) {
         const double w0 = now_s();
-        if (int rc = hint_host_pipelined(ctx, seed, g, m, K, ncols, c.as<uint32_t>(), o.host_chunk_rows, pipe, st, &gemm_ms, &srv->timing.xof_host_busy_s);
+        if (int rc = hint_host_pipelined(ctx, seed, g, m, K, ncols, c.as<uint32_t>(), o.host_chunk_rows, pipe, st, &gemm_ms, &srv->timing.xof_host_busy_s,
+                                         &srv->timing.xof_host_wait_s, o.a_cache != 0);
             rc != CHPIR_OK)
           return rc;
         host_wall_ms = float((now_s() - w0) * 1e3);
@@ -344,6 +414,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
         guard.g = nullptr;
       }
     }
+    trace_phase("core: A + hint GEMM", tt);
     const float all_ms = host_wall_ms > 0.f ? host_wall_ms : t_all.ms();
     const double t0 = now_s();
     const uint32_t hdr[2] = {m, ncols};
@@ -351,6 +422,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
     CHPIR_CUDA(cudaMemcpyAsync(hint_out + 8, c.p, size_t(m) * ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
     srv->timing.d2h_s = now_s() - t0;
+    trace_phase("core: hint download", tt);
     srv->timing.gemm_s = gemm_ms * 1e-3;
     srv->timing.expand_a_s = (all_ms - gemm_ms) * 1e-3;
     srv->last_gemm_ms = gemm_ms;
@@ -539,7 +611,22 @@ void chpir_ctx_destroy(chpir_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
   }
+  if (ctx->a_cache.a) cudaFree(ctx->a_cache.a);
   delete ctx;
+}
+
+int chpir_ctx_drop_a_cache(chpir_ctx *ctx, uint64_t *bytes_freed) {
+  CHPIR_GUARD_BEGIN
+  if (!ctx) return CHPIR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (bytes_freed) *bytes_freed = ctx->a_cache.a ? uint64_t(ctx->a_cache.m) * ctx->a_cache.K * 4 : 0;
+  if (ctx->a_cache.a) {
+    CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    cudaFree(ctx->a_cache.a);
+  }
+  ctx->a_cache = chpir_ctx::ACache{};
+  return CHPIR_OK;
+  CHPIR_GUARD_END
 }
 
 int chpir_host_alloc(size_t bytes, void **out) {
@@ -694,7 +781,12 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
   // its panel ring is as deep as A itself (lwe_rows x K u32 in HBM) so that it never has to wait for D
   HostAPipe pipe;
   HostAPipe *pipe_p = nullptr;
-  if (opts && opts->a_expand == CHPIR_A_EXPAND_HOST_PIPELINED && !opts->skip_hint && opts->gemm_variant == 0) {
+  bool a_cached = false;
+  if (opts && opts->a_cache) {  // A from an earlier setup with this seed: no chain to walk
+    std::lock_guard<std::mutex> g(ctx->mu);
+    a_cached = ctx->a_cache.matches(seed, opts->lwe_rows ? opts->lwe_rows : CHPIR_LWE_DIMENSION, K);
+  }
+  if (opts && opts->a_expand == CHPIR_A_EXPAND_HOST_PIPELINED && !opts->skip_hint && opts->gemm_variant == 0 && !a_cached) {
     const uint32_t m = opts->lwe_rows ? opts->lwe_rows : CHPIR_LWE_DIMENSION;
     if (int rc = pipe.start(ctx->device, seed, m, K, opts->host_chunk_rows, (m + 127) / 128); rc != CHPIR_OK) return rc;
     pipe_p = &pipe;
@@ -714,8 +806,16 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
     set_encode_threads(0);
     if (rc != CHPIR_OK) return rc;
     const double t1 = now_s();
+    {
+      double tt = t0;
+      trace_phase("from_db: start pipe + device encode", tt);
+    }
     chpir_server *srv = new chpir_server();
     rc = setup_core(ctx, seed, d.as<uint32_t>(), K, uint32_t(N), c0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv, pipe_p);
+    {
+      double tt = t1;
+      trace_phase("from_db: setup_core", tt);
+    }
     if (rc != CHPIR_OK) {
       delete srv;
       return rc;

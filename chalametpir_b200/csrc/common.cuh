@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -102,4 +103,12 @@ struct chpir_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   std::mutex mu;  // serialises setup-type work on `stream`
+  // chpir_setup_opts.a_cache: A = generate_from_seed(m, K, seed) as row-major u32, kept between setups (guarded by mu)
+  struct ACache {
+    uint8_t seed[32] = {};
+    uint32_t m = 0;
+    uint64_t K = 0;
+    uint32_t *a = nullptr;
+    bool matches(const uint8_t *s, uint32_t m_, uint64_t K_) const { return a && m == m_ && K == K_ && std::memcmp(seed, s, 32) == 0; }
+  } a_cache;
 };

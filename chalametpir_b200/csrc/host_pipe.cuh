@@ -120,13 +120,30 @@ class HostAPipe {
     depth_ = std::max(1u, std::min(depth, panels_));
     while (depth_ > 2 && uint64_t(depth_) * panel_bytes_ > (48ull << 30)) depth_--;
     if (cudaSetDevice(device) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
-    for (int i = 0; i < kBufs; i++) {
-      if (cudaMallocHost(&pinned_[i], uint64_t(chunk_rows) * row_bytes_) != cudaSuccess) {
+    // The chain is the critical path of the whole setup, so it starts the moment ONE pinned chunk exists; the other chunks, the
+    // events, the panel ring in HBM (8.4 GB at 2^20 entries: a few tenths of a second of cudaMalloc) and the upload stream are
+    // created while the producer is already squeezing: kBufs chunks of ~32 MB are ~0.3 s of chain to fill before it needs the
+    // uploader to have started.
+    const uint64_t chunk_bytes = uint64_t(chunk_rows) * row_bytes_;
+    auto pin = [&](int i) {
+      if (cudaMallocHost(&pinned_[i], chunk_bytes) != cudaSuccess) {
         set_last_cuda_error(cudaGetLastError(), "pinned XOF chunk ring");
-        return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+        pinned_[i] = nullptr;
+        return false;
       }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pinned_ready_ = i + 1;
+      }
+      cv_.notify_all();
+      return true;
+    };
+    if (!pin(0)) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
+    producer_ = std::thread([this] { produce(); });
+    for (int i = 1; i < kBufs; i++)  // ~10 ms each; the producer needs ~20 ms per chunk, so it never catches up with this loop
+      if (!pin(i)) return CHPIR_ERR_HOST_ALLOCATION_FAILED;  // (on any failure below the destructor stops the threads)
+    for (int i = 0; i < kBufs; i++)
       if (cudaEventCreateWithFlags(&copied_[i], cudaEventDisableTiming) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    }
     if (int rc = panels_dev_.alloc(uint64_t(depth_) * panel_bytes_); rc != CHPIR_OK) return rc;
     ready_.assign(panels_, nullptr);
     consumed_.assign(panels_, nullptr);
@@ -135,8 +152,7 @@ class HostAPipe {
           cudaEventCreateWithFlags(&consumed_[p], cudaEventDisableTiming) != cudaSuccess)
         return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
     if (cudaStreamCreateWithFlags(&up_, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    producer_ = std::thread([this] { produce(); });
-    uploader_ = std::thread([this] { upload(); });
+    uploader_ = std::thread([this] { upload(); });  // the first chunks are already waiting for it
     return CHPIR_OK;
   }
 
@@ -170,15 +186,20 @@ class HostAPipe {
     if (producer_.joinable()) producer_.join();
     if (uploader_.joinable()) uploader_.join();
     if (up_) cudaStreamSynchronize(up_);
+    for (auto &p : pinned_)  // the chunk ring is only needed while the chain runs (a client keeps the pipe alive as the owner of A)
+      if (p) cudaFreeHost(p), p = nullptr;
   }
   double busy_s() const { return busy_; }            // time the producer core spent inside the XOF
+  double wait_s() const { return wait_; }            // time the producer core waited for a free pinned chunk (the chain stood still)
   uint32_t panels() const { return panels_; }
   uint32_t depth() const { return depth_; }
   // the panel ring; with depth() == panels() this is A itself, row-major u32
   const uint32_t *base() const { return panels_dev_.as<uint32_t>(); }
+  // hands the ring over to the caller (chpir_setup_opts.a_cache); only meaningful after shutdown() and with depth() == panels()
+  uint32_t *take_panels() { return static_cast<uint32_t *>(panels_dev_.release()); }
 
  private:
-  static constexpr int kBufs = 4;
+  static constexpr int kBufs = 16;
 
   void fail(int rc) {
     {
@@ -195,13 +216,20 @@ class HostAPipe {
     host_xof_init(&xs.x, seed_);
     for (uint64_t i = 0; i < chunks_.size(); i++) {
       const int b = int(i % kBufs);
+      if (i < uint64_t(kBufs)) {  // first lap: the chunk may still be on its way through cudaMallocHost in start()
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return pinned_ready_ > b || abort_; });
+        if (abort_) return;
+      }
       if (i >= uint64_t(kBufs)) {
+        const double w0 = now_s();
         {
           std::unique_lock<std::mutex> lk(mu_);
           cv_.wait(lk, [&] { return issued_ > i - kBufs || abort_; });
           if (abort_) return;
         }
         cudaEventSynchronize(copied_[b]);  // the upload of chunk i - kBufs has left this buffer
+        wait_ += now_s() - w0;
       }
       {
         std::lock_guard<std::mutex> lk(mu_);
@@ -263,11 +291,12 @@ class HostAPipe {
   std::mutex mu_;
   std::condition_variable cv_;
   uint64_t filled_ = 0, issued_ = 0;
+  int pinned_ready_ = 0;
   uint32_t uploaded_panels_ = 0, released_panels_ = 0;
   bool abort_ = false;
   int rc_ = CHPIR_OK;
   std::thread producer_, uploader_;
-  double busy_ = 0.0;
+  double busy_ = 0.0, wait_ = 0.0;
 };
 
 }  // namespace chpir

@@ -87,6 +87,9 @@ CHPIR_API const char *chpir_last_cuda_error(void);
 CHPIR_API int chpir_device_count(int *count);
 CHPIR_API int chpir_ctx_create(int device_ordinal, chpir_ctx **out);
 CHPIR_API void chpir_ctx_destroy(chpir_ctx *ctx);
+/* Frees the LWE matrix a setup with chpir_setup_opts.a_cache = 1 left resident in the ctx (no-op if there is none);
+ * *bytes_freed (may be NULL) receives its size. */
+CHPIR_API int chpir_ctx_drop_a_cache(chpir_ctx *ctx, uint64_t *bytes_freed);
 
 /* Page-locked host buffers for queries and responses: chpir_server_respond* accept any host pointer, but only page-locked memory
  * is copied by DMA at the full PCIe rate (a 4.7 MB query moves in 90 us instead of ~500 us from pageable memory). */
@@ -137,6 +140,11 @@ typedef struct chpir_setup_opts {
                             still gets a batch of one with no added wait.  Costs 2 x 128 x K x 4 bytes of HBM staging.  */
   uint32_t db_encode;    /* chpir_server_setup_from_db only: where the rows of D are encoded and filled, CHPIR_DB_ENCODE_HOST
                             (default, north_star) or CHPIR_DB_ENCODE_DEVICE                                            */
+  uint32_t a_cache;      /* 1 = keep A = generate_from_seed(lwe_rows, K, seed) resident in the ctx (row-major u32, 8.4 GB of HBM at
+                            2^20 entries) and reuse it: A depends on the seed and on K only, not on the database, so a server that
+                            re-runs setup after a database update with the same seed skips the serial XOF chain -- the whole of
+                            the hint computation is then the tensor-core GEMM (milliseconds).  A setup with another seed,
+                            lwe_rows or K replaces the cached matrix.  Same hint bytes either way.                      */
 } chpir_setup_opts;
 
 /* chpir_setup_opts.db_encode.  Key digests and filter construction (peeling) always run on the host.
@@ -196,6 +204,9 @@ typedef struct chpir_setup_timing {
   double device_encode_s; /* db_encode = DEVICE: device time of the row-fill waves (part of host_encode_s's wall time) */
   double xof_host_busy_s; /* host-pipelined mode: time the producer core spent inside the XOF (0 in device mode); expand_a_s is the
                              wall time of the whole expansion phase in either mode            */
+  double a_cache_hit;     /* 1.0 if A came from the ctx cache (chpir_setup_opts.a_cache): no XOF chain ran; expand_a_s is then the
+                             time of the u32 -> byte-plane splits around the panel GEMMs            */
+  double xof_host_wait_s; /* host-pipelined mode: time the producer core stood still waiting for a free pinned chunk (uploader behind) */
 } chpir_setup_timing;
 CHPIR_API int chpir_server_setup_timing(const chpir_server *srv, chpir_setup_timing *out);
 

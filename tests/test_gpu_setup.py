@@ -252,3 +252,73 @@ def test_setup_with_device_row_fill_end_to_end(arity):
         done += 1
     assert done >= 5
     assert srv.setup_timing()["device_encode_s"] > 0
+
+
+# ------------------------------------------------------------------ A kept resident between setups (chpir_setup_opts.a_cache)
+@pytest.mark.parametrize("a_expand", ["host", "device"])
+def test_a_cache_reuses_a_for_a_new_database_and_gives_identical_hints(a_expand):
+    """A depends on (seed, lwe_rows, K) only.  The first setup with a_cache fills the cache, a second one with ANOTHER database of
+    the same K takes A from HBM (no XOF chain) and must produce exactly the hint an uncached setup produces; a different seed,
+    LWE dimension or K is a miss and replaces the cached matrix."""
+    cp.drop_a_cache()
+    K, N, b, lwe = 2051, 70, 9, 300  # ragged: 3 panels (128 + 128 + 44 rows), 4K not a multiple of the XOF rate
+    rng = np.random.default_rng(31)
+    D1 = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    D2 = rng.integers(0, 1 << b, size=(K, N + 9), dtype=np.uint32)
+    want1 = O.Server.setup_from_matrix(SEED, D1, b, lwe_rows=lwe, want_server=False)[1]
+    want2 = O.Server.setup_from_matrix(SEED, D2, b, lwe_rows=lwe, want_server=False)[1]
+    s1, h1 = cp.Server.setup_from_matrix(SEED, D1, b, lwe_rows=lwe, a_expand=a_expand, a_cache=True)
+    assert h1 == want1 and s1.setup_timing()["a_cache_hit"] == 0
+    s2, h2 = cp.Server.setup_from_matrix(SEED, D2, b, lwe_rows=lwe, a_expand=a_expand, a_cache=True)
+    t2 = s2.setup_timing()
+    assert h2 == want2 and t2["a_cache_hit"] == 1 and t2["xof_host_busy_s"] == 0
+    # the cached route also serves the other expansion mode (the cache is keyed by what A is, not by how it was made)
+    other = "device" if a_expand == "host" else "host"
+    s3, h3 = cp.Server.setup_from_matrix(SEED, D1, b, lwe_rows=lwe, a_expand=other, a_cache=True)
+    assert h3 == want1 and s3.setup_timing()["a_cache_hit"] == 1
+    # a_cache off: the cache is neither consulted nor touched
+    s4, h4 = cp.Server.setup_from_matrix(SEED, D1, b, lwe_rows=lwe, a_expand=a_expand)
+    assert h4 == want1 and s4.setup_timing()["a_cache_hit"] == 0
+    # misses: another seed, another LWE dimension, another K
+    seed2 = bytes(range(32, 64))
+    s5, h5 = cp.Server.setup_from_matrix(seed2, D1, b, lwe_rows=lwe, a_expand=a_expand, a_cache=True)
+    assert s5.setup_timing()["a_cache_hit"] == 0 and h5 == O.Server.setup_from_matrix(seed2, D1, b, lwe_rows=lwe, want_server=False)[1]
+    s6, h6 = cp.Server.setup_from_matrix(seed2, D1, b, lwe_rows=lwe - 45, a_expand=a_expand, a_cache=True)
+    assert s6.setup_timing()["a_cache_hit"] == 0 and h6 == O.Server.setup_from_matrix(seed2, D1, b, lwe_rows=lwe - 45, want_server=False)[1]
+    s7, h7 = cp.Server.setup_from_matrix(seed2, D1[:-3], b, lwe_rows=lwe - 45, a_expand=a_expand, a_cache=True)
+    assert s7.setup_timing()["a_cache_hit"] == 0 and h7 == O.Server.setup_from_matrix(seed2, D1[:-3], b, lwe_rows=lwe - 45, want_server=False)[1]
+    s8, h8 = cp.Server.setup_from_matrix(seed2, D1[:-3], b, lwe_rows=lwe - 45, a_expand=a_expand, a_cache=True)
+    assert s8.setup_timing()["a_cache_hit"] == 1 and h8 == h7
+    assert cp.drop_a_cache() == (lwe - 45) * (K - 3) * 4
+    assert cp.drop_a_cache() == 0
+    # responses do not depend on any of this
+    q = O.matrix_to_bytes(rand_u32(rng, (1, K)))
+    assert s1.respond(q) == s3.respond(q) == s4.respond(q)
+
+
+@pytest.mark.parametrize("db_encode", ["host", "device"])
+def test_a_cache_full_setup_after_a_database_update(db_encode):
+    """Server::setup(seed, db) twice with the same seed and a database of the same size but new values (the filter is rebuilt, K stays):
+    the second call reuses A, and its hint still lets the client recover every queried value."""
+    cp.drop_a_cache()
+    seed = bytes(random.Random(19).randbytes(32))
+    db1 = make_db(1800, seed=5, val_len=(8, 120))
+    db2 = {k: bytes(reversed(v)) + b"!" for k, v in db1.items()}
+    lwe = 256
+    s1, h1, f1 = cp.Server.setup(seed, db1, 3, filter_seed_rng=3, a_expand="host", a_cache=True, lwe_rows=lwe, db_encode=db_encode)
+    assert s1.setup_timing()["a_cache_hit"] == 0
+    s2, h2, f2 = cp.Server.setup(seed, db2, 3, filter_seed_rng=4, a_expand="host", a_cache=True, lwe_rows=lwe, db_encode=db_encode)
+    assert s2.setup_timing()["a_cache_hit"] == 1 and s2.rows_k == s1.rows_k
+    s2u, h2u, f2u = cp.Server.setup(seed, db2, 3, filter_seed_rng=4, a_expand="host", lwe_rows=lwe, db_encode=db_encode)
+    assert h2 == h2u and f2 == f2u
+    client = O.Client.setup(seed, h2, f2, lwe_rows=lwe)
+    done = 0
+    for key in list(db2)[:6]:
+        try:
+            q = client.query(key)
+        except O.OracleError:
+            continue
+        assert client.process_response(key, s2.respond(q)) == db2[key]
+        done += 1
+    assert done >= 4
+    cp.drop_a_cache()
