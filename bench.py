@@ -32,6 +32,7 @@ import sys
 import threading
 import time
 
+NO_BCAST = bool(os.environ.get("CHPIR_BENCH_NO_BCAST"))
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -450,8 +451,20 @@ def run_b200(args):
             for _ in range(n):
                 srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
             return
-        bw = dist.broadcast(q_bufs[0], 0, async_op=True)
         gw = [None, None]
+        if NO_BCAST:  # experiment (tools/README.md): queries already resident on every rank, isolates the cost of moving them
+            for i in range(n):
+                p = i & 1
+                srv.respond_device(q_bufs[p].data_ptr(), Q, resp_dev.data_ptr(), stream)
+                if gw[p] is not None:
+                    gw[p].wait()
+                send_bufs[p][:, :nc] = resp_dev
+                gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), async_op=True)
+            for w in gw:
+                if w is not None:
+                    w.wait()
+            return
+        bw = dist.broadcast(q_bufs[0], 0, async_op=True)
         for i in range(n):
             p = i & 1
             bw.wait()
@@ -468,6 +481,31 @@ def run_b200(args):
 
     def step_device():
         run_steps(1)
+
+    if os.environ.get("CHPIR_BENCH_PROFILE") and rank == 0:
+        # experiment: kernel timeline of a few steps on rank 0 (CUPTI through torch.profiler), summarised on stderr
+        from torch.profiler import ProfilerActivity, profile
+        run_steps(3)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_steps(int(os.environ["CHPIR_BENCH_PROFILE"]))
+            torch.cuda.synchronize()
+        try:
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60), file=sys.stderr)
+            evs = sorted((e for e in prof.events() if e.device_type.name == "CUDA"), key=lambda e: e.time_range.start)
+            for e in evs[: 40]:
+                print(f"  t={e.time_range.start - evs[0].time_range.start:9.1f} us  dur={e.time_range.end - e.time_range.start:8.1f} us  {e.name[:70]}", file=sys.stderr)
+            rk = [e for e in evs if "respond_ring" in e.name]
+            if len(rk) > 2:
+                period = [b.time_range.start - a.time_range.start for a, b in zip(rk, rk[1:])]
+                dur = [e.time_range.end - e.time_range.start for e in rk]
+                print(f"  respond kernels: n={len(rk)} period median {statistics.median(period):.1f} us (min {min(period):.1f}, max {max(period):.1f}); "
+                      f"duration median {statistics.median(dur):.1f} us", file=sys.stderr)
+        except Exception as ex:  # diagnostics only
+            print("profile summary failed:", ex, file=sys.stderr)
+    elif os.environ.get("CHPIR_BENCH_PROFILE"):
+        run_steps(3)
+        run_steps(int(os.environ["CHPIR_BENCH_PROFILE"]))
 
     step_device()
     torch.cuda.synchronize()

@@ -33,6 +33,11 @@ PackedLayout make_layout(uint32_t b, uint32_t ncols) {
 
 namespace {
 
+uint32_t env_u32(const char *name, uint32_t dflt) {
+  const char *v = std::getenv(name);
+  return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
 constexpr int kMaxThreads = 768;
 constexpr int kUnroll = 4;
 
@@ -200,11 +205,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 constexpr int kRingMaxThreads = 1024;
 
+__device__ __forceinline__ void bar_sync_consumers(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+// One CTA per SM; CTA (x, y) owns k-rows [x*rows_per_cta, ...) of queries y*q_per_cta ... (q_per_cta = 1 in production, see
+// respond_ring_dispatch).  Within a CTA the producer lane never stops at a query boundary -- the chunk sequence is (query, chunk)
+// flattened -- and the epilogue of a query (fold the R row lanes, one atomic per column) borrows the last stage the consumers read
+// as scratch: two consumer-only barriers and a few shuffles instead of 2*FPW block-wide reduction rounds (at 8-way column sharding
+// a query is ~25 us of streaming per rank, and the old epilogue was ~3 us of it).
 template <int B, int RPT>
 __global__ void __launch_bounds__(kRingMaxThreads, 1)
-    respond_ring_kernel(const uint8_t *__restrict__ packed, const uint32_t *__restrict__ q, uint32_t *__restrict__ resp, uint64_t K, uint32_t units,
-                        uint32_t R, uint32_t stages, uint32_t stage_bytes, uint64_t rows_per_cta, uint32_t ncols, uint32_t q_bulk) {
+    respond_ring_kernel(const uint8_t *__restrict__ packed, const uint32_t *__restrict__ q_all, uint32_t *__restrict__ resp_all, uint64_t K,
+                        uint32_t units, uint32_t R, uint32_t stages, uint32_t stage_bytes, uint64_t rows_per_cta, uint32_t ncols, uint32_t q_bulk,
+                        uint32_t nq, uint32_t q_per_cta) {
   constexpr int FPW = 64 / B;
+  constexpr int NACC = 2 * FPW;
+  // accumulators folded per epilogue pass: the scratch is the last stage of the query, RPT*16 bytes of it per consumer thread
+  constexpr int G = NACC < RPT * 4 ? NACC : RPT * 4;
   extern __shared__ __align__(128) uint8_t ring[];
   const uint32_t S = R * RPT;  // rows per stage
   const uint32_t pitch = units * 16;
@@ -216,13 +232,13 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
   const uint32_t cons_warps = (n_cons + 31) / 32;
   const uint32_t warp = t / 32, lane = t % 32;
 
-  // blockIdx.y = query of a batch (q: nq x K, resp: nq x ncols); the CTAs of consecutive queries overlap head to tail
-  q += uint64_t(blockIdx.y) * K;
-  resp += uint64_t(blockIdx.y) * ncols;
+  const uint32_t q_begin = blockIdx.y * q_per_cta;
+  const uint32_t q_end = q_begin + q_per_cta < nq ? q_begin + q_per_cta : nq;
   const uint64_t k0 = uint64_t(blockIdx.x) * rows_per_cta;
   uint64_t k1 = k0 + rows_per_cta;
   if (k1 > K) k1 = K;
   const uint32_t n_chunks = k0 < k1 ? uint32_t((k1 - k0 + S - 1) / S) : 0u;
+  if (n_chunks == 0 || q_begin >= q_end) return;  // uniform per CTA
 
   if (t == 0) {
     for (uint32_t s = 0; s < stages; s++) {
@@ -234,34 +250,44 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
   }
   __syncthreads();
 
-  uint32_t acc[2 * FPW];
-#pragma unroll
-  for (int i = 0; i < 2 * FPW; i++) acc[i] = 0;
-  const uint32_t u = t % units, r = t / units;
-  const bool active = t < n_cons;
-
   if (warp == cons_warps) {
     // ------------------------------------------------------------------ producer (one lane)
     if (lane == 0) {
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t s = c % stages, ph = (c / stages) & 1;
-        mbar_wait(bar_base + 8 * (stages + s), ph ^ 1);
-        const uint64_t kc = k0 + uint64_t(c) * S;
-        const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
-        const bool qb = q_bulk && rows == S;
-        const uint32_t full = bar_base + 8 * s;
-        mbar_expect_tx(full, rows * pitch + (qb ? S * 4 : 0));
-        const uint32_t dst = ring_base + s * stage_bytes;
-        bulk_g2s(dst, packed + kc * pitch, rows * pitch, full, policy);
-        if (qb) bulk_g2s(dst + d_bytes, q + kc, S * 4, full);
+      uint32_t g = 0;  // chunks issued so far, across queries
+      for (uint32_t qi = q_begin; qi < q_end; qi++) {
+        const uint32_t *q = q_all + uint64_t(qi) * K;
+        for (uint32_t c = 0; c < n_chunks; c++, g++) {
+          const uint32_t s = g % stages, ph = (g / stages) & 1;
+          mbar_wait(bar_base + 8 * (stages + s), ph ^ 1);
+          const uint64_t kc = k0 + uint64_t(c) * S;
+          const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
+          const bool qb = q_bulk && rows == S;
+          const uint32_t full = bar_base + 8 * s;
+          mbar_expect_tx(full, rows * pitch + (qb ? S * 4 : 0));
+          const uint32_t dst = ring_base + s * stage_bytes;
+          bulk_g2s(dst, packed + kc * pitch, rows * pitch, full, policy);
+          if (qb) bulk_g2s(dst + d_bytes, q + kc, S * 4, full);
+        }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ consumers
-    for (uint32_t c = 0; c < n_chunks; c++) {
-      const uint32_t s = c % stages, ph = (c / stages) & 1;
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const uint32_t u = t % units, r = t / units;
+  const bool active = t < n_cons;
+  const uint32_t n_sync = cons_warps * 32;
+  uint32_t g = 0;
+  for (uint32_t qi = q_begin; qi < q_end; qi++) {
+    const uint32_t *q = q_all + uint64_t(qi) * K;
+    uint32_t acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0;
+    uint32_t last_s = 0;
+    for (uint32_t c = 0; c < n_chunks; c++, g++) {
+      const uint32_t s = g % stages, ph = (g / stages) & 1;
       const uint64_t kc = k0 + uint64_t(c) * S;
       const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
       const bool qb = q_bulk && rows == S;
@@ -295,26 +321,49 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * (stages + s));
+      // the last stage of a query is handed back only after the epilogue, which uses it as scratch
+      if (c + 1 < n_chunks) {
+        if (lane == 0) mbar_arrive(bar_base + 8 * (stages + s));
+      } else {
+        last_s = s;
+      }
     }
     unmask_fields<B>(acc);
     unmask_fields<B>(acc + FPW);
-  }
 
-  // fold the R row lanes of each unit (the ring is free now), then one atomic per (CTA, column)
-  __syncthreads();
-  uint32_t *red = reinterpret_cast<uint32_t *>(ring);
+    // Fold the R row lanes of every (unit, accumulator) and publish one atomic per (CTA, column).  Scratch = the stage just
+    // consumed (S*pitch >= n_cons * RPT * 16 bytes), G accumulators per pass; every (accumulator, unit) item is summed by P
+    // adjacent lanes (R/P values each) and finished with shuffles.
+    uint32_t *red = reinterpret_cast<uint32_t *>(ring + last_s * stage_bytes);
+    uint32_t *resp = resp_all + uint64_t(qi) * ncols;
+    const uint32_t P = (R % 4 == 0 && G * units * 4 <= n_sync) ? 4u : (R % 2 == 0 && G * units * 2 <= n_sync) ? 2u : 1u;
+    const uint32_t per = R / P;
 #pragma unroll
-  for (int i = 0; i < 2 * FPW; i++) {
-    if (t < kRingMaxThreads) red[t] = active ? acc[i] : 0u;
-    __syncthreads();
-    if (active && r == 0 && n_chunks > 0) {
-      uint32_t sum = 0;
-      for (uint32_t rr = 0; rr < R; rr++) sum += red[rr * units + u];
-      const uint32_t col = (2 * u + i / FPW) * FPW + (i % FPW);
-      if (col < ncols && sum != 0) atomicAdd(resp + col, sum);
+    for (int g0 = 0; g0 < NACC; g0 += G) {
+      bar_sync_consumers(n_sync);  // everyone is done reading the stage (first pass) / the previous pass's sums
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < G; i++)
+          if (g0 + i < NACC) red[i * n_cons + t] = acc[g0 + i];
+      }
+      bar_sync_consumers(n_sync);
+      const uint32_t n_items = G * units;
+      for (uint32_t base = 0; base < n_items; base += n_sync / P) {  // same trip count for every consumer thread (full-warp shuffles)
+        const uint32_t it = base + t / P, part = t % P;
+        const bool valid = it < n_items;
+        const uint32_t i = valid ? it / units : 0u, uu = valid ? it % units : 0u;
+        uint32_t sum = 0;
+        if (valid)
+          for (uint32_t rr = part * per; rr < (part + 1) * per; rr++) sum += red[i * n_cons + rr * units + uu];
+        if (P >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        if (P == 4) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const uint32_t a = g0 + i;
+        const uint32_t col = (2 * uu + a / FPW) * FPW + (a % FPW);
+        if (valid && part == 0 && a < NACC && col < ncols && sum != 0) atomicAdd(resp + col, sum);
+      }
     }
-    __syncthreads();
+    bar_sync_consumers(n_sync);  // the scratch is dead: hand the stage back to the producer
+    if (lane == 0) mbar_arrive(bar_base + 8 * (stages + last_s));
   }
 }
 
@@ -396,8 +445,13 @@ int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
       configured = reinterpret_cast<const void *>(kernel);
     }
-    kernel<<<dim3(P.ring_grid, nq), P.ring_block, P.ring_smem_bytes, s>>>(packed, q, resp, K, L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes,
-                                                                P.ring_rows_per_cta, L.ncols, q_bulk);
+    // One grid row per query (q_per_cta = 1): the hardware scheduler hands the next query's CTAs to whichever SMs finish first.
+    // Looping over several queries inside one CTA lifetime (CHPIR_RING_Q_PER_CTA > 1) saves the per-query pipeline fill but fixes
+    // the K-range -> SM assignment for the whole batch, and SMs do not stream at equal rates: measured on a 118-column slice
+    // (8-way sharding) 24.7 us per query at 1, 26.0 at 4, 27.3 at 16 (profiles/r1_slice_sweep.txt).
+    const uint32_t q_per_cta = std::max(1u, std::min(env_u32("CHPIR_RING_Q_PER_CTA", 1), nq));
+    kernel<<<dim3(P.ring_grid, (nq + q_per_cta - 1) / q_per_cta), P.ring_block, P.ring_smem_bytes, s>>>(
+        packed, q, resp, K, L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes, P.ring_rows_per_cta, L.ncols, q_bulk, nq, q_per_cta);
     return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   };
   switch (P.ring_rpt) {
@@ -445,13 +499,9 @@ int occupancy_of(int threads) {
     default: return CHPIR_ERR_IMPOSSIBLE_ENCODED_DB_MATRIX_ELEMENT_BIT_LENGTH; \
   }
 
-static uint32_t env_u32(const char *name, uint32_t dflt) {
-  const char *v = std::getenv(name);
-  return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
-}
 
 // Geometry of the bulk-copy ring kernel.  Tunables can be overridden from the environment for experiments:
-// CHPIR_RESPOND_RING=0 disables it, CHPIR_RING_R / CHPIR_RING_RPT / CHPIR_RING_STAGES / CHPIR_RING_CTAS_PER_SM_X100.
+// CHPIR_RESPOND_RING=0 disables it, CHPIR_RING_R / CHPIR_RING_RPT / CHPIR_RING_STAGES / CHPIR_RING_BUDGET_KB (shared memory per CTA) / CHPIR_RING_GRID_MULT (CTAs per SM) / CHPIR_RING_Q_PER_CTA.
 static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPlan *P) {
   P->ring = 0;
   if (env_u32("CHPIR_RESPOND_RING", 1) == 0) return;
@@ -468,7 +518,7 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
   uint32_t rpt = env_u32("CHPIR_RING_RPT", 4);
   if (rpt != 1 && rpt != 2) rpt = 4;
   const uint32_t pitch = units * 16;
-  const uint32_t budget = 200 * 1024;
+  const uint32_t budget = std::min(env_u32("CHPIR_RING_BUDGET_KB", 200), 200u) * 1024;
   while (rpt > 1 && 3 * R * rpt * (pitch + 4) > budget) rpt /= 2;
   const uint32_t S = R * rpt;
   const uint32_t stage_bytes = S * (pitch + 4);
@@ -483,7 +533,7 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
   P->ring_stages = stages;
   P->ring_stage_bytes = stage_bytes;
   P->ring_smem_bytes = std::max<uint32_t>(stages * stage_bytes + 16 * stages, 4096 + 64);
-  P->ring_grid = uint32_t(sm_count);
+  P->ring_grid = uint32_t(sm_count) * std::max(1u, env_u32("CHPIR_RING_GRID_MULT", 1));
   const uint64_t per = (K + P->ring_grid - 1) / P->ring_grid;
   P->ring_rows_per_cta = (per + S - 1) / S * S;
   if (P->ring_rows_per_cta == 0) P->ring_rows_per_cta = S;
