@@ -260,6 +260,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    pg_out = None
     if world > 1:
         # NCCL's kernels run on a high-priority stream: the respond kernel fills every SM (one 175 KB-smem CTA each), and without
         # priority the query broadcast of the next batch only gets SMs once the current batch has drained (no overlap)
@@ -267,6 +268,13 @@ def run_b200(args):
         if os.environ.get("CHPIR_NCCL_MAX_CTAS"):  # experiment knob: fewer NCCL CTAs leave more SMs to the respond kernel
             pg_opts.config.max_ctas = int(os.environ["CHPIR_NCCL_MAX_CTAS"])
         dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
+        # A second communicator for the response gathers.  Collectives of one communicator run in issue order on one stream, and the
+        # gather of batch i-1 cannot finish before the SLOWEST rank has answered batch i-1; with a single communicator the query
+        # broadcast of batch i+1 sat behind it and started ~330 us late, leaving an ~85 us hole in front of every respond launch
+        # (timeline in profiles/r1_n8_timeline.txt).  CHPIR_BENCH_ONE_COMM=1 restores the single communicator.
+        if not os.environ.get("CHPIR_BENCH_ONE_COMM"):
+            pg_out_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            pg_out = dist.new_group(backend="nccl", pg_options=pg_out_opts)
 
     def barrier():
         if world > 1:
@@ -459,7 +467,7 @@ def run_b200(args):
                 if gw[p] is not None:
                     gw[p].wait()
                 send_bufs[p][:, :nc] = resp_dev
-                gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), async_op=True)
+                gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), group=pg_out, async_op=True)
             for w in gw:
                 if w is not None:
                     w.wait()
@@ -474,7 +482,7 @@ def run_b200(args):
             if gw[p] is not None:
                 gw[p].wait()
             send_bufs[p][:, :nc] = resp_dev
-            gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), async_op=True)
+            gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), group=pg_out, async_op=True)
         for w in gw:
             if w is not None:
                 w.wait()
@@ -629,7 +637,7 @@ def run_b200(args):
                     send_bufs[p][:, :nc] = resp2[p]
                     sent[p] = torch.cuda.Event()
                     sent[p].record(s_out)
-                    dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1))
+                    dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), group=pg_out)
                     if rank == 0:
                         r_all_host[p].copy_(gather_bufs[p], non_blocking=True)
             torch.cuda.synchronize()
