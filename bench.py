@@ -597,21 +597,24 @@ def run_b200(args):
 
         k0, k1, ks = sharding.query_slice(K, rank, world)
         q_words = q_host[:, 8:].view(torch.int32)  # Q x K, pinned
-        q_slice = [torch.zeros((Q, ks), dtype=torch.int32, device=dev) for _ in range(2)]
-        q_all = [torch.empty((world, Q, ks), dtype=torch.int32, device=dev) for _ in range(2)]
-        q_rows = [torch.empty((Q, K), dtype=torch.int32, device=dev) for _ in range(2)]
-        resp2 = [torch.zeros((Q, nc), dtype=torch.int32, device=dev) for _ in range(2)]
-        r_all_host = [torch.empty((world, Q, pad), dtype=torch.int32).pin_memory() for _ in range(2)]
+        NB = 3  # batches in flight: with 2, the upload of batch i+1 could only start once batch i-1 had left the GPU
+        q_slice = [torch.zeros((Q, ks), dtype=torch.int32, device=dev) for _ in range(NB)]
+        q_all = [torch.empty((world, Q, ks), dtype=torch.int32, device=dev) for _ in range(NB)]
+        q_rows = [torch.empty((Q, K), dtype=torch.int32, device=dev) for _ in range(NB)]
+        resp2 = [torch.zeros((Q, nc), dtype=torch.int32, device=dev) for _ in range(NB)]
+        e_send = [torch.zeros((Q, pad), dtype=torch.int32, device=dev) for _ in range(NB)]
+        e_gather = [torch.zeros((world, Q, pad), dtype=torch.int32, device=dev) for _ in range(NB)]
+        r_all_host = [torch.empty((world, Q, pad), dtype=torch.int32).pin_memory() for _ in range(NB)]
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         s_main = torch.cuda.current_stream()
 
         def e2e_steps(n):
-            """Two-deep software pipeline: the upload + all-gather of batch i+1 is issued before the respond of batch i, so PCIe,
-            NVLink and HBM streaming overlap; every batch's gathered responses are copied to pinned host memory on rank 0."""
-            done, ready, sent = [None, None], [None, None], [None, None]
+            """Software pipeline NB deep: the upload + all-gather of batches i+1 and i+2 are issued before the respond of batch i, so
+            PCIe, NVLink and HBM streaming overlap; every batch's gathered responses are copied to pinned host memory on rank 0."""
+            done, ready, sent = [None] * NB, [None] * NB, [None] * NB
 
             def stage_in(i):
-                p = i & 1
+                p = i % NB
                 with torch.cuda.stream(s_in):
                     if done[p] is not None:
                         s_in.wait_event(done[p])
@@ -621,11 +624,12 @@ def run_b200(args):
                     ready[p] = torch.cuda.Event()
                     ready[p].record(s_in)
 
-            stage_in(0)
+            for i in range(min(NB - 1, n)):
+                stage_in(i)
             for i in range(n):
-                p = i & 1
-                if i + 1 < n:
-                    stage_in(i + 1)
+                p = i % NB
+                if i + NB - 1 < n:
+                    stage_in(i + NB - 1)
                 s_main.wait_event(ready[p])
                 if sent[p] is not None:
                     s_main.wait_event(sent[p])
@@ -634,12 +638,12 @@ def run_b200(args):
                 done[p].record(s_main)
                 with torch.cuda.stream(s_out):  # the gather and the read-back never hold up the next batch's respond
                     s_out.wait_event(done[p])
-                    send_bufs[p][:, :nc] = resp2[p]
+                    e_send[p][:, :nc] = resp2[p]
                     sent[p] = torch.cuda.Event()
                     sent[p].record(s_out)
-                    dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), group=pg_out)
+                    dist.all_gather_into_tensor(e_gather[p].view(-1), e_send[p].view(-1), group=pg_out)
                     if rank == 0:
-                        r_all_host[p].copy_(gather_bufs[p], non_blocking=True)
+                        r_all_host[p].copy_(e_gather[p], non_blocking=True)
             torch.cuda.synchronize()
     else:
         e2e_steps = e2e_steps_single
@@ -658,7 +662,7 @@ def run_b200(args):
     e2e_qps = n_queries / float(te[0])
     # e2e parity: the host-path bytes equal the device-path result
     if world > 1:
-        got = resp2[(args.steps - 1) & 1][0].cpu().numpy().view(np.uint32)
+        got = resp2[(args.steps - 1) % NB][0].cpu().numpy().view(np.uint32)
     else:
         got = r_host[0, 8:].numpy().view(np.uint32)
     srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
