@@ -300,8 +300,10 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   EventTimer t_pack;
   {
     void *p = nullptr;
-    CHPIR_CUDA(cudaMalloc(&p, srv->packed_bytes), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+    CHPIR_CUDA(cudaMalloc(&p, srv->layout.alloc_bytes(K)), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
     srv->d_packed = static_cast<uint8_t *>(p);
+    if (srv->layout.alloc_bytes(K) > srv->packed_bytes)  // the zeroed pad row behind tight rows (PackedLayout::alloc_bytes)
+      CHPIR_CUDA(cudaMemsetAsync(srv->d_packed + srv->packed_bytes, 0, srv->layout.alloc_bytes(K) - srv->packed_bytes, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   }
   t_pack.start(st);
   if (int rc = launch_pack(d_dev, K, ld, col0, srv->layout, srv->d_packed, st); rc != CHPIR_OK) return rc;
@@ -861,7 +863,7 @@ static_assert(sizeof(SavedHeader) == 64, "on-disk header is 64 bytes");
 constexpr char kSavedMagic[8] = {'C', 'H', 'P', 'I', 'R', 'S', 'V', '1'};
 constexpr size_t kIoChunk = 64ull << 20;
 
-// FNV-1a over 64-bit words (the payload is a whole number of 16-byte units)
+// FNV-1a over 64-bit words (the payload is a whole number of u64 words)
 inline uint64_t fnv1a64(uint64_t h, const uint8_t *p, size_t n) {
   for (size_t i = 0; i + 8 <= n; i += 8) {
     uint64_t w;
@@ -894,6 +896,7 @@ int chpir_server_save(chpir_server *srv, const char *path) {
   std::memcpy(h.magic, kSavedMagic, 8);
   h.version = 1, h.b = srv->b, h.K = srv->K, h.ncols = srv->ncols, h.col_begin = srv->col_begin;
   h.fpw = srv->layout.fpw, h.units = srv->layout.units, h.packed_bytes = srv->packed_bytes;
+  h.reserved[0] = uint8_t(srv->layout.tight);  // 1 = tight rows (PackedLayout); 0 also in files written before they existed
   if (std::fwrite(&h, sizeof h, 1, f.get()) != 1) return CHPIR_ERR_IO_FAILED;
   PinnedPair buf;
   if (cudaMallocHost(&buf.p[0], kIoChunk) != cudaSuccess) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
@@ -924,8 +927,10 @@ int chpir_server_load(chpir_ctx *ctx, const char *path, const chpir_setup_opts *
   if (std::fread(&h, sizeof h, 1, f.get()) != 1) return CHPIR_ERR_INVALID_SAVED_SERVER;
   if (std::memcmp(h.magic, kSavedMagic, 8) != 0 || h.version != 1) return CHPIR_ERR_INVALID_SAVED_SERVER;
   if (validate_bits(h.b) != CHPIR_OK || h.K == 0 || h.ncols == 0) return CHPIR_ERR_INVALID_SAVED_SERVER;
-  const PackedLayout L = make_layout(h.b, h.ncols);
-  if (L.fpw != h.fpw || L.units != h.units || h.packed_bytes != h.K * L.pitch_bytes()) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  // the file's own row layout (not whatever make_layout would choose today): the kernels read either
+  PackedLayout L{};
+  if (!make_layout_explicit(h.b, h.ncols, h.units, h.reserved[0], &L)) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  if (L.fpw != h.fpw || h.packed_bytes != h.K * L.pitch_bytes()) return CHPIR_ERR_INVALID_SAVED_SERVER;
   std::lock_guard<std::mutex> g(ctx->mu);
   CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
   const double t0 = now_s();
@@ -934,8 +939,10 @@ int chpir_server_load(chpir_ctx *ctx, const char *path, const chpir_setup_opts *
   srv->layout = L, srv->packed_bytes = h.packed_bytes;
   {
     void *p = nullptr;
-    CHPIR_CUDA(cudaMalloc(&p, srv->packed_bytes), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+    CHPIR_CUDA(cudaMalloc(&p, L.alloc_bytes(h.K)), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
     srv->d_packed = static_cast<uint8_t *>(p);
+    if (L.alloc_bytes(h.K) > srv->packed_bytes)
+      CHPIR_CUDA(cudaMemsetAsync(srv->d_packed + srv->packed_bytes, 0, L.alloc_bytes(h.K) - srv->packed_bytes, ctx->stream), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   }
   PinnedPair buf;
   if (cudaMallocHost(&buf.p[0], kIoChunk) != cudaSuccess || cudaMallocHost(&buf.p[1], kIoChunk) != cudaSuccess) return CHPIR_ERR_HOST_ALLOCATION_FAILED;

@@ -29,11 +29,19 @@ void set_last_cuda_error(cudaError_t e, const char *what);
 struct PackedLayout {
   uint32_t b;      // bits per element
   uint32_t fpw;    // fields per u64 word
-  uint32_t units;  // 16-byte units per row
+  uint32_t units;  // 16-byte units (two u64 words) per row = columns owned by one thread of the respond kernels
   uint32_t ncols;  // logical columns
-  __host__ __device__ uint64_t pitch_bytes() const { return uint64_t(units) * 16; }
+  uint32_t tight;  // 1 = rows with an odd number of words are NOT padded to 16 bytes (pitch = 8 * words).  Exists for the narrow
+                   // column slices of 8-way sharding: 118 columns x 9 bit = 17 words = 136 bytes instead of 144
+  __host__ __device__ uint32_t words() const { return (ncols + fpw - 1) / fpw; }
+  __host__ __device__ uint64_t pitch_bytes() const { return tight ? uint64_t(words()) * 8 : uint64_t(units) * 16; }
+  // rows to allocate for K logical rows: tight rows are fetched in even-sized groups by the bulk-copy engine (16-byte granules),
+  // and the last unit of a row reads 8 bytes into the next one, so one zeroed pad row follows the last
+  __host__ __device__ uint64_t alloc_bytes(uint64_t K) const { return (K + (tight ? 1 : 0)) * pitch_bytes(); }
 };
 PackedLayout make_layout(uint32_t b, uint32_t ncols);
+// the layout a saved server was written with (units / tight from its header); false if they do not describe (b, ncols)
+bool make_layout_explicit(uint32_t b, uint32_t ncols, uint32_t units, uint32_t tight, PackedLayout *out);
 
 // ---- kernels (defined in respond.cu / expand.cu / gemm_simt.cu / gemm_tc.cu) --------------------------------
 // D (u32, K x ld, columns [col_begin, col_begin+ncols)) -> packed rows.

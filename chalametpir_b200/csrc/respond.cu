@@ -21,14 +21,36 @@
 
 namespace chpir {
 
+static uint32_t env_u32_early(const char *name, uint32_t dflt) {
+  const char *v = std::getenv(name);
+  return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
 PackedLayout make_layout(uint32_t b, uint32_t ncols) {
   PackedLayout L{};
   L.b = b;
   L.fpw = 64 / b;
   const uint32_t words = (ncols + L.fpw - 1) / L.fpw;
-  L.units = (words + 1) / 2;
   L.ncols = ncols;
+  // Tight rows (CHPIR_TIGHT_PITCH=1, off by default): an odd word count is not rounded up to 16 bytes -- 17 words instead of 18 at
+  // 8-way sharding of N = 940, 5.6 % fewer bytes per query.  Measured on a 118-column slice it does not pay: 27.0-28.4 us per
+  // query against 24.9-26.3 us padded (profiles/r1_slice_sweep_tight.txt) -- at that width the kernel is bound by the consumers'
+  // per-row work (the same 9 units per row either way, plus a second 8-byte load and 2-way bank conflicts), not by the bytes.
+  // Only the ring kernel reads this layout, so it is tied to it.
+  const bool tight = (words & 1u) && words <= 64 && env_u32_early("CHPIR_RESPOND_RING", 1) != 0 && env_u32_early("CHPIR_TIGHT_PITCH", 0) != 0;
+  L.tight = tight ? 1 : 0;
+  L.units = (words + 1) / 2;
   return L;
+}
+
+bool make_layout_explicit(uint32_t b, uint32_t ncols, uint32_t units, uint32_t tight, PackedLayout *out) {
+  if (b < 4 || b > 14 || ncols == 0 || tight > 1) return false;
+  PackedLayout L{};
+  L.b = b, L.fpw = 64 / b, L.ncols = ncols, L.units = units, L.tight = tight;
+  const uint32_t words = L.words();
+  if (units != (words + 1) / 2 || (tight && !((words & 1u) && words <= 64))) return false;
+  *out = L;
+  return true;
 }
 
 namespace {
@@ -212,18 +234,18 @@ __device__ __forceinline__ void bar_sync_consumers(uint32_t nthreads) { asm vola
 // flattened -- and the epilogue of a query (fold the R row lanes, one atomic per column) borrows the last stage the consumers read
 // as scratch: two consumer-only barriers and a few shuffles instead of 2*FPW block-wide reduction rounds (at 8-way column sharding
 // a query is ~25 us of streaming per rank, and the old epilogue was ~3 us of it).
-template <int B, int RPT>
+template <int B, int RPT, bool TIGHT>
 __global__ void __launch_bounds__(kRingMaxThreads, 1)
     respond_ring_kernel(const uint8_t *__restrict__ packed, const uint32_t *__restrict__ q_all, uint32_t *__restrict__ resp_all, uint64_t K,
-                        uint32_t units, uint32_t R, uint32_t stages, uint32_t stage_bytes, uint64_t rows_per_cta, uint32_t ncols, uint32_t q_bulk,
+                        uint32_t pitch, uint32_t units, uint32_t R, uint32_t stages, uint32_t stage_bytes, uint64_t rows_per_cta, uint32_t ncols, uint32_t q_bulk,
                         uint32_t nq, uint32_t q_per_cta) {
   constexpr int FPW = 64 / B;
   constexpr int NACC = 2 * FPW;
-  // accumulators folded per epilogue pass: the scratch is the last stage of the query, RPT*16 bytes of it per consumer thread
-  constexpr int G = NACC < RPT * 4 ? NACC : RPT * 4;
+  // accumulators folded per epilogue pass: the scratch is the last stage of the query, S*pitch bytes = at least RPT*16 bytes per
+  // consumer thread (RPT*8 when rows are tight: pitch >= 8 * units)
+  constexpr int G = TIGHT ? (NACC < RPT * 2 ? NACC : RPT * 2) : (NACC < RPT * 4 ? NACC : RPT * 4);
   extern __shared__ __align__(128) uint8_t ring[];
   const uint32_t S = R * RPT;  // rows per stage
-  const uint32_t pitch = units * 16;
   const uint32_t d_bytes = S * pitch;
   const uint32_t ring_base = smem_addr(ring);
   const uint32_t bar_base = ring_base + stages * stage_bytes;  // full[stages], empty[stages]
@@ -265,9 +287,11 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
           const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
           const bool qb = q_bulk && rows == S;
           const uint32_t full = bar_base + 8 * s;
-          mbar_expect_tx(full, rows * pitch + (qb ? S * 4 : 0));
+          // tight rows are 8 (mod 16) bytes long: copy an even number of them (S is even; past row K lies the zeroed pad row)
+          const uint32_t rows_cp = TIGHT ? rows + (rows & 1u) : rows;
+          mbar_expect_tx(full, rows_cp * pitch + (qb ? S * 4 : 0));
           const uint32_t dst = ring_base + s * stage_bytes;
-          bulk_g2s(dst, packed + kc * pitch, rows * pitch, full, policy);
+          bulk_g2s(dst, packed + kc * pitch, rows_cp * pitch, full, policy);
           if (qb) bulk_g2s(dst + d_bytes, q + kc, S * 4, full);
         }
       }
@@ -298,12 +322,20 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
         uint4 w[RPT];
         uint32_t qk[RPT];
         // shared-memory reads are unconditional (rows past the end of a partial chunk hold stale bytes and are
-        // multiplied by zero), so that all RPT loads of a stage are in flight together
+        // multiplied by zero), so that all RPT loads of a stage are in flight together.  Tight rows start on 8-byte boundaries:
+        // two 8-byte loads; the second word of a row's last unit is the first word of the next row (or of the q slice behind the
+        // last row) and only ever feeds accumulators of columns >= ncols, which are never published.
 #pragma unroll
-        for (int j = 0; j < RPT; j++)
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(w[j].x), "=r"(w[j].y), "=r"(w[j].z), "=r"(w[j].w)
-                       : "r"(base + j * R * pitch));
+        for (int j = 0; j < RPT; j++) {
+          if (!TIGHT) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[j].x), "=r"(w[j].y), "=r"(w[j].z), "=r"(w[j].w)
+                         : "r"(base + j * R * pitch));
+          } else {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[j].x), "=r"(w[j].y) : "r"(base + j * R * pitch));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[j].z), "=r"(w[j].w) : "r"(base + j * R * pitch + 8));
+          }
+        }
         if (qb) {
 #pragma unroll
           for (int j = 0; j < RPT; j++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qk[j]) : "r"(qbase + j * R * 4));
@@ -332,7 +364,7 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
     unmask_fields<B>(acc + FPW);
 
     // Fold the R row lanes of every (unit, accumulator) and publish one atomic per (CTA, column).  Scratch = the stage just
-    // consumed (S*pitch >= n_cons * RPT * 16 bytes), G accumulators per pass; every (accumulator, unit) item is summed by P
+    // consumed, G accumulators per pass; every (accumulator, unit) item is summed by P
     // adjacent lanes (R/P values each) and finished with shuffles.
     uint32_t *red = reinterpret_cast<uint32_t *>(ring + last_s * stage_bytes);
     uint32_t *resp = resp_all + uint64_t(qi) * ncols;
@@ -367,59 +399,55 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
   }
 }
 
+// One thread per u64 word of the packed matrix (row k, word w -> columns w*FPW ...): works for both row layouts, the words of a
+// row are contiguous and rows follow each other at `words` u64.
 template <int B>
-__global__ void pack_kernel(const uint32_t *__restrict__ d, uint64_t K, uint32_t ld, uint32_t col_begin, uint32_t ncols, uint32_t units,
-                            uint4 *__restrict__ packed) {
+__global__ void pack_kernel(const uint32_t *__restrict__ d, uint64_t K, uint32_t ld, uint32_t col_begin, uint32_t ncols, uint32_t words,
+                            uint64_t *__restrict__ packed) {
   constexpr int FPW = 64 / B;
   constexpr uint32_t MASK = (1u << B) - 1u;
-  const uint64_t total = K * units;
+  const uint64_t total = K * words;
   for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < total; idx += uint64_t(gridDim.x) * blockDim.x) {
-    const uint64_t k = idx / units;
-    const uint32_t u = uint32_t(idx - k * units);
+    const uint64_t k = idx / words;
+    const uint32_t wi = uint32_t(idx - k * words);
     const uint32_t *row = d + k * ld + col_begin;
-    uint64_t w[2] = {0, 0};
+    uint64_t w = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-#pragma unroll
-      for (int f = 0; f < FPW; f++) {
-        const uint32_t col = (2 * u + h) * FPW + f;
-        if (col < ncols) w[h] |= uint64_t(row[col] & MASK) << (f * B);  // `& mat_elem_mask` as matrix.rs:121-156
-      }
+    for (int f = 0; f < FPW; f++) {
+      const uint32_t col = wi * FPW + f;
+      if (col < ncols) w |= uint64_t(row[col] & MASK) << (f * B);  // `& mat_elem_mask` as matrix.rs:121-156
     }
-    packed[idx] = make_uint4(uint32_t(w[0]), uint32_t(w[0] >> 32), uint32_t(w[1]), uint32_t(w[1] >> 32));
+    packed[idx] = w;
   }
 }
 
 // packed rows -> K x ncols u32 (the inverse of pack_kernel; used to rebuild the GEMM's limb planes for a server loaded from disk)
 template <int B>
-__global__ void unpack_kernel(const uint4 *__restrict__ packed, uint64_t K, uint32_t ncols, uint32_t units, uint32_t *__restrict__ d) {
+__global__ void unpack_kernel(const uint64_t *__restrict__ packed, uint64_t K, uint32_t ncols, uint32_t words, uint32_t *__restrict__ d) {
   constexpr int FPW = 64 / B;
   constexpr uint32_t MASK = (1u << B) - 1u;
-  const uint64_t total = K * units;
+  const uint64_t total = K * words;
   for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < total; idx += uint64_t(gridDim.x) * blockDim.x) {
-    const uint64_t k = idx / units;
-    const uint32_t u = uint32_t(idx - k * units);
-    const uint4 v = packed[idx];
-    const uint64_t w[2] = {uint64_t(v.x) | uint64_t(v.y) << 32, uint64_t(v.z) | uint64_t(v.w) << 32};
+    const uint64_t k = idx / words;
+    const uint32_t wi = uint32_t(idx - k * words);
+    const uint64_t w = packed[idx];
     uint32_t *row = d + k * ncols;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-#pragma unroll
-      for (int f = 0; f < FPW; f++) {
-        const uint32_t col = (2 * u + h) * FPW + f;
-        if (col < ncols) row[col] = uint32_t(w[h] >> (f * B)) & MASK;
-      }
+    for (int f = 0; f < FPW; f++) {
+      const uint32_t col = wi * FPW + f;
+      if (col < ncols) row[col] = uint32_t(w >> (f * B)) & MASK;
     }
   }
 }
 
 template <int B>
 int unpack_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t K, uint32_t *d, cudaStream_t s) {
-  const uint64_t total = K * L.units;
+  const uint32_t wpr = uint32_t(L.pitch_bytes() / 8);  // u64 words per row, padding included
+  const uint64_t total = K * wpr;
   const int block = 256;
   const uint64_t want = (total + block - 1) / block;
   const int grid = int(want < 148ull * 32 ? (want ? want : 1) : 148ull * 32);
-  unpack_kernel<B><<<grid, block, 0, s>>>(reinterpret_cast<const uint4 *>(packed), K, L.ncols, L.units, d);
+  unpack_kernel<B><<<grid, block, 0, s>>>(reinterpret_cast<const uint64_t *>(packed), K, L.ncols, wpr, d);
   return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
 }
 
@@ -451,23 +479,31 @@ int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t
     // (8-way sharding) 24.7 us per query at 1, 26.0 at 4, 27.3 at 16 (profiles/r1_slice_sweep.txt).
     const uint32_t q_per_cta = std::max(1u, std::min(env_u32("CHPIR_RING_Q_PER_CTA", 1), nq));
     kernel<<<dim3(P.ring_grid, (nq + q_per_cta - 1) / q_per_cta), P.ring_block, P.ring_smem_bytes, s>>>(
-        packed, q, resp, K, L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes, P.ring_rows_per_cta, L.ncols, q_bulk, nq, q_per_cta);
+        packed, q, resp, K, uint32_t(L.pitch_bytes()), L.units, P.ring_R, P.ring_stages, P.ring_stage_bytes, P.ring_rows_per_cta, L.ncols, q_bulk, nq, q_per_cta);
     return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   };
+  if (L.tight) {
+    switch (P.ring_rpt) {
+      case 1: return launch(respond_ring_kernel<B, 1, true>);
+      case 2: return launch(respond_ring_kernel<B, 2, true>);
+      default: return launch(respond_ring_kernel<B, 4, true>);
+    }
+  }
   switch (P.ring_rpt) {
-    case 1: return launch(respond_ring_kernel<B, 1>);
-    case 2: return launch(respond_ring_kernel<B, 2>);
-    default: return launch(respond_ring_kernel<B, 4>);
+    case 1: return launch(respond_ring_kernel<B, 1, false>);
+    case 2: return launch(respond_ring_kernel<B, 2, false>);
+    default: return launch(respond_ring_kernel<B, 4, false>);
   }
 }
 
 template <int B>
 int pack_dispatch(const uint32_t *d, uint64_t K, uint32_t ld, uint32_t col_begin, const PackedLayout &L, uint8_t *packed, cudaStream_t s) {
-  const uint64_t total = K * L.units;
+  const uint32_t wpr = uint32_t(L.pitch_bytes() / 8);  // u64 words per row, padding included (written as zero)
+  const uint64_t total = K * wpr;
   const int block = 256;
   const uint64_t want = (total + block - 1) / block;
-  const int grid = int(want < 148ull * 32 ? (want ? want : 1) : 148ull * 32);
-  pack_kernel<B><<<grid, block, 0, s>>>(d, K, ld, col_begin, L.ncols, L.units, reinterpret_cast<uint4 *>(packed));
+  const int grid = int(want < 148ull * 64 ? (want ? want : 1) : 148ull * 64);
+  pack_kernel<B><<<grid, block, 0, s>>>(d, K, ld, col_begin, L.ncols, wpr, reinterpret_cast<uint64_t *>(packed));
   return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
 }
 
@@ -517,7 +553,7 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
   while (R > 4 && R * units > uint32_t(kRingMaxThreads) - 32) R -= 4;
   uint32_t rpt = env_u32("CHPIR_RING_RPT", 4);
   if (rpt != 1 && rpt != 2) rpt = 4;
-  const uint32_t pitch = units * 16;
+  const uint32_t pitch = uint32_t(L.pitch_bytes());
   const uint32_t budget = std::min(env_u32("CHPIR_RING_BUDGET_KB", 200), 200u) * 1024;
   while (rpt > 1 && 3 * R * rpt * (pitch + 4) > budget) rpt /= 2;
   const uint32_t S = R * rpt;
@@ -588,11 +624,21 @@ static int launch_respond_one(const uint8_t *packed, const PackedLayout &L, uint
 int launch_respond(const uint8_t *packed, const PackedLayout &L, uint64_t K, const RespondPlan &P, const uint32_t *q_dev, uint32_t *resp_dev,
                    uint32_t nq, cudaStream_t s) {
   if (nq == 0) return CHPIR_OK;
-  if (P.ring && nq <= 65535) {
-#define CHPIR_RING(B) respond_ring_dispatch<B>(packed, L, K, P, q_dev, resp_dev, nq, s)
-    CHPIR_DISPATCH_B(L.b, CHPIR_RING)
+  if (P.ring) {
+    for (uint32_t i0 = 0; i0 < nq; i0 += 65535) {  // grid.y limit
+      const uint32_t n = std::min(nq - i0, 65535u);
+      const uint32_t *qd = q_dev + uint64_t(i0) * K;
+      uint32_t *rd = resp_dev + uint64_t(i0) * L.ncols;
+      const int rc = [&]() -> int {
+#define CHPIR_RING(B) respond_ring_dispatch<B>(packed, L, K, P, qd, rd, n, s)
+        CHPIR_DISPATCH_B(L.b, CHPIR_RING)
 #undef CHPIR_RING
+      }();
+      if (rc != CHPIR_OK) return rc;
+    }
+    return CHPIR_OK;
   }
+  if (L.tight) return CHPIR_ERR_INVALID_ARGUMENT;  // tight rows are only ever planned together with the ring kernel
   for (uint32_t i = 0; i < nq; i++)
     if (int rc = launch_respond_one(packed, L, K, P, q_dev + uint64_t(i) * K, resp_dev + uint64_t(i) * L.ncols, s); rc != CHPIR_OK) return rc;
   return CHPIR_OK;

@@ -304,7 +304,7 @@ def test_respond_tensor_core_batch_needs_planes():
 
 
 # ------------------------------------------------------------------ persisted server state (chpir_server_save / chpir_server_load)
-@pytest.mark.parametrize("b,K,N", [(9, 5003, 941), (10, 20000, 300), (4, 777, 17), (14, 1024, 64)])
+@pytest.mark.parametrize("b,K,N", [(9, 5003, 941), (10, 20000, 300), (4, 777, 17), (14, 1024, 64), (9, 5003, 121), (10, 4098, 7)])
 def test_saved_server_answers_identically_after_load(tmp_path, b, K, N):
     rng = np.random.default_rng(b + K)
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
@@ -334,3 +334,28 @@ def test_saved_server_answers_identically_after_load(tmp_path, b, K, N):
     with pytest.raises(cp.ChalametPIRError) as e:
         cp.Server.load(tmp_path / "does-not-exist")
     assert e.value.variant == "IoFailed"
+
+
+@pytest.mark.parametrize("b,K,N", [(9, 5003, 118), (9, 20001, 117), (9, 1, 119), (10, 777, 13), (4, 3001, 17 * 16 - 3), (14, 4097, 63 * 4), (9, 2 * 4096, 63 * 7)])
+def test_tight_rows_answer_exactly_like_padded_rows(monkeypatch, tmp_path, b, K, N):
+    """Narrow slices with an odd number of u64 words per row (118 columns x 9 bit = 17 words at 8-way sharding) can be stored without
+    the 16-byte row padding (csrc/common.cuh PackedLayout.tight, CHPIR_TIGHT_PITCH=1).  Same bytes out as the padded layout, fewer
+    bytes streamed; odd K exercises the even-row bulk copies that run into the zeroed pad row."""
+    rng = np.random.default_rng(K + N)
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    qs = [rand_u32(rng, K) for _ in range(5)]
+    padded, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True)
+    monkeypatch.setenv("CHPIR_TIGHT_PITCH", "1")  # opt-in: measured slower than padded rows on the slices it was meant for
+    tight, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True, batch_tc=1)
+    monkeypatch.delenv("CHPIR_TIGHT_PITCH")
+    words = -(-N // (64 // b))
+    assert words % 2 == 1 and tight.info.row_pitch_bytes == 8 * words and padded.info.row_pitch_bytes == 8 * (words + 1)
+    assert tight.packed_bytes == K * 8 * words
+    want = [oracle_respond(D, b, q) for q in qs]
+    assert [tight.respond(qbytes(q)) for q in qs] == want
+    assert [padded.respond(qbytes(q)) for q in qs] == want
+    assert tight.respond_batch([qbytes(q) for q in qs]) == want
+    # the saved file records its own row layout: it loads as tight whatever the default is at load time
+    tight.save(tmp_path / "tight.chpir")
+    ld = cp.Server.load(tmp_path / "tight.chpir")
+    assert ld.info.row_pitch_bytes == 8 * words and [ld.respond(qbytes(q)) for q in qs] == want

@@ -14,7 +14,7 @@ Q = 16
 
 def run(ncols, env, iters=30):
     for k in list(os.environ):
-        if k.startswith("CHPIR_R"):
+        if k.startswith("CHPIR_R") or k.startswith("CHPIR_T"):
             del os.environ[k]
     os.environ.update({k: str(v) for k, v in env.items()})
     torch.manual_seed(ncols)
@@ -45,6 +45,24 @@ def run(ncols, env, iters=30):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tight":  # 8-byte row pitch against 16-byte padded rows, interleaved repeats
+        for nc in (118, 117):
+            for rep in range(4):
+                for tp in (1, 0):
+                    run(nc, {"CHPIR_TIGHT_PITCH": tp}, iters=100)
+        for tp in (1, 0):
+            run(118, {"CHPIR_TIGHT_PITCH": tp, "CHPIR_RING_RPT": 2}, iters=100)
+            run(118, {"CHPIR_TIGHT_PITCH": tp, "CHPIR_RING_R": 48}, iters=100)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rows":  # row lanes per stage at full width and on the slices, interleaved repeats
+        for rep in range(3):
+            for R in (8, 12):
+                run(940, {"CHPIR_RING_R": R}, iters=60)
+        for nc, Rs in ((470, (16, 20, 24)), (235, (32, 40)), (118, (64, 56))):
+            for rep in range(2):
+                for R in Rs:
+                    run(nc, {"CHPIR_RING_R": R}, iters=60)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grid":
         for nc in (118, 235, 470, 940):
             for env in [{}, {"CHPIR_RING_GRID_MULT": 2}, {"CHPIR_RING_GRID_MULT": 3}, {"CHPIR_RING_GRID_MULT": 4}]:
