@@ -729,7 +729,7 @@ def run_b200(args):
     # ---------------- CPU baseline on the host cores (rank 0, N = 1 only)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_respond_qps(K, N, b, args.cpu_sample_frac, iters=5)
+        r = cpu_respond_qps(K, N, b, args.cpu_sample_frac, iters=25)
         cpu_baseline = {
             "value": r["qps_full"], "unit": "queries/s", "cores": r["threads"], "kind": "port",
             "sample": f"rows [0,{r['rows_sample']}) of K={K} (1/{args.cpu_sample_frac} of the database, all {N} columns), median of {len(r['times'])} queries = "
