@@ -618,8 +618,7 @@ def run_b200(args):
                 with torch.cuda.stream(s_in):
                     if done[p] is not None:
                         s_in.wait_event(done[p])
-                    for j in range(Q):  # one contiguous pinned -> device DMA per query (a strided 2-D copy_ would be staged through the host)
-                        q_slice[p][j, : k1 - k0].copy_(q_words[j, k0:k1], non_blocking=True)
+                    sharding.upload_query_slices(q_words, k0, k1, q_slice[p], s_in)  # one strided DMA for the 16 slices
                     sharding.allgather_query_slices(dist, torch, q_slice[p], q_all[p], q_rows[p])
                     ready[p] = torch.cuda.Event()
                     ready[p].record(s_in)

@@ -83,6 +83,7 @@ EXPORTS = [
     "chpir_ctx_drop_a_cache",
     "chpir_host_alloc",
     "chpir_host_free",
+    "chpir_upload_rows",
     "chpir_find_mat_elem_bit_len",
     "chpir_db_matrix_shape",
     "chpir_encode_kv_database",
@@ -136,6 +137,8 @@ lib.chpir_ctx_drop_a_cache.argtypes = [_vp, C.POINTER(C.c_uint64)]
 lib.chpir_host_alloc.argtypes = [C.c_size_t, C.POINTER(_vp)]
 lib.chpir_host_free.restype = None
 lib.chpir_host_free.argtypes = [_vp]
+lib.chpir_upload_rows.restype = C.c_int
+lib.chpir_upload_rows.argtypes = [_vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp]
 lib.chpir_find_mat_elem_bit_len.argtypes = [C.c_uint64, C.POINTER(C.c_uint32)]
 lib.chpir_db_matrix_shape.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 lib.chpir_encode_kv_database.argtypes = [C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), _vp, _vp]

@@ -645,6 +645,16 @@ void chpir_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 
+int chpir_upload_rows(void *dst_device, size_t dst_pitch, const void *src_host, size_t src_pitch, size_t width_bytes, size_t rows, void *cuda_stream) {
+  CHPIR_GUARD_BEGIN
+  if (!dst_device || !src_host || width_bytes > dst_pitch || width_bytes > src_pitch) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || width_bytes == 0) return CHPIR_OK;
+  CHPIR_CUDA(cudaMemcpy2DAsync(dst_device, dst_pitch, src_host, src_pitch, width_bytes, rows, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(cuda_stream)),
+             CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  return CHPIR_OK;
+  CHPIR_GUARD_END
+}
+
 int chpir_find_mat_elem_bit_len(uint64_t n, uint32_t *b) {
   if (!b) return CHPIR_ERR_INVALID_ARGUMENT;
   return find_mat_elem_bit_len(n, b);

@@ -49,6 +49,19 @@ def query_slice(K: int, rank: int, world: int) -> Tuple[int, int, int]:
     return k0, min(K, k0 + ks), ks
 
 
+def upload_query_slices(q_words: "torch.Tensor", k0: int, k1: int, q_slice: "torch.Tensor", stream) -> None:
+    """q_words: (Q, K) int32 view of the batch in page-locked host memory; q_slice: (Q, ks) device buffer of this rank.  Copies words
+    [k0, k1) of every query with ONE strided DMA on `stream` (a torch ``copy_`` of the strided view would be staged through pageable
+    memory, and one ``copy_`` per query costs ~25 us of host time each -- more than the GPU needs per batch at 8-way sharding)."""
+    from ._lib import lib
+    from .errors import check
+
+    if k1 <= k0:
+        return
+    Q, K = q_words.shape
+    check(lib.chpir_upload_rows(q_slice.data_ptr(), q_slice.shape[1] * 4, q_words.data_ptr() + 4 * k0, K * 4, (k1 - k0) * 4, Q, stream.cuda_stream))
+
+
 def allgather_query_slices(dist, torch, q_slice: "torch.Tensor", q_all: "torch.Tensor", q_rows: "torch.Tensor", group=None) -> "torch.Tensor":
     """q_slice: (Q, ks) this rank's words of Q queries (zero padded) -> q_rows: (Q, K) whole queries on every rank.
     q_all is the (world, Q, ks) all-gather landing buffer; the rank-major result is re-laid out query-major into q_rows."""

@@ -95,6 +95,11 @@ CHPIR_API int chpir_ctx_drop_a_cache(chpir_ctx *ctx, uint64_t *bytes_freed);
  * is copied by DMA at the full PCIe rate (a 4.7 MB query moves in 90 us instead of ~500 us from pageable memory). */
 CHPIR_API int chpir_host_alloc(size_t bytes, void **out);
 CHPIR_API void chpir_host_free(void *p);
+/* Column-sharded serving: rank r uploads only words [k0, k1) of every query of a batch over its own PCIe link
+ * before the slices are all-gathered over NVLink.  One strided DMA for the whole batch: `rows` rows of `width_bytes` from page-locked
+ * host memory (row pitch src_pitch) into device memory (row pitch dst_pitch), asynchronously on `cuda_stream`. */
+CHPIR_API int chpir_upload_rows(void *dst_device, size_t dst_pitch, const void *src_host, size_t src_pitch, size_t width_bytes, size_t rows,
+                      void *cuda_stream);
 
 /* ---- host side that stays on the host (north_star); mirrors chalametpir_common --------------------- */
 /* server.rs:193-218 find_encoded_db_matrix_element_bit_length */

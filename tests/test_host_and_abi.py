@@ -129,3 +129,21 @@ def test_host_xof_rfc9861_known_answer():
     want = np.frombuffer(O.turboshake128(seed, 4 * 500), dtype="<u4")
     assert np.array_equal(cp.host_generate_from_seed(1, 500, seed)[0], want)
     assert cp.host_xof_impl() in ("avx512", "bmi2", "scalar")
+
+
+def test_upload_query_slices_binding_without_a_gpu():
+    """sharding.upload_query_slices -> chpir_upload_rows: an empty slice is a no-op, and without a CUDA device the strided DMA is
+    reported as a ChalametPIRError (not a crash, not a silent success)."""
+    import torch
+
+    from chalametpir_b200 import sharding
+
+    class FakeStream:
+        cuda_stream = 0
+
+    q_words = torch.zeros((3, 10), dtype=torch.int32)
+    q_slice = torch.zeros((3, 4), dtype=torch.int32)
+    assert sharding.upload_query_slices(q_words, 5, 5, q_slice, FakeStream()) is None
+    if not torch.cuda.is_available():
+        with pytest.raises(cp.ChalametPIRError):
+            sharding.upload_query_slices(q_words, 0, 4, q_slice, FakeStream())
