@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -95,8 +96,7 @@ class HostAPipe {
   HostAPipe &operator=(const HostAPipe &) = delete;
   ~HostAPipe() {
     shutdown();
-    for (auto p : pinned_)
-      if (p) cudaFreeHost(p);
+    free_chunks();
     for (auto e : copied_)
       if (e) cudaEventDestroy(e);
     for (auto e : ready_)
@@ -125,11 +125,23 @@ class HostAPipe {
     // created while the producer is already squeezing: kBufs chunks of ~32 MB are ~0.3 s of chain to fill before it needs the
     // uploader to have started.
     const uint64_t chunk_bytes = uint64_t(chunk_rows) * row_bytes_;
+    // The chunks are PAGEABLE by default: page-locking them cost 50-140 ms per 32 MB chunk on the measured box whenever the host was
+    // busy touching memory (the filter/encode phase next door), which stalled the chain for up to 2 s in its first lap, while the
+    // rate needed (8.4 GB in 5.8 s) is a fraction of what a staged pageable upload sustains.  CHPIR_XOF_PINNED=1 page-locks them.
+    const char *pe = std::getenv("CHPIR_XOF_PINNED");
+    pinned_alloc_ = pe && *pe && *pe != '0';
     auto pin = [&](int i) {
-      if (cudaMallocHost(&pinned_[i], chunk_bytes) != cudaSuccess) {
-        set_last_cuda_error(cudaGetLastError(), "pinned XOF chunk ring");
-        pinned_[i] = nullptr;
-        return false;
+      if (pinned_alloc_) {
+        if (cudaMallocHost(&pinned_[i], chunk_bytes) != cudaSuccess) {
+          set_last_cuda_error(cudaGetLastError(), "pinned XOF chunk ring");
+          pinned_[i] = nullptr;
+          return false;
+        }
+      } else {
+        void *m = nullptr;
+        if (posix_memalign(&m, 4096, chunk_bytes ? chunk_bytes : 1) != 0) return false;
+        std::memset(m, 0, chunk_bytes);  // first touch here, not in the producer
+        pinned_[i] = static_cast<uint8_t *>(m);
       }
       {
         std::lock_guard<std::mutex> lk(mu_);
@@ -186,8 +198,7 @@ class HostAPipe {
     if (producer_.joinable()) producer_.join();
     if (uploader_.joinable()) uploader_.join();
     if (up_) cudaStreamSynchronize(up_);
-    for (auto &p : pinned_)  // the chunk ring is only needed while the chain runs (a client keeps the pipe alive as the owner of A)
-      if (p) cudaFreeHost(p), p = nullptr;
+    free_chunks();  // the chunk ring is only needed while the chain runs (a client keeps the pipe alive as the owner of A)
   }
   double busy_s() const { return busy_; }            // time the producer core spent inside the XOF
   double wait_s() const { return wait_; }            // time the producer core waited for a free pinned chunk (the chain stood still)
@@ -200,6 +211,17 @@ class HostAPipe {
 
  private:
   static constexpr int kBufs = 16;
+
+  void free_chunks() {
+    for (auto &p : pinned_)
+      if (p) {
+        if (pinned_alloc_)
+          cudaFreeHost(p);
+        else
+          std::free(p);
+        p = nullptr;
+      }
+  }
 
   void fail(int rc) {
     {
@@ -216,10 +238,12 @@ class HostAPipe {
     host_xof_init(&xs.x, seed_);
     for (uint64_t i = 0; i < chunks_.size(); i++) {
       const int b = int(i % kBufs);
-      if (i < uint64_t(kBufs)) {  // first lap: the chunk may still be on its way through cudaMallocHost in start()
+      if (i < uint64_t(kBufs)) {  // first lap: the chunk may still be on its way through the allocation loop in start()
+        const double w0 = now_s();
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return pinned_ready_ > b || abort_; });
         if (abort_) return;
+        wait_ += now_s() - w0;
       }
       if (i >= uint64_t(kBufs)) {
         const double w0 = now_s();
@@ -292,6 +316,7 @@ class HostAPipe {
   std::condition_variable cv_;
   uint64_t filled_ = 0, issued_ = 0;
   int pinned_ready_ = 0;
+  bool pinned_alloc_ = false;
   uint32_t uploaded_panels_ = 0, released_panels_ = 0;
   bool abort_ = false;
   int rc_ = CHPIR_OK;
