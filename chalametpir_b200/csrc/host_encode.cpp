@@ -419,34 +419,28 @@ void plan_fill_levels(uint32_t arity, const PeelResult &pr, FillPlan *plan) {
 // ------------------------------------------------------------------------------------------------------------
 // row codec (serialization.rs:22-116): digest || value || 0x81, LSB-first b-bit fields
 // ------------------------------------------------------------------------------------------------------------
-namespace {
-struct BitWriter {
-  uint32_t *dst;
-  uint32_t b;
-  uint64_t acc = 0;
-  unsigned bits = 0;
-  void push_byte(uint8_t v) {
-    acc |= static_cast<uint64_t>(v) << bits;
-    bits += 8;
-    while (bits >= b) {
-      *dst++ = static_cast<uint32_t>(acc & ((1ULL << b) - 1));
-      acc >>= b;
-      bits -= b;
-    }
-  }
-  void flush() {
-    if (bits) *dst++ = static_cast<uint32_t>(acc);
-  }
-};
-}  // namespace
-
+// The byte stream digest || value || 0x81 is laid out once in a zero-padded scratch buffer; field f is then bits [f*b, f*b + b) of
+// it, read with one unaligned 64-bit load (b <= 14, so a field never spans more than 3 bytes).  Same fields as pushing the bytes
+// through a bit accumulator LSB-first and flushing the remainder (serialization.rs:31-113), a few times faster.
 void encode_row(const uint8_t digest[32], const uint8_t *value, size_t vlen, uint32_t b, uint32_t *row, uint64_t cols) {
-  std::memset(row, 0, cols * sizeof(uint32_t));
-  BitWriter w{row, b};
-  for (int i = 0; i < 32; i++) w.push_byte(digest[i]);
-  for (size_t i = 0; i < vlen; i++) w.push_byte(value[i]);
-  w.push_byte(0x81);
-  w.flush();
+  static thread_local std::vector<uint8_t> scratch;
+  const size_t stream = 32 + vlen + 1;
+  const size_t need = std::max<size_t>(stream, (cols * b + 7) / 8) + 8;
+  if (scratch.size() < need) scratch.resize(need);
+  uint8_t *buf = scratch.data();
+  std::memcpy(buf, digest, 32);
+  if (vlen) std::memcpy(buf + 32, value, vlen);
+  buf[32 + vlen] = 0x81;
+  std::memset(buf + stream, 0, need - stream);
+  const uint32_t mask = (1u << b) - 1u;
+  // fields past the end of the stream read zeros; a row narrower than the stream (cannot happen for shapes from db_matrix_shape)
+  // would simply be truncated, as the reference's writer would overrun -- callers size cols from the longest value
+  for (uint64_t f = 0; f < cols; f++) {
+    const uint64_t bit = f * b;
+    uint64_t w;
+    std::memcpy(&w, buf + (bit >> 3), 8);
+    row[f] = static_cast<uint32_t>(w >> (bit & 7)) & mask;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -491,33 +485,61 @@ int encode_kv_database(uint32_t arity, uint64_t n, const uint8_t *key_blob, cons
   const uint32_t mask = (1u << b) - 1;
   const FilterParams &fp = pr.params;
 
-  // 1. zero D and write every key's packed row into its own slot -- independent, parallel.
-  parallel_for(K, 256, [&](uint64_t lo, uint64_t hi) { std::memset(D + lo * N, 0, (hi - lo) * N * sizeof(uint32_t)); });
+  // the slot rows of every key, own row first, in peel order (computed once, in parallel)
+  std::vector<uint32_t> rows(n * arity);
+  std::vector<uint8_t> owned(K, 0);
+  parallel_for(n, 1 << 12, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) {
+      const Slots s = slots_of(arity, pr.order[i], fp.segment_length, fp.segment_count_length);
+      for (uint32_t j = 0; j < arity; j++) rows[i * arity + j] = s.h[(pr.found[i] + j) % arity];
+      owned[rows[i * arity]] = 1;  // distinct keys own distinct rows: no two threads write the same byte
+    }
+  });
+  // 1. write every key's packed row into its own slot and zero the rows no key owns -- independent, parallel.
+  parallel_for(K, 256, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t r = lo; r < hi; r++)
+      if (!owned[r]) std::memset(D + r * N, 0, N * sizeof(uint32_t));
+  });
   parallel_for(n, 256, [&](uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi; i++) {
       const uint64_t key = pr.key_of_order[i];
-      const Slots s = slots_of(arity, pr.order[i], fp.segment_length, fp.segment_count_length);
-      encode_row(&digests[32 * key], val_blob + val_off[key], val_off[key + 1] - val_off[key], b, D + uint64_t(s.h[pr.found[i]]) * N, N);
+      encode_row(&digests[32 * key], val_blob + val_off[key], val_off[key + 1] - val_off[key], b, D + uint64_t(rows[i * arity]) * N, N);
     }
   });
   trace_phase("zero + own rows", tt);
   // 2. dependent pass in reverse peel order (matrix.rs:707-746 / :839-885).  A slot read here is either final
   //    (its key was peeled later, i.e. handled earlier in this loop) or never owned by any key (all zero), because a
   //    key is peeled only when it is the last one left on its own slot.
-  for (uint64_t i = n; i-- > 0;) {
-    const uint64_t hash = pr.order[i];
-    const Slots s = slots_of(arity, hash, fp.segment_length, fp.segment_count_length);
-    const uint32_t which = pr.found[i];
-    uint32_t *own = D + uint64_t(s.h[which]) * N;
-    const uint32_t *o1 = D + uint64_t(s.h[(which + 1) % arity]) * N;
-    const uint32_t *o2 = D + uint64_t(s.h[(which + 2) % arity]) * N;
-    if (arity == 3) {
-      for (uint64_t e = 0; e < N; e++) own[e] = (own[e] - o1[e] - o2[e] - static_cast<uint32_t>(mix(hash, e))) & mask;
-    } else {
-      const uint32_t *o3 = D + uint64_t(s.h[(which + 3) % arity]) * N;
-      for (uint64_t e = 0; e < N; e++) own[e] = (own[e] - o1[e] - o2[e] - o3[e] - static_cast<uint32_t>(mix(hash, e))) & mask;
+  //    The dependency runs from key to key, never from column to column, so the columns are split among the worker threads
+  //    and every thread walks ALL keys in the reference's order over its own column range: no synchronisation, the same
+  //    arithmetic per element, hence the same D.
+  unsigned workers = std::max(1u, std::thread::hardware_concurrency());
+  if (t_max_threads) workers = std::min(workers, t_max_threads);
+  // column ranges in multiples of 16 (one cache line of u32), at least 32 columns each
+  const uint64_t col_grain = std::max<uint64_t>(32, ((N + workers - 1) / workers + 15) / 16 * 16);
+  constexpr uint64_t kAhead = 6;  // rows of the key this many steps ahead are prefetched (random 3.8 KB rows: DRAM latency bound otherwise)
+  parallel_for(N, col_grain, [&](uint64_t c0, uint64_t c1) {
+    for (uint64_t i = n; i-- > 0;) {
+      if (i >= kAhead) {
+        const uint32_t *r = &rows[(i - kAhead) * arity];
+        for (uint32_t j = 0; j < arity; j++) {
+          const char *p = reinterpret_cast<const char *>(D + uint64_t(r[j]) * N + c0);
+          for (uint64_t off = 0; off < (c1 - c0) * 4; off += 64) __builtin_prefetch(p + off, 0, 1);
+        }
+      }
+      const uint64_t hash = pr.order[i];
+      const uint32_t *r = &rows[i * arity];
+      uint32_t *own = D + uint64_t(r[0]) * N;
+      const uint32_t *o1 = D + uint64_t(r[1]) * N;
+      const uint32_t *o2 = D + uint64_t(r[2]) * N;
+      if (arity == 3) {
+        for (uint64_t e = c0; e < c1; e++) own[e] = (own[e] - o1[e] - o2[e] - static_cast<uint32_t>(mix(hash, e))) & mask;
+      } else {
+        const uint32_t *o3 = D + uint64_t(r[3]) * N;
+        for (uint64_t e = c0; e < c1; e++) own[e] = (own[e] - o1[e] - o2[e] - o3[e] - static_cast<uint32_t>(mix(hash, e))) & mask;
+      }
     }
-  }
+  });
   trace_phase("dependent row fill", tt);
   if (std::getenv("CHPIR_TRACE_LEVELS")) {
     FillPlan plan;
