@@ -1283,7 +1283,7 @@ int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64
 int chpir_host_generate_from_seed(const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols, uint64_t row_begin,
                                   uint64_t row_count, uint32_t impl, uint32_t *out_host) {
   CHPIR_GUARD_BEGIN
-  if (!seed || !out_host || impl > 3) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (!seed || !out_host || impl > 4) return CHPIR_ERR_INVALID_ARGUMENT;
   if (rows == 0 || cols == 0 || row_begin + row_count > rows) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
   HostXofStream xs;
   xs.impl = int(impl);

@@ -13,7 +13,7 @@ struct HostXof {
 
 // TurboShake128::default(); absorb(seed[32]); finalize::<0x1F>()  (matrix.rs:542-551)
 void host_xof_init(HostXof *x, const uint8_t seed[32]);
-enum : int { kXofAuto = 0, kXofScalar = 1, kXofBmi2 = 2, kXofAvx512 = 3 };
+enum : int { kXofAuto = 0, kXofScalar = 1, kXofBmi2 = 2, kXofAvx512 = 3, kXofEvex128 = 4 };
 // squeeze the next nblocks whole rate blocks (168 bytes each) into out; false if this CPU lacks the requested implementation
 bool host_xof_squeeze_blocks(HostXof *x, uint8_t *out, uint64_t nblocks, int impl);
 // advance the stream by nblocks blocks without producing output

@@ -291,11 +291,12 @@ CHPIR_API int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_ro
                  uint64_t b_cols, uint32_t b_elem_bit_len, uint32_t variant, uint32_t *out_host);
 /* Matrix::generate_from_seed (matrix.rs:541-558) on a host core (csrc/host_xof.cpp; no GPU involved): rows
  * [row_begin, row_begin+row_count) of the rows x cols matrix.  impl: 0 = fastest available on this CPU, 1 = portable scalar,
- * 2 = BMI2 scalar, 3 = AVX-512 (CHPIR_ERR_INVALID_ARGUMENT if the CPU lacks it).  This is the producer of the
+ * 2 = BMI2 scalar, 3 = AVX-512 (one plane per zmm register), 4 = EVEX-128 (one lane per xmm register, AVX-512VL)
+ * (CHPIR_ERR_INVALID_ARGUMENT if the CPU lacks it).  This is the producer of the
  * host-pipelined setup mode, exposed so that it can be checked against the device expander and the oracle byte for byte. */
 CHPIR_API int chpir_host_generate_from_seed(const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols, uint64_t row_begin,
                                   uint64_t row_count, uint32_t impl, uint32_t *out_host);
-/* Name of the implementation impl = 0 resolves to on this CPU ("avx512", "bmi2" or "scalar"). */
+/* Name of the implementation impl = 0 resolves to on this CPU ("evex128", "avx512", "bmi2" or "scalar"). */
 CHPIR_API const char *chpir_host_xof_impl(void);
 /* Device time (ms) of the dominant kernels in the last call on this ctx/server, for bench.py's roofline block. */
 CHPIR_API int chpir_server_last_kernel_ms(const chpir_server *srv, float *respond_ms, float *gemm_ms, float *expand_ms);

@@ -108,7 +108,7 @@ def test_product_never_imports_the_oracle():
 
 
 # ------------------------------------------------------------------ host XOF producer (csrc/host_xof.cpp), no GPU involved
-@pytest.mark.parametrize("impl", [0, 1, 2, 3])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("rows,cols,r0,nr", [(1, 1, 0, 1), (1, 41, 0, 1), (1, 42, 0, 1), (1, 43, 0, 1), (3, 14, 1, 2), (7, 1000, 2, 4), (64, 4099, 60, 4)])
 def test_host_generate_from_seed_matches_oracle(impl, rows, cols, r0, nr):
     """Matrix::generate_from_seed (matrix.rs:541-558) from every host implementation == the oracle's TurboSHAKE128 stream."""
@@ -116,7 +116,7 @@ def test_host_generate_from_seed_matches_oracle(impl, rows, cols, r0, nr):
     try:
         got = cp.host_generate_from_seed(rows, cols, seed, r0, nr, impl)
     except cp.ChalametPIRError as e:
-        assert impl in (2, 3) and e.variant == "InvalidArgument"  # this CPU lacks BMI2 / AVX-512
+        assert impl in (2, 3, 4) and e.variant == "InvalidArgument"  # this CPU lacks BMI2 / AVX-512
         pytest.skip("instruction set not available on this CPU")
     assert np.array_equal(got, O.generate_rows_from_seed(cols, seed, r0, nr))
 
@@ -128,7 +128,7 @@ def test_host_xof_rfc9861_known_answer():
     seed = bytes(i % 251 for i in range(32))
     want = np.frombuffer(O.turboshake128(seed, 4 * 500), dtype="<u4")
     assert np.array_equal(cp.host_generate_from_seed(1, 500, seed)[0], want)
-    assert cp.host_xof_impl() in ("avx512", "bmi2", "scalar")
+    assert cp.host_xof_impl() in ("evex128", "avx512", "bmi2", "scalar")
 
 
 def test_upload_query_slices_binding_without_a_gpu():

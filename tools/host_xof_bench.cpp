@@ -1,5 +1,5 @@
 // host_xof_bench.cpp -- ns per Keccak-p[1600,12] permutation of every host XOF implementation on THIS machine's cores
-// (csrc/host_xof.cpp: 1 = portable scalar, 2 = BMI2 scalar, 3 = AVX-512), each checked against the scalar stream.
+// (csrc/host_xof.cpp: 1 = portable scalar, 2 = BMI2 scalar, 3 = AVX-512 planes, 4 = EVEX-128 lane per register), each checked against the scalar stream.
 //   g++ -O3 -std=c++17 -I chalametpir_b200/csrc tools/host_xof_bench.cpp chalametpir_b200/csrc/host_xof.cpp -o tools/host_xof_bench
 #include <chrono>
 #include <cstdio>
@@ -15,7 +15,7 @@ int main() {
   std::vector<uint8_t> buf(kBlocks * kXofRate), ref;
   uint8_t seed[32];
   for (int i = 0; i < 32; i++) seed[i] = uint8_t(i * 7 + 1);
-  for (int impl : {1, 2, 3}) {
+  for (int impl : {1, 2, 3, 4}) {
     HostXof x;
     host_xof_init(&x, seed);
     if (!host_xof_squeeze_blocks(&x, buf.data(), kCheck, impl)) {
