@@ -76,6 +76,16 @@ def test_host_encode_is_byte_identical_to_oracle(arity, n):
             assert O.recover_value(D, O.Filter.from_bytes(fb), k) == db[k]
 
 
+@pytest.mark.parametrize("b", range(4, 15))
+def test_host_row_codec_every_bit_length(b):
+    """encode_kv_as_row (serialization.rs:22-116) through the C++ host encoder for every legal field width: the fields are read out
+    of the byte stream with unaligned 64-bit loads there, pushed through a bit accumulator in the oracle -- same rows."""
+    db = make_db(257, seed=b, val_len=(1, 333))
+    D, fb = cp.encode_kv_database(db, b, 4 if b % 2 else 3, filter_seed_rng=b)
+    D2, f2 = O.from_kv_database(db, b, 4 if b % 2 else 3, rng_seed=b)
+    assert fb == f2.to_bytes() and np.array_equal(D, D2)
+
+
 def test_host_encode_os_entropy_seed_is_still_valid():
     db = make_db(500, seed=1)
     D, fb = cp.encode_kv_database(db, 10, 3)  # filter seed from the OS, like the reference
