@@ -80,3 +80,68 @@ def _worker(rank, world, port, K, N, b, lwe, out_dir):
 def test_two_rank_gloo_column_sharding(tmp_path, world, N):
     mp.spawn(_worker, args=(world, _free_port(), 997, N, 9, 16, str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").read_text() == "ok"
+
+
+def _pipeline_worker(rank, world, port, K, N, b, steps, out_dir):
+    """The serving schedule of bench.py at N > 1 on CPU tensors: query batches are broadcast one step ahead (double-buffered) on the
+    default group, every rank answers for its column slice, and the response slices are gathered asynchronously on a SECOND group so
+    that a gather -- which cannot finish before the slowest rank has answered -- never sits in front of the next broadcast."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pg_out = dist.new_group(backend="gloo")
+    try:
+        rng = np.random.default_rng(5)
+        D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+        Q = 2
+        batches = rng.integers(0, 2**32, size=(steps, Q, K), dtype=np.uint64).astype(np.uint32)
+        c0, nc = sharding.slice_of(N, rank, world)
+        counts = sharding.slice_counts(N, world)
+        pad = max(counts)
+        srv, _ = O.Server.setup_from_matrix(SEED, np.ascontiguousarray(D[:, c0 : c0 + nc]), b, want_hint=False)
+        q_bufs = [torch.zeros((Q, K), dtype=torch.int32) for _ in range(2)]
+        send = [torch.zeros((Q, pad), dtype=torch.int32) for _ in range(2)]
+        gathered = [torch.zeros((world, Q, pad), dtype=torch.int32) for _ in range(2)]
+        results = []
+
+        def load(i, buf):  # only the root holds the queries before the broadcast
+            if rank == 0:
+                buf.copy_(torch.from_numpy(batches[i].view(np.int32)))
+            else:
+                buf.zero_()
+
+        load(0, q_bufs[0])
+        bw = dist.broadcast(q_bufs[0], 0, async_op=True)
+        gw = [None, None]
+        for i in range(steps):
+            p = i & 1
+            bw.wait()
+            if i + 1 < steps:
+                load(i + 1, q_bufs[p ^ 1])
+                bw = dist.broadcast(q_bufs[p ^ 1], 0, async_op=True)
+            q_here = q_bufs[p].numpy().view(np.uint32)
+            local = np.stack([O.matrix_from_bytes(srv.respond(O.matrix_to_bytes(q_here[j : j + 1])))[0] for j in range(Q)])
+            if gw[p] is not None:
+                gw[p][0].wait()
+                results.append(sharding.unpad_gathered(torch, gathered[p], counts).clone())
+            send[p].zero_()
+            send[p][:, :nc] = torch.from_numpy(local.view(np.int32))
+            gw[p] = (dist.all_gather_into_tensor(gathered[p].view(-1), send[p].view(-1), group=pg_out, async_op=True), i)
+        for w in sorted((w for w in gw if w is not None), key=lambda t: t[1]):
+            w[0].wait()
+            results.append(sharding.unpad_gathered(torch, gathered[w[1] & 1], counts).clone())
+        assert len(results) == steps
+        if rank == 0:
+            ref, _ = O.Server.setup_from_matrix(SEED, D, b, want_hint=False)
+            for i in range(steps):
+                for j in range(Q):
+                    want = ref.respond(O.matrix_to_bytes(batches[i, j : j + 1]))
+                    assert sharding.response_bytes(results[i][j].numpy().view(np.uint32)) == want, (i, j)
+            open(os.path.join(out_dir, "ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pipelined_serving_schedule_with_a_second_group_for_the_gathers(tmp_path, world):
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), 503, 118, 9, 5, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
