@@ -292,6 +292,7 @@ int peel(uint32_t arity, const std::vector<uint8_t> &digests, uint64_t n, uint32
   const uint64_t slots = fs.num_fingerprints;
   std::vector<uint8_t> count(slots);
   std::vector<uint64_t> xored(slots);
+  std::vector<uint32_t> xidx(slots);  // XOR of the key indices on a slot: the index of the last key left, next to its hash in xored
   std::vector<uint32_t> alone(slots);
   std::vector<uint64_t> hashes(n);
   res->order.assign(n, 0);
@@ -320,15 +321,18 @@ int peel(uint32_t arity, const std::vector<uint8_t> &digests, uint64_t n, uint32
 
     std::fill(count.begin(), count.end(), 0);
     std::fill(xored.begin(), xored.end(), 0);
+    std::fill(xidx.begin(), xidx.end(), 0u);
     uint8_t seen = 0;
     bool wrapped = false;
     for (uint64_t j = 0; j < n; j++) {
-      const uint64_t h = hashes[sorted_idx[j]];
+      const uint32_t key = sorted_idx[j];
+      const uint64_t h = hashes[key];
       const Slots s = slots_of(arity, h, fs.segment_length, fs.segment_count_length);
       for (uint32_t a = 0; a < arity; a++) {
         wrapped |= count[s.h[a]] >= 252;
         count[s.h[a]] = static_cast<uint8_t>((count[s.h[a]] + 4) ^ a);
         xored[s.h[a]] ^= h;
+        xidx[s.h[a]] ^= key;
         seen |= count[s.h[a]];
       }
     }
@@ -346,9 +350,11 @@ int peel(uint32_t arity, const std::vector<uint8_t> &digests, uint64_t n, uint32
       const uint32_t slot = alone[--q];
       if ((count[slot] >> 2) != 1) continue;
       const uint64_t h = xored[slot];
+      const uint32_t key = xidx[slot];
       const uint8_t which = count[slot] & 3;
       res->found[top] = which;
       res->order[top] = h;
+      res->key_of_order[top] = key;  // hash -> key (the reference's HashMap<u64,&[u8]> hash_to_key) without a lookup
       top++;
       const Slots s = slots_of(arity, h, fs.segment_length, fs.segment_count_length);
       for (uint32_t step = 1; step < arity; step++) {
@@ -358,20 +364,11 @@ int peel(uint32_t arity, const std::vector<uint8_t> &digests, uint64_t n, uint32
         q += (count[other] >> 2) == 2;
         count[other] = static_cast<uint8_t>((count[other] - 4) ^ a);
         xored[other] ^= h;
+        xidx[other] ^= key;
       }
     }
     if (top != n) continue;
 
-    // hash -> key index (the reference's HashMap<u64,&[u8]> hash_to_key)
-    std::vector<std::pair<uint64_t, uint32_t>> by_hash(n);
-    for (uint64_t i = 0; i < n; i++) by_hash[i] = {hashes[i], static_cast<uint32_t>(i)};
-    std::sort(by_hash.begin(), by_hash.end());
-    parallel_for(n, 1 << 14, [&](uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; i++) {
-        auto it = std::lower_bound(by_hash.begin(), by_hash.end(), std::make_pair(res->order[i], 0u));
-        res->key_of_order[i] = it->second;
-      }
-    });
     std::memcpy(res->params.seed, seed, 32);
     res->params.arity = arity;
     res->params.segment_length = fs.segment_length;
