@@ -157,3 +157,34 @@ def test_upload_query_slices_binding_without_a_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(cp.ChalametPIRError):
             sharding.upload_query_slices(q_words, 0, 4, q_slice, FakeStream())
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The Python mirror of every struct that crosses the C ABI has the size and the field offsets the C compiler gives the header's
+    declaration (guards against the two drifting apart when a field is added on one side only)."""
+    import ctypes as C
+    import subprocess
+
+    from chalametpir_b200 import _lib as L
+
+    pairs = {"chpir_setup_opts": L.SetupOpts, "chpir_setup_timing": L.SetupTiming, "chpir_server_info": L.ServerInfo,
+             "chpir_client_opts": L.ClientOpts, "chpir_client_info": L.ClientInfo}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "chalamet_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c11", "-I", inc, str(src), "-o", str(exe)])  # the header is plain C, as an FFI header must be
+    got = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, val = line.split()
+        got[(cname, field)] = int(val)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
