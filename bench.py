@@ -189,6 +189,35 @@ def cpu_respond_qps(K_full: int, N: int, b: int, frac: int, iters: int, min_iter
             "scale": scale}
 
 
+def cpu_setup_extrapolated(K_full: int, N: int, b: int, frac: int, a_rows: int = 4):
+    """CPU restatement of the reference's Server::setup cost at full size, EXTRAPOLATED from a bounded sample (SURVEY.md section 8d):
+    the hint product M = A.D with the reference's own loop structure (matrix.rs:1040-1059: one fold per output element, D read
+    column-wise; rayon -> OpenMP over outputs) on `a_rows` rows of A and the first K/frac rows of D, scaled by (1774 / a_rows) * frac;
+    plus the TurboSHAKE128 squeeze of A (matrix.rs:541-558) timed on 8 MB of stream and scaled to 4 * 1774 * K bytes."""
+    from oracle import oracle as O
+
+    Ks = max(3, K_full // frac)
+    D = host_d(Ks, N, b)
+    A = O.generate_rows_from_seed(Ks, SEED_MU, 0, a_rows)
+    O.matmul(A[:1], D, fast=False)  # warm the thread pool and the pages
+    t = time.perf_counter()
+    O.matmul(A, D, fast=False)
+    gemm_sample_s = time.perf_counter() - t
+    gemm_full_s = gemm_sample_s * (LWE / a_rows) * (K_full / Ks)
+    nbytes = 8 << 20
+    t = time.perf_counter()
+    O.turboshake128(SEED_MU, nbytes)
+    xof_sample_s = time.perf_counter() - t
+    xof_full_s = xof_sample_s * (4.0 * LWE * K_full / nbytes)
+    return {
+        "extrapolated": True, "kind": "port", "cores": O.num_threads(),
+        "hint_gemm_s": gemm_full_s, "expand_a_s": xof_full_s, "total_s": gemm_full_s + xof_full_s,
+        "sample": f"hint GEMM: {a_rows} of {LWE} rows of A x rows [0,{Ks}) of K={K_full} (all {N} columns) in {gemm_sample_s:.3f} s, scaled by "
+                  f"{LWE / a_rows * K_full / Ks:.0f}; XOF: {nbytes >> 20} MB of the stream in {xof_sample_s:.3f} s on one core, scaled by "
+                  f"{4.0 * LWE * K_full / nbytes:.0f}; filter construction and row encoding not included",
+    }
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference's Server::respond on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -753,6 +782,11 @@ def run_b200(args):
             "sample": f"rows [0,{r['rows_sample']}) of K={K} (1/{args.cpu_sample_frac} of the database, all {N} columns), median of {len(r['times'])} queries = "
                       f"{r['ms_sample']:.2f} ms; respond is linear in K so queries/s is scaled by 1/{r['scale']:.2f}; OpenMP threads={r['threads']} of {os.cpu_count()} cpus",
         }
+
+        try:  # the reference's setup cost on these host cores, extrapolated from a sample (a reported baseline, never a target)
+            setup["cpu_baseline_extrapolated"] = cpu_setup_extrapolated(K, N, b, args.cpu_sample_frac)
+        except Exception as ex:  # pragma: no cover -- diagnostics must never cost the bench line
+            setup["cpu_baseline_extrapolated"] = {"error": repr(ex)}
 
     line = {
         "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
