@@ -784,7 +784,7 @@ def run_b200(args):
         }
 
         try:  # the reference's setup cost on these host cores, extrapolated from a sample (a reported baseline, never a target)
-            setup["cpu_baseline_extrapolated"] = cpu_setup_extrapolated(K, N, b, args.cpu_sample_frac)
+            setup["cpu_baseline_extrapolated"] = cpu_setup_extrapolated(K, N, b, frac=2, a_rows=2)  # half of D: well past the host's last-level cache
         except Exception as ex:  # pragma: no cover -- diagnostics must never cost the bench line
             setup["cpu_baseline_extrapolated"] = {"error": repr(ex)}
 
