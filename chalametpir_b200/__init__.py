@@ -6,6 +6,7 @@ byte layouts are unchanged.  The compute lives in ``libchalamet_b200.so`` (hand-
 """
 from ._lib import FILTER_PARAM_BYTE_LEN, LIB_PATH, LWE_DIMENSION, SEED_BYTE_LEN, SERVER_SETUP_MAX_ATTEMPT_COUNT
 from .client import Client
+from .cluster import RESPOND_GEMV, RESPOND_TC, Cluster, ClusterServer, cluster_plan
 from .errors import ChalametPIRError
 from .server import (
     PinnedBuffer,
@@ -25,6 +26,11 @@ from .server import (
 
 __all__ = [
     "Server",
+    "Cluster",
+    "ClusterServer",
+    "cluster_plan",
+    "RESPOND_GEMV",
+    "RESPOND_TC",
     "Client",
     "PinnedBuffer",
     "ChalametPIRError",

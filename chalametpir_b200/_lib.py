@@ -30,11 +30,13 @@ class SetupOpts(C.Structure):
         ("respond_coalesce", C.c_uint32),
         ("db_encode", C.c_uint32),
         ("a_cache", C.c_uint32),
+        ("hint_on_device", C.c_uint32),
     ]
 
 
-A_EXPAND_DEVICE = 0
+A_EXPAND_AUTO = 0
 A_EXPAND_HOST_PIPELINED = 1
+A_EXPAND_DEVICE = 2
 
 
 class SetupTiming(C.Structure):
@@ -54,6 +56,29 @@ class ServerInfo(C.Structure):
         ("row_pitch_bytes", C.c_uint64),
         ("packed_bytes", C.c_uint64),
     ]
+
+
+class ClusterServerInfo(C.Structure):
+    _fields_ = [
+        ("n_gpus", C.c_uint32),
+        ("cols_n", C.c_uint32),
+        ("rows_k", C.c_uint64),
+        ("mat_elem_bit_len", C.c_uint32),
+        ("lwe_rows", C.c_uint32),
+        ("k_pitch", C.c_uint64),
+        ("packed_bytes_total", C.c_uint64),
+        ("packed_bytes_max_rank", C.c_uint64),
+        ("setup_total_s", C.c_double),
+        ("hint_gather_s", C.c_double),
+        ("gather_uses_nccl", C.c_uint32),
+        ("nccl_version", C.c_uint32),
+        ("batches", C.c_uint64),
+        ("queries", C.c_uint64),
+        ("tc_batches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class ClientOpts(C.Structure):
@@ -96,6 +121,23 @@ EXPORTS = [
     "chpir_server_load",
     "chpir_server_setup_timing",
     "chpir_server_get_info",
+    "chpir_server_hint_device",
+    "chpir_cluster_create",
+    "chpir_cluster_destroy",
+    "chpir_cluster_size",
+    "chpir_cluster_ctx",
+    "chpir_cluster_plan",
+    "chpir_cluster_server_setup_from_db",
+    "chpir_cluster_server_setup",
+    "chpir_cluster_server_setup_device",
+    "chpir_cluster_server_destroy",
+    "chpir_cluster_server_shard",
+    "chpir_cluster_server_save",
+    "chpir_cluster_server_load",
+    "chpir_cluster_server_respond",
+    "chpir_cluster_server_respond_batch",
+    "chpir_cluster_server_respond_device",
+    "chpir_cluster_server_get_info",
     "chpir_server_respond",
     "chpir_server_respond_batch",
     "chpir_server_respond_device",
@@ -171,3 +213,25 @@ lib.chpir_client_query_with.argtypes = [_vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c
 lib.chpir_client_process_response.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _szp]
 lib.chpir_client_get_info.argtypes = [_vp, C.POINTER(ClientInfo)]
 lib.chpir_server_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.chpir_server_hint_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_uint32)]
+_u32p, _u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+lib.chpir_cluster_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
+lib.chpir_cluster_destroy.restype = None
+lib.chpir_cluster_destroy.argtypes = [_vp]
+lib.chpir_cluster_size.argtypes = [_vp, C.POINTER(C.c_int)]
+lib.chpir_cluster_ctx.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int)]
+lib.chpir_cluster_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, _u32p, _u32p, _u64p, _u64p, _u64p]
+lib.chpir_cluster_server_setup_from_db.argtypes = [
+    _vp, C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64), C.POINTER(SetupOpts), _vp, C.c_size_t, _szp, _vp, C.POINTER(_vp),
+]
+lib.chpir_cluster_server_setup.argtypes = [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(SetupOpts), _vp, C.c_size_t, _szp, C.POINTER(_vp)]
+lib.chpir_cluster_server_setup_device.argtypes = [_vp, _vp, C.POINTER(_vp), C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(SetupOpts), _vp, C.c_size_t, _szp, C.POINTER(_vp)]
+lib.chpir_cluster_server_destroy.restype = None
+lib.chpir_cluster_server_destroy.argtypes = [_vp]
+lib.chpir_cluster_server_shard.argtypes = [_vp, C.c_int, C.POINTER(_vp)]
+lib.chpir_cluster_server_save.argtypes = [_vp, C.c_char_p]
+lib.chpir_cluster_server_load.argtypes = [_vp, C.c_char_p, C.POINTER(SetupOpts), C.POINTER(_vp)]
+lib.chpir_cluster_server_respond.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp]
+lib.chpir_cluster_server_respond_batch.argtypes = [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32, _vp, C.c_size_t]
+lib.chpir_cluster_server_respond_device.argtypes = [_vp, C.POINTER(_vp), C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+lib.chpir_cluster_server_get_info.argtypes = [_vp, C.POINTER(ClusterServerInfo)]

@@ -28,13 +28,13 @@ class Client:
         self.mat_elem_bit_len, self.arity = info.mat_elem_bit_len, info.arity
 
     @staticmethod
-    def setup(seed_mu: bytes, hint_bytes: bytes, filter_param_bytes: bytes, *, device: int = 0, lwe_rows: int = 0, a_expand: str = "device",
+    def setup(seed_mu: bytes, hint_bytes: bytes, filter_param_bytes: bytes, *, device: int = 0, lwe_rows: int = 0, a_expand: str = "auto",
               host_chunk_rows: int = 0) -> "Client":
         """Client::setup(seed_mu, hint_bytes, filter_param_bytes)   [client.rs:39-57]"""
         seed = _seed_arr(seed_mu)
         hint = np.frombuffer(hint_bytes, dtype=np.uint8)
         fb = np.frombuffer(filter_param_bytes, dtype=np.uint8)
-        o = ClientOpts(lwe_rows, {"device": 0, "host": 1}[a_expand], host_chunk_rows)
+        o = ClientOpts(lwe_rows, {"auto": 0, "host": 1, "device": 2}[a_expand], host_chunk_rows)
         h = C.c_void_p()
         check(lib.chpir_client_setup(get_ctx(device), seed.ctypes.data, hint.ctypes.data if hint.size else None, hint.size,
                                      fb.ctypes.data if fb.size else None, fb.size, C.byref(o), C.byref(h)))

@@ -15,6 +15,7 @@
 #include "host_encode.hpp"
 #include "host_pipe.cuh"
 #include "host_xof.hpp"
+#include "server_state.cuh"
 
 namespace chpir {
 
@@ -24,171 +25,9 @@ void set_last_cuda_error(cudaError_t e, const char *what) {
   (void)cudaGetLastError();  // clear the sticky-less error state
 }
 
-// One in-flight respond: its own stream and buffers, so concurrent callers never share state.
-struct RespondSlot {
-  cudaStream_t stream = nullptr;
-  uint32_t *d_q = nullptr;
-  uint32_t *d_resp = nullptr;
-  uint32_t *h_resp = nullptr;  // pinned
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-};
-
-// Transparent coalescing of concurrent chpir_server_respond calls (chpir_setup_opts.respond_coalesce).  Callers join the open
-// batch, each uploading its own query straight into its row of the batch's device buffer; the first caller of a batch is its
-// leader: it waits for the previous batch to leave the GPU (that wait IS the batching window -- an idle GPU means a batch of
-// one and no added latency), closes the batch, runs one launch for all of it (grid.y GEMV for a handful of queries, the
-// tensor-core limb GEMM beyond that, where one pass over D serves up to 128 queries) and reads the responses back.  Two batches
-// ping-pong, so the uploads of the next batch overlap the compute of the current one.
-struct CoalesceBatch {
-  uint32_t *d_q = nullptr, *d_resp = nullptr, *h_resp = nullptr;
-  cudaStream_t copy = nullptr;
-  cudaEvent_t uploaded = nullptr;
-  uint32_t count = 0, issued = 0, picked = 0;
-  bool closed = false, done = false;
-  int rc = CHPIR_OK;
-};
-
-struct Coalescer {
-  static constexpr uint32_t kMaxBatch = 128;
-  static constexpr uint32_t kTensorCoreFrom = 6;  // a tensor-core pass costs about as much as five streaming GEMVs
-  std::mutex mu;
-  std::condition_variable cv;
-  std::mutex exec_mu;  // one batch on the GPU at a time
-  CoalesceBatch b[2];
-  int open = 0;
-  cudaStream_t compute = nullptr;
-  bool ready = false;
-  uint64_t batches = 0, queries = 0, tc_batches = 0;  // statistics
-};
-
 }  // namespace chpir
 
 using namespace chpir;
-
-struct chpir_server {
-  chpir_ctx *ctx = nullptr;
-  uint64_t K = 0;
-  uint32_t ncols = 0, col_begin = 0, b = 0;
-  PackedLayout layout{};
-  RespondPlan plan{};
-  uint8_t *d_packed = nullptr;
-  uint64_t packed_bytes = 0;
-  GemmTcB *gemm = nullptr;  // D's byte-limb planes + operand ring, kept for the tensor-core batched respond
-  std::mutex gemm_mu;
-  bool coalesce = false;
-  Coalescer co;
-  chpir_setup_timing timing{};
-  float last_respond_ms = 0.f, last_gemm_ms = 0.f, last_expand_ms = 0.f;
-  std::mutex pool_mu;
-  std::vector<RespondSlot *> free_slots;
-  std::vector<RespondSlot *> all_slots;
-  // chpir_server_respond_batch: one batch in flight per server, buffers grown on demand
-  std::mutex batch_mu;
-  cudaStream_t batch_stream = nullptr;
-  uint32_t *batch_q = nullptr, *batch_resp = nullptr, *batch_h_resp = nullptr;
-  uint32_t batch_cap = 0;
-
-  ~chpir_server() {
-    if (ctx) cudaSetDevice(ctx->device);
-    for (RespondSlot *s : all_slots) {
-      if (s->stream) cudaStreamSynchronize(s->stream);
-      if (s->d_q) cudaFree(s->d_q);
-      if (s->d_resp) cudaFree(s->d_resp);
-      if (s->h_resp) cudaFreeHost(s->h_resp);
-      if (s->e0) cudaEventDestroy(s->e0);
-      if (s->e1) cudaEventDestroy(s->e1);
-      if (s->stream) cudaStreamDestroy(s->stream);
-      delete s;
-    }
-    if (batch_stream) {
-      cudaStreamSynchronize(batch_stream);
-      cudaStreamDestroy(batch_stream);
-    }
-    if (batch_q) cudaFree(batch_q);
-    if (batch_resp) cudaFree(batch_resp);
-    if (batch_h_resp) cudaFreeHost(batch_h_resp);
-    if (d_packed) cudaFree(d_packed);
-    if (gemm) gemm_tc_free(gemm);
-    for (CoalesceBatch &cb : co.b) {
-      if (cb.copy) {
-        cudaStreamSynchronize(cb.copy);
-        cudaStreamDestroy(cb.copy);
-      }
-      if (cb.uploaded) cudaEventDestroy(cb.uploaded);
-      if (cb.d_q) cudaFree(cb.d_q);
-      if (cb.d_resp) cudaFree(cb.d_resp);
-      if (cb.h_resp) cudaFreeHost(cb.h_resp);
-    }
-    if (co.compute) {
-      cudaStreamSynchronize(co.compute);
-      cudaStreamDestroy(co.compute);
-    }
-  }
-
-  int init_coalescer() {
-    for (CoalesceBatch &cb : co.b) {
-      if (cudaMalloc(&cb.d_q, size_t(Coalescer::kMaxBatch) * K * 4) != cudaSuccess ||
-          cudaMalloc(&cb.d_resp, size_t(Coalescer::kMaxBatch) * ncols * 4) != cudaSuccess ||
-          cudaMallocHost(&cb.h_resp, size_t(Coalescer::kMaxBatch) * ncols * 4) != cudaSuccess ||
-          cudaStreamCreateWithFlags(&cb.copy, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&cb.uploaded, cudaEventDisableTiming) != cudaSuccess) {
-        set_last_cuda_error(cudaGetLastError(), "respond coalescer allocation");
-        return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-      }
-    }
-    if (cudaStreamCreateWithFlags(&co.compute, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    co.ready = true;
-    return CHPIR_OK;
-  }
-
-  int reserve_batch(uint32_t nq) {
-    if (!batch_stream && cudaStreamCreateWithFlags(&batch_stream, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    if (nq <= batch_cap) return CHPIR_OK;
-    if (batch_q) cudaFree(batch_q);
-    if (batch_resp) cudaFree(batch_resp);
-    if (batch_h_resp) cudaFreeHost(batch_h_resp);
-    batch_q = batch_resp = batch_h_resp = nullptr;
-    batch_cap = 0;
-    if (cudaMalloc(&batch_q, size_t(nq) * K * 4) != cudaSuccess || cudaMalloc(&batch_resp, size_t(nq) * ncols * 4) != cudaSuccess ||
-        cudaMallocHost(&batch_h_resp, size_t(nq) * ncols * 4) != cudaSuccess) {
-      set_last_cuda_error(cudaGetLastError(), "respond batch allocation");
-      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    }
-    batch_cap = nq;
-    return CHPIR_OK;
-  }
-
-  int acquire(RespondSlot **out) {
-    {
-      std::lock_guard<std::mutex> g(pool_mu);
-      if (!free_slots.empty()) {
-        *out = free_slots.back();
-        free_slots.pop_back();
-        return CHPIR_OK;
-      }
-    }
-    RespondSlot *s = new (std::nothrow) RespondSlot();
-    if (!s) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
-    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMalloc(&s->d_q, K * 4) == cudaSuccess && cudaMalloc(&s->d_resp, size_t(ncols) * 4) == cudaSuccess &&
-              cudaMallocHost(&s->h_resp, size_t(ncols) * 4) == cudaSuccess && cudaEventCreate(&s->e0) == cudaSuccess &&
-              cudaEventCreate(&s->e1) == cudaSuccess;
-    {
-      std::lock_guard<std::mutex> g(pool_mu);
-      all_slots.push_back(s);
-    }
-    if (!ok) {
-      set_last_cuda_error(cudaGetLastError(), "respond slot allocation");
-      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    }
-    *out = s;
-    return CHPIR_OK;
-  }
-  void release(RespondSlot *s) {
-    std::lock_guard<std::mutex> g(pool_mu);
-    free_slots.push_back(s);
-  }
-};
 
 namespace {
 
@@ -315,7 +154,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   const uint32_t m = o.lwe_rows ? o.lwe_rows : CHPIR_LWE_DIMENSION;
   if (!o.skip_hint) {
     const size_t need = 8 + size_t(m) * ncols * 4;
-    if (!hint_out || hint_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
+    if (!o.hint_on_device && (!hint_out || hint_cap < need)) return CHPIR_ERR_BUFFER_TOO_SMALL;
     DevBuf scratch, c;
     if (int rc = scratch.alloc(512); rc != CHPIR_OK) return rc;
     if (int rc = c.alloc(size_t(m) * ncols * 4); rc != CHPIR_OK) return rc;
@@ -357,7 +196,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
       CHPIR_CUDA(cudaMemsetAsync(c.p, 0, size_t(m) * ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
       t_all.start(st);
       bool a_filled_now = false;
-      if (o.a_cache && !ctx->a_cache.matches(seed, m, K) && o.a_expand != CHPIR_A_EXPAND_HOST_PIPELINED) {
+      if (o.a_cache && !ctx->a_cache.matches(seed, m, K) && o.a_expand == CHPIR_A_EXPAND_DEVICE) {
         a_filled_now = true;
         // device expansion with a_cache: squeeze A once as row-major u32 (what the cache holds), then take the cached route below
         if (ctx->a_cache.a) cudaFree(ctx->a_cache.a);
@@ -379,7 +218,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
         if (int rc = hint_from_cached_a(ctx, g, m, K, ncols, c.as<uint32_t>(), st, &gemm_ms); rc != CHPIR_OK) return rc;
         t_all.stop(st);
         srv->timing.a_cache_hit = a_filled_now ? 0.0 : 1.0;
-      } else if (o.a_expand == CHPIR_A_EXPAND_HOST_PIPELINED) {
+      } else if (o.a_expand != CHPIR_A_EXPAND_DEVICE) {
         const double w0 = now_s();
         if (int rc = hint_host_pipelined(ctx, seed, g, m, K, ncols, c.as<uint32_t>(), o.host_chunk_rows, pipe, st, &gemm_ms, &srv->timing.xof_host_busy_s,
                                          &srv->timing.xof_host_wait_s, o.a_cache != 0);
@@ -419,9 +258,15 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
     trace_phase("core: A + hint GEMM", tt);
     const float all_ms = host_wall_ms > 0.f ? host_wall_ms : t_all.ms();
     const double t0 = now_s();
-    const uint32_t hdr[2] = {m, ncols};
-    std::memcpy(hint_out, hdr, 8);
-    CHPIR_CUDA(cudaMemcpyAsync(hint_out + 8, c.p, size_t(m) * ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    if (o.hint_on_device) {
+      // the slice stays in HBM for whoever gathers the slices of all ranks (csrc/cluster.cu); no download here
+      srv->d_hint = static_cast<uint32_t *>(c.release());
+      srv->hint_rows = m;
+    } else {
+      const uint32_t hdr[2] = {m, ncols};
+      std::memcpy(hint_out, hdr, 8);
+      CHPIR_CUDA(cudaMemcpyAsync(hint_out + 8, c.p, size_t(m) * ncols * 4, cudaMemcpyDeviceToHost, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    }
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
     srv->timing.d2h_s = now_s() - t0;
     trace_phase("core: hint download", tt);
@@ -429,7 +274,7 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
     srv->timing.expand_a_s = (all_ms - gemm_ms) * 1e-3;
     srv->last_gemm_ms = gemm_ms;
     srv->last_expand_ms = all_ms - gemm_ms;
-    if (hint_len) *hint_len = need;
+    if (hint_len) *hint_len = o.hint_on_device ? 0 : need;
   } else {
     CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
     if (hint_len) *hint_len = 0;
@@ -560,6 +405,8 @@ const char *chpir_strerror(int status) {
     case CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED: return "CudaKernelLaunchFailed";
     case CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED: return "CudaKernelExecutionFailed";
     case CHPIR_ERR_CUDA_UNSUPPORTED_DEVICE: return "CudaUnsupportedDevice";
+    case CHPIR_ERR_CUDA_PEER_ACCESS_UNAVAILABLE: return "CudaPeerAccessUnavailable";
+    case CHPIR_ERR_NCCL_FAILED: return "NcclFailed";
     case CHPIR_ERR_HOST_ALLOCATION_FAILED: return "HostAllocationFailed";
     default: return "UnknownStatus";
   }
@@ -726,7 +573,8 @@ int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE
   CHPIR_GUARD_END
 }
 
-static int server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k,
+extern "C++" {
+int chpir::server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k,
                                          uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
                                          size_t *hint_len, chpir_server **out, HostAPipe *pipe) {
   CHPIR_GUARD_BEGIN
@@ -764,6 +612,7 @@ static int server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPI
   return CHPIR_OK;
   CHPIR_GUARD_END
 }
+}  // extern "C++"
 
 int chpir_server_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k, uint32_t cols_n,
                        uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out) {
@@ -798,9 +647,11 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
     std::lock_guard<std::mutex> g(ctx->mu);
     a_cached = ctx->a_cache.matches(seed, opts->lwe_rows ? opts->lwe_rows : CHPIR_LWE_DIMENSION, K);
   }
-  if (opts && opts->a_expand == CHPIR_A_EXPAND_HOST_PIPELINED && !opts->skip_hint && opts->gemm_variant == 0 && !a_cached) {
-    const uint32_t m = opts->lwe_rows ? opts->lwe_rows : CHPIR_LWE_DIMENSION;
-    if (int rc = pipe.start(ctx->device, seed, m, K, opts->host_chunk_rows, (m + 127) / 128); rc != CHPIR_OK) return rc;
+  chpir_setup_opts o0{};
+  if (opts) o0 = *opts;
+  if (o0.a_expand != CHPIR_A_EXPAND_DEVICE && !o0.skip_hint && o0.gemm_variant == 0 && !a_cached) {
+    const uint32_t m = o0.lwe_rows ? o0.lwe_rows : CHPIR_LWE_DIMENSION;
+    if (int rc = pipe.start(ctx->device, seed, m, K, o0.host_chunk_rows, (m + 127) / 128); rc != CHPIR_OK) return rc;
     pipe_p = &pipe;
   }
   if (opts && opts->db_encode == CHPIR_DB_ENCODE_DEVICE) {
@@ -1016,9 +867,18 @@ int chpir_server_get_info(const chpir_server *srv, chpir_server_info *out) {
   return CHPIR_OK;
 }
 
+int chpir_server_hint_device(const chpir_server *srv, const uint32_t **hint_device, uint32_t *rows) {
+  if (!srv || !hint_device) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (!srv->d_hint) return CHPIR_ERR_INVALID_ARGUMENT;  // set up without chpir_setup_opts.hint_on_device
+  *hint_device = srv->d_hint;
+  if (rows) *rows = srv->hint_rows;
+  return CHPIR_OK;
+}
+
+extern "C++" {
 // Matrix::from_bytes validation (matrix.rs:973-1010) + the dimension check of
 // row_vector_x_compressed_transposed_matrix (matrix.rs:329-331), in that order.
-static int validate_query(const chpir_server *srv, const uint8_t *query, size_t len) {
+int chpir::validate_query_bytes(uint64_t K, const uint8_t *query, size_t len) {
   if (!query || len <= 8) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
   uint32_t rows, cols;
   std::memcpy(&rows, query, 4);
@@ -1026,9 +886,11 @@ static int validate_query(const chpir_server *srv, const uint8_t *query, size_t 
   const uint64_t n = uint64_t(rows) * cols;
   if (n == 0) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
   if (n * 4 != uint64_t(len - 8)) return CHPIR_ERR_FAILED_TO_DESERIALIZE_MATRIX_FROM_BYTES;
-  if (!(rows == 1 && cols == srv->K)) return CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_ROW_VECTOR_TRANSPOSED_MATRIX_MULTIPLICATION;
+  if (!(rows == 1 && cols == K)) return CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_ROW_VECTOR_TRANSPOSED_MATRIX_MULTIPLICATION;
   return CHPIR_OK;
 }
+static int validate_query(const chpir_server *srv, const uint8_t *query, size_t len) { return chpir::validate_query_bytes(srv->K, query, len); }
+}  // extern "C++"
 
 // One caller's share of a coalesced batch (see Coalescer).  query has been validated; resp_out holds 8 + 4*ncols bytes.
 static int respond_coalesced(chpir_server *srv, const uint8_t *query, uint8_t *resp_out) {
@@ -1220,10 +1082,13 @@ int chpir_server_respond_device_tc(chpir_server *srv, const uint32_t *q_device, 
   std::lock_guard<std::mutex> g(srv->gemm_mu);
   CHPIR_CUDA(cudaMemsetAsync(resp_device, 0, size_t(nq) * srv->ncols * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   // 128 queries per pass over D: the query block is the "A" operand of the hint GEMM, D's planes the "B" operand
+  // (gemm_mu serialises the enqueue; the buffer events order the EXECUTION of calls that arrive on different streams)
   for (uint32_t q0 = 0, p = 0; q0 < nq; q0 += 128, p++) {
     const uint32_t rows = std::min<uint32_t>(128u, nq - q0);
+    if (int rc = gemm_tc_buf_acquire(srv->gemm, p & 1, st); rc != CHPIR_OK) return rc;
     if (int rc = gemm_tc_load_panel_u32(srv->gemm, p & 1, q_device + size_t(q0) * srv->K, rows, st); rc != CHPIR_OK) return rc;
     if (int rc = gemm_tc_panel(srv->gemm, p & 1, rows, resp_device + size_t(q0) * srv->ncols, st); rc != CHPIR_OK) return rc;
+    if (int rc = gemm_tc_buf_release(srv->gemm, p & 1, st); rc != CHPIR_OK) return rc;
   }
   return CHPIR_OK;
   CHPIR_GUARD_END

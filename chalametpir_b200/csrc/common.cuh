@@ -98,6 +98,11 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
 int gemm_tc_panel(const GemmTcB *g, int buf, uint32_t rows, uint32_t *C_panel, cudaStream_t s);
 int gemm_tc_load_panel_u32(const GemmTcB *g, int buf, const uint32_t *A_rows, uint32_t rows, cudaStream_t s);
 uint8_t *gemm_tc_ring(const GemmTcB *g);
+uint64_t gemm_tc_panel_bytes(const GemmTcB *g);  // bytes of one ring buffer: [4 limbs][128 rows][kp]
+// Cross-stream ordering of the two-buffer operand ring: acquire before refilling `buf` on stream s, release after the panel GEMM
+// that read it has been enqueued on s.
+int gemm_tc_buf_acquire(const GemmTcB *g, int buf, cudaStream_t s);
+int gemm_tc_buf_release(const GemmTcB *g, int buf, cudaStream_t s);
 uint64_t gemm_tc_kp(const GemmTcB *g);
 void gemm_tc_free(GemmTcB *g);
 // Whole product, A: m x k u32 (device), C: m x n u32 (ldc = n), overwritten.  Workspace is allocated/freed internally.

@@ -340,7 +340,13 @@ struct GemmTcB {
   uint64_t k = 0, kp = 0;
   uint32_t n = 0, nb = 0, bn = 0, tiles_n = 0, kblocks = 0, kbps = 0, splits = 0;
   CUtensorMap map_b{}, map_a[2]{};
+  // Last reader of each ring buffer (the panel GEMM that consumed it), on whatever stream it ran: callers on different streams
+  // -- concurrent respond_batch / coalesced respond / respond_device_tc on one server -- order themselves against it before
+  // refilling the buffer (gemm_tc_buf_acquire / gemm_tc_buf_release), so the ring can be shared without serialising execution.
+  cudaEvent_t buf_done[2] = {nullptr, nullptr};
   ~GemmTcB() {
+    for (auto e : buf_done)
+      if (e) cudaEventDestroy(e);
     if (b8) cudaFree(b8);
     if (a_ring) cudaFree(a_ring);
   }
@@ -349,6 +355,12 @@ struct GemmTcB {
 uint64_t gemm_tc_panel_bytes(const GemmTcB *g) { return 4ull * BM * g->kp; }
 uint8_t *gemm_tc_ring(const GemmTcB *g) { return g->a_ring; }
 uint64_t gemm_tc_kp(const GemmTcB *g) { return g->kp; }
+int gemm_tc_buf_acquire(const GemmTcB *g, int buf, cudaStream_t s) {
+  return cudaStreamWaitEvent(s, g->buf_done[buf & 1], 0) == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+int gemm_tc_buf_release(const GemmTcB *g, int buf, cudaStream_t s) {
+  return cudaEventRecord(g->buf_done[buf & 1], s) == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
 void gemm_tc_free(GemmTcB *g) { delete g; }
 
 int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uint32_t b_bits, int sm_count, cudaStream_t s, GemmTcB **out) {
@@ -362,7 +374,9 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
   g->nb = b_bits <= 8 ? 1 : 2;
   int rc = CHPIR_OK;
   do {
-    if (cudaMalloc(&g->b8, uint64_t(g->nb) * n * g->kp) != cudaSuccess || cudaMalloc(&g->a_ring, 2 * gemm_tc_panel_bytes(g)) != cudaSuccess) {
+    if (cudaMalloc(&g->b8, uint64_t(g->nb) * n * g->kp) != cudaSuccess || cudaMalloc(&g->a_ring, 2 * gemm_tc_panel_bytes(g)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g->buf_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g->buf_done[1], cudaEventDisableTiming) != cudaSuccess) {
       rc = CHPIR_ERR_CUDA_ALLOCATION_FAILED;
       break;
     }

@@ -226,6 +226,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 constexpr int kRingMaxThreads = 1024;
+constexpr int kMaxDevices = 64;
 
 __device__ __forceinline__ void bar_sync_consumers(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
@@ -468,10 +469,14 @@ int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t
   // bulk copies of q need 16-byte aligned sources for every query of the batch
   const uint32_t q_bulk = (reinterpret_cast<uintptr_t>(q) % 16 == 0 && (nq == 1 || (K * 4) % 16 == 0)) ? 1u : 0u;
   auto launch = [&](auto kernel) -> int {
-    static thread_local const void *configured = nullptr;  // per instantiation (the lambda is instantiated per kernel type)
-    if (configured != reinterpret_cast<const void *>(kernel)) {
+    // Function attributes are per device: a thread that serves several GPUs of one process (the cluster of csrc/cluster.cu, or two
+    // servers on two devices) must raise the limit on each of them.  Cache = last kernel configured per device ordinal.
+    static thread_local const void *configured[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+    if (dev >= kMaxDevices || configured[dev] != reinterpret_cast<const void *>(kernel)) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-      configured = reinterpret_cast<const void *>(kernel);
+      if (dev < kMaxDevices) configured[dev] = reinterpret_cast<const void *>(kernel);
     }
     // One grid row per query (q_per_cta = 1): the hardware scheduler hands the next query's CTAs to whichever SMs finish first.
     // Looping over several queries inside one CTA lifetime (CHPIR_RING_Q_PER_CTA > 1) saves the per-query pipeline fill but fixes

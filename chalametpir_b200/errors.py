@@ -33,6 +33,8 @@ VARIANTS = {
     103: "CudaKernelLaunchFailed",
     104: "CudaKernelExecutionFailed",
     105: "CudaUnsupportedDevice",
+    106: "CudaPeerAccessUnavailable",
+    107: "NcclFailed",
     110: "HostAllocationFailed",
 }
 

@@ -159,16 +159,17 @@ class Server:
 
     # ------------------------------------------------------------------ setup
     @staticmethod
-    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0, a_expand="device", host_chunk_rows=0,
-              db_encode="host", respond_coalesce=False, a_cache=False) -> SetupOpts:
-        """a_expand: "device" (default; TurboSHAKE128 chain on one GPU warp) or "host" (one host core squeezes the chain and the
-        uploads + panel GEMMs are pipelined behind it -- same bytes, several times lower setup latency).
+    def _opts(lwe_rows=0, col_begin=0, col_count=0, gemm_variant=0, skip_hint=False, batch_tc=0, a_expand="auto", host_chunk_rows=0,
+              db_encode="host", respond_coalesce=False, a_cache=False, hint_on_device=False) -> SetupOpts:
+        """a_expand: "auto" (default: the faster walker, i.e. "host"), "host" (one host core squeezes the TurboSHAKE128 chain and the
+        uploads + panel GEMMs are pipelined behind it) or "device" (the chain on one GPU warp, A never leaves the device) -- same
+        bytes every way, ~10x lower setup latency on the host core.
         a_cache: keep A resident in the device context and reuse it in later setups with the same seed, LWE dimension and K (a
         database update): the XOF chain is skipped and the hint is the tensor-core GEMM alone -- same bytes."""
-        mode = {"device": 0, "host": 1, 0: 0, 1: 1}[a_expand]
+        mode = {"auto": 0, "host": 1, "device": 2, 0: 0, 1: 1, 2: 2}[a_expand]
         enc = {"host": 0, "device": 1, 0: 0, 1: 1}[db_encode]  # setup / setup_from_arrays only: where the rows of D are encoded and filled
         return SetupOpts(lwe_rows, col_begin, col_count, gemm_variant, 1 if skip_hint else 0, batch_tc, mode, host_chunk_rows,
-                         1 if respond_coalesce else 0, enc, 1 if a_cache else 0)
+                         1 if respond_coalesce else 0, enc, 1 if a_cache else 0, 1 if hint_on_device else 0)
 
     @staticmethod
     def setup(seed_mu: bytes, db: Mapping[bytes, bytes], arity: int = 3, *, device: int = 0, filter_seed_rng: Optional[int] = None,

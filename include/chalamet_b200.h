@@ -73,6 +73,8 @@ typedef enum chpir_status {
   CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED = 103,
   CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED = 104,
   CHPIR_ERR_CUDA_UNSUPPORTED_DEVICE = 105,
+  CHPIR_ERR_CUDA_PEER_ACCESS_UNAVAILABLE = 106, /* a cluster needs peer access (NVLink / NVSwitch) between all of its GPUs */
+  CHPIR_ERR_NCCL_FAILED = 107,                  /* libnccl.so.2 could not be loaded, or an NCCL call failed */
   CHPIR_ERR_HOST_ALLOCATION_FAILED = 110
 } chpir_status;
 
@@ -137,7 +139,7 @@ typedef struct chpir_setup_opts {
                             planes resident iff the hint GEMM built them anyway, 1 = always build and keep them,
                             2 = never keep them (saves 2*K*N bytes of HBM)                                */
   uint32_t a_expand;     /* where the LWE matrix A = generate_from_seed(lwe_rows, K, seed) (matrix.rs:541-558) is squeezed out of
-                            TurboSHAKE128: CHPIR_A_EXPAND_DEVICE (default) or CHPIR_A_EXPAND_HOST_PIPELINED            */
+                            TurboSHAKE128: CHPIR_A_EXPAND_AUTO (default), _HOST_PIPELINED or _DEVICE                  */
   uint32_t host_chunk_rows; /* host-pipelined mode: rows of A per pinned upload chunk; 0 = about 32 MB worth (tests shrink it) */
   uint32_t respond_coalesce; /* 1 = concurrent chpir_server_respond calls on this server are coalesced: whoever arrives while the
                             previous batch is on the GPU is answered by ONE launch (a grid.y GEMV for up to 5 queries, the
@@ -150,6 +152,9 @@ typedef struct chpir_setup_opts {
                             re-runs setup after a database update with the same seed skips the serial XOF chain -- the whole of
                             the hint computation is then the tensor-core GEMM (milliseconds).  A setup with another seed,
                             lwe_rows or K replaces the cached matrix.  Same hint bytes either way.                      */
+  uint32_t hint_on_device; /* 1 = leave this server's hint slice (lwe_rows x col_count u32, row-major) in HBM instead of downloading it:
+                            hint_out may be NULL, *hint_len is 0, and chpir_server_hint_device returns the pointer.  This is what the
+                            cluster layer gathers over NCCL / NVLink into the wire-format hint.                          */
 } chpir_setup_opts;
 
 /* chpir_setup_opts.db_encode.  Key digests and filter construction (peeling) always run on the host.
@@ -161,14 +166,18 @@ typedef struct chpir_setup_opts {
 #define CHPIR_DB_ENCODE_DEVICE 1u
 
 /* chpir_setup_opts.a_expand.  The squeeze is ONE serial chain of Keccak-p[1600,12] permutations (49.8 M of them at
- * 2^20 entries); neither mode changes a single byte of A or of the hint.
- *   DEVICE:         one warp walks the chain on the GPU and writes the GEMM's byte planes directly (csrc/expand.cu).
- *   HOST_PIPELINED: one host core walks the chain (csrc/host_xof.cpp) into a ring of pinned chunks that are uploaded and
+ * 2^20 entries); no mode changes a single byte of A or of the hint.
+ *   AUTO (0, the default): whichever walker is faster -- HOST_PIPELINED on every machine measured so far (one host core: ~100 ns
+ *                   per permutation, 5.3 s at 2^20 entries; one GPU warp: 1146 ns, 57 s), so that the stock call is the
+ *                   seconds-scale setup.
+ *   HOST_PIPELINED: one host core walks the chain (csrc/host_xof.cpp) into a ring of chunks that are uploaded and
  *                   multiplied panel by panel while the core keeps squeezing -- what the reference's own `gpu` feature does
- *                   with its CPU-side generate_from_seed + upload (server.rs:115-123), but overlapped.  A CPU core runs the
- *                   chain several times faster than a GPU warp, so this is the low-latency setup. */
-#define CHPIR_A_EXPAND_DEVICE 0u
+ *                   with its CPU-side generate_from_seed + upload (server.rs:115-123), but overlapped.
+ *   DEVICE:         one warp walks the chain on the GPU and writes the GEMM's byte planes directly (csrc/expand.cu): A never
+ *                   leaves the device (north_star's "A expanded on device"), at the latency of a GPU warp. */
+#define CHPIR_A_EXPAND_AUTO 0u
 #define CHPIR_A_EXPAND_HOST_PIPELINED 1u
+#define CHPIR_A_EXPAND_DEVICE 2u
 
 /* d_host: K x N row-major u32 (Matrix elems), values < 2^mat_elem_bit_len.
  * hint_out receives the wire-format hint slice: header (lwe_rows, col_count) + lwe_rows*col_count u32; with the
@@ -226,6 +235,8 @@ typedef struct chpir_server_info {
   uint64_t packed_bytes;    /* total resident packed bytes = what one respond streams */
 } chpir_server_info;
 CHPIR_API int chpir_server_get_info(const chpir_server *srv, chpir_server_info *out);
+/* The hint slice a setup with chpir_setup_opts.hint_on_device = 1 left in HBM (*rows x cols_n u32; owned by the server). */
+CHPIR_API int chpir_server_hint_device(const chpir_server *srv, const uint32_t **hint_device, uint32_t *rows);
 
 /* ---- respond: replaces Server::respond (server.rs:184-190) -> Matrix::from_bytes (matrix.rs:973-1010) +
  *      row_vector_x_compressed_transposed_matrix (matrix.rs:328-485) + to_bytes --------------------------- */
@@ -248,13 +259,103 @@ CHPIR_API int chpir_server_respond_device(chpir_server *srv, const uint32_t *q_d
  * Returns CHPIR_ERR_INVALID_ARGUMENT if the server was set up without limb planes (chpir_setup_opts.batch_tc). */
 CHPIR_API int chpir_server_respond_device_tc(chpir_server *srv, const uint32_t *q_device, uint32_t nq, uint32_t *resp_device, void *cuda_stream);
 
+/* ---- cluster: the same server on 1..8 GPUs of ONE process (north_star (3)) ---------------------------
+ * The reference's public surface cannot grow a rank argument -- `Server::setup(seed, db)` (server.rs:103) and
+ * `Server::respond(&self, query)` (server.rs:184) -- so the sharding lives behind the handle: D, the hint and every response are
+ * split by COLUMN slices over the GPUs (rank r owns chpir_cluster_plan's columns; no cross-rank arithmetic), the library owns the
+ * per-device contexts, peer mappings, streams and NCCL communicators, and the Rust stub in INTEGRATION.md reaches all GPUs through
+ * the unchanged two calls.  Data movement inside a respond:
+ *   host query --(every GPU's own PCIe link: its K/n words)--> HBM --(NVLink peer reads, fused with the limb split / CE copies)-->
+ *   whole query on every GPU --> GEMV or tensor-core GEMM on the column slice --> response columns written straight into the
+ *   caller-visible row (strided D2H per GPU; no gather kernel).
+ * NCCL (libnccl.so.2, resolved at run time) gathers the hint slices once per setup. */
+typedef struct chpir_cluster chpir_cluster;
+typedef struct chpir_cluster_server chpir_cluster_server;
+
+/* n_gpus GPUs: device_ordinals[0..n_gpus) or, if NULL, ordinals 0..n_gpus-1.  n_gpus = 0 reads the environment variable CHPIR_GPUS
+ * (default 1) -- the runtime knob a Rust `Server::setup` uses, since its signature has no room for one.  Every pair of GPUs must
+ * have peer access (CHPIR_ERR_CUDA_PEER_ACCESS_UNAVAILABLE otherwise). */
+CHPIR_API int chpir_cluster_create(int n_gpus, const int *device_ordinals, chpir_cluster **out);
+CHPIR_API void chpir_cluster_destroy(chpir_cluster *cluster);
+CHPIR_API int chpir_cluster_size(const chpir_cluster *cluster, int *n_gpus);
+/* The per-GPU context of rank `rank` (borrowed; owned by the cluster). */
+CHPIR_API int chpir_cluster_ctx(const chpir_cluster *cluster, int rank, chpir_ctx **ctx, int *device_ordinal);
+/* The slice plan, pure host arithmetic: rank r of n owns columns [*col_begin, +*col_count) of D / hint / response (sizes differ by
+ * at most one, earlier ranks take the remainder) and ingests words [*k_begin, +*k_count) of every query over its own PCIe link;
+ * *k_pitch (may be NULL) receives the padded slice length in words (a multiple of 32, the same on every rank). */
+CHPIR_API int chpir_cluster_plan(uint32_t n_ranks, uint32_t rank, uint64_t rows_k, uint32_t cols_n, uint32_t *col_begin, uint32_t *col_count,
+                                 uint64_t *k_begin, uint64_t *k_count, uint64_t *k_pitch);
+
+/* Server::setup on the cluster.  opts as for the single-GPU calls (col_begin / col_count / hint_on_device must be 0: the cluster
+ * slices; respond_coalesce is implied for n_gpus > 1; db_encode = DEVICE needs n_gpus = 1).  hint_out receives the COMPLETE
+ * wire-format hint (8 + 4 * lwe_rows * N bytes), byte-identical to a single-GPU setup: each rank computes its column slice and
+ * the slices are gathered on GPU 0 (NCCL by default, see CHPIR_CLUSTER_GATHER below) and downloaded once. */
+CHPIR_API int chpir_cluster_server_setup_from_db(chpir_cluster *cluster, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN],
+                                                 uint64_t db_entry_count, const uint8_t *key_blob, const uint64_t *key_offsets,
+                                                 const uint8_t *value_blob, const uint64_t *value_offsets, const uint64_t *filter_seed_rng,
+                                                 const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
+                                                 uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN], chpir_cluster_server **out);
+/* d_host: the whole K x N matrix in host memory; every rank uploads its own columns. */
+CHPIR_API int chpir_cluster_server_setup(chpir_cluster *cluster, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host,
+                                         uint64_t rows_k, uint32_t cols_n, uint32_t mat_elem_bit_len, const chpir_setup_opts *opts,
+                                         uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_cluster_server **out);
+/* d_slices[r]: rank r's columns as a compact K x col_count(r) u32 matrix already resident on rank r's GPU (synthetic D). */
+CHPIR_API int chpir_cluster_server_setup_device(chpir_cluster *cluster, const uint8_t seed[CHPIR_SEED_BYTE_LEN],
+                                                const uint32_t *const *d_slices, uint64_t rows_k, uint32_t cols_n, uint32_t mat_elem_bit_len,
+                                                const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
+                                                chpir_cluster_server **out);
+CHPIR_API void chpir_cluster_server_destroy(chpir_cluster_server *srv);
+/* Rank r's resident slice as a plain single-GPU server handle, borrowed (info, timing, save); do not destroy it. */
+CHPIR_API int chpir_cluster_server_shard(const chpir_cluster_server *srv, int rank, chpir_server **shard);
+/* One file per rank, `<path_prefix>.rank<r>of<n>` in chpir_server_save's format; load needs a cluster of the same size. */
+CHPIR_API int chpir_cluster_server_save(chpir_cluster_server *srv, const char *path_prefix);
+CHPIR_API int chpir_cluster_server_load(chpir_cluster *cluster, const char *path_prefix, const chpir_setup_opts *opts, chpir_cluster_server **out);
+
+/* Server::respond on the cluster: the same contract as chpir_server_respond (validation order, wire formats, thread-safe and
+ * re-entrant), N = all columns.  Concurrent callers are coalesced: each caller DMAs its query's K/n slices to the n GPUs itself,
+ * whoever arrives while the previous batch is on the GPUs shares one launch per GPU (GEMV for up to 5 queries, the tensor-core
+ * limb GEMM for 6..128 when batch_tc planes are resident). */
+CHPIR_API int chpir_cluster_server_respond(chpir_cluster_server *srv, const uint8_t *query, size_t query_len, uint8_t *resp_out,
+                                           size_t resp_cap, size_t *resp_len);
+CHPIR_API int chpir_cluster_server_respond_batch(chpir_cluster_server *srv, const uint8_t *const *queries, const size_t *query_lens,
+                                                 uint32_t nq, uint8_t *resp_out, size_t resp_stride);
+
+/* Device-resident respond (inputs already in the cluster's HBM): q_slices[r] = nq x k_pitch u32 on rank r's GPU holding words
+ * [k_begin(r), +k_count(r)) of every query -- exactly what the PCIe ingest above leaves behind -- and resp_device0 = nq x N u32 on
+ * rank 0's GPU.  mode CHPIR_RESPOND_GEMV: every query streams every rank's packed slice once (the HBM-bound path); mode
+ * CHPIR_RESPOND_TC: the limb GEMM, one pass over the byte planes per 128 queries.  `repeats` passes are enqueued back to back and
+ * the call returns when they have finished; *device_ms (may be NULL) receives the device time of all of them, measured with CUDA
+ * events on rank 0's GPU from before the first byte moves until the last rank's columns have landed in resp_device0. */
+#define CHPIR_RESPOND_GEMV 0u
+#define CHPIR_RESPOND_TC 1u
+CHPIR_API int chpir_cluster_server_respond_device(chpir_cluster_server *srv, const uint32_t *const *q_slices, uint32_t nq,
+                                                  uint32_t *resp_device0, uint32_t mode, uint32_t repeats, float *device_ms);
+
+typedef struct chpir_cluster_server_info {
+  uint32_t n_gpus;
+  uint32_t cols_n;  /* all columns */
+  uint64_t rows_k;
+  uint32_t mat_elem_bit_len;
+  uint32_t lwe_rows;
+  uint64_t k_pitch;               /* padded query-slice length (words) */
+  uint64_t packed_bytes_total;    /* resident packed bytes over all ranks = what one query streams in total */
+  uint64_t packed_bytes_max_rank; /* the largest rank's share (bounds the per-query time) */
+  double setup_total_s;           /* wall time of the whole cluster setup */
+  double hint_gather_s;           /* of which: gathering the hint slices + download */
+  uint32_t gather_uses_nccl;      /* 1 = the hint slices moved over NCCL, 0 = peer copies */
+  uint32_t nccl_version;          /* ncclGetVersion, 0 if NCCL was not needed */
+  /* coalescer statistics of chpir_cluster_server_respond since setup */
+  uint64_t batches, queries, tc_batches;
+} chpir_cluster_server_info;
+CHPIR_API int chpir_cluster_server_get_info(const chpir_cluster_server *srv, chpir_cluster_server_info *out);
+
 /* ---- client: chalametpir_client::Client (chalametpir_client/src/client.rs:21-283) with the public
  *      matrix A resident in HBM and b = s*A + e computed there.  Not on the server hot path; it lets a complete PIR round be run and
  *      checked at the full 2^20-entry shape. ------------------------------------------------------------------------------------ */
 typedef struct chpir_client chpir_client;
 typedef struct chpir_client_opts {
   uint32_t lwe_rows;        /* 0 = CHPIR_LWE_DIMENSION; must equal the hint's row count (else InvalidHintMatrix) */
-  uint32_t a_expand;        /* CHPIR_A_EXPAND_DEVICE / CHPIR_A_EXPAND_HOST_PIPELINED, as in chpir_setup_opts       */
+  uint32_t a_expand;        /* CHPIR_A_EXPAND_AUTO / _HOST_PIPELINED / _DEVICE, as in chpir_setup_opts             */
   uint32_t host_chunk_rows; /* as in chpir_setup_opts                                                              */
 } chpir_client_opts;
 typedef struct chpir_client_info {
@@ -268,8 +369,10 @@ typedef struct chpir_client_info {
 CHPIR_API int chpir_client_setup(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint8_t *hint, size_t hint_len,
                        const uint8_t *filter_params, size_t filter_params_len, const chpir_client_opts *opts, chpir_client **out);
 CHPIR_API void chpir_client_destroy(chpir_client *client);
-/* Client::query (client.rs:95-194): query_out receives the wire-format 1 x K query (8 + 4K bytes).  rng_seed NULL = OS entropy
- * (reference behaviour), otherwise a reproducible stream.  ArithmeticOverflowAddingQueryIndicator: retry (fresh randomness). */
+/* Client::query (client.rs:95-194): query_out receives the wire-format 1 x K query (8 + 4K bytes).  The LWE secret and error are
+ * drawn from ChaCha8 keyed by the OS (getrandom), as the reference's ChaCha8Rng::from_os_rng (matrix.rs:583); rng_seed != NULL
+ * replaces the OS key by a reproducible one and is a TEST-ONLY hook (queries made with it are not private).
+ * ArithmeticOverflowAddingQueryIndicator: retry (fresh randomness). */
 CHPIR_API int chpir_client_query(chpir_client *client, const uint8_t *key, size_t key_len, const uint64_t *rng_seed, uint8_t *query_out,
                        size_t query_cap, size_t *query_len);
 /* The same with the secret vector s (lwe_rows words) and the error vector e (K words) supplied: the deterministic core, used

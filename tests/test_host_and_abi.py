@@ -168,7 +168,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     from chalametpir_b200 import _lib as L
 
     pairs = {"chpir_setup_opts": L.SetupOpts, "chpir_setup_timing": L.SetupTiming, "chpir_server_info": L.ServerInfo,
-             "chpir_client_opts": L.ClientOpts, "chpir_client_info": L.ClientInfo}
+             "chpir_client_opts": L.ClientOpts, "chpir_client_info": L.ClientInfo, "chpir_cluster_server_info": L.ClusterServerInfo}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "chalamet_b200.h"', "int main(void) {"]
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
@@ -188,3 +188,41 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert got[(cname, "size")] == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+# ------------------------------------------------------------------ cluster: slice plan and no-GPU behaviour (csrc/cluster.cu)
+def test_cluster_plan_partitions_columns_and_query_words_exactly():
+    """chpir_cluster_plan: the column slices tile [0, N) in rank order with sizes differing by at most one (earlier ranks take the
+    remainder -- the same rule as sharding.slice_of), the query slices tile [0, K) with one padded pitch (a multiple of 32 words)."""
+    from chalametpir_b200 import sharding
+
+    for K, N in ((1, 1), (5, 7), (997, 33), (77824, 846), (303104, 846), (1179648, 940), (1130496, 940), (4718592, 940)):
+        for n in (1, 2, 3, 4, 8):
+            if N < n:
+                continue
+            plans = [cp.cluster_plan(n, r, K, N) for r in range(n)]
+            assert [(p["col_begin"], p["col_count"]) for p in plans] == [sharding.slice_of(N, r, n) for r in range(n)]
+            assert plans[0]["k_begin"] == 0 and plans[-1]["k_begin"] + plans[-1]["k_count"] == K
+            for a, b in zip(plans, plans[1:]):
+                assert a["k_begin"] + a["k_count"] == b["k_begin"]
+            pitch = {p["k_pitch"] for p in plans}
+            assert len(pitch) == 1 and pitch.pop() % 32 == 0
+            assert all(p["k_count"] <= p["k_pitch"] for p in plans)
+            assert all(p["k_begin"] == min(K, r * p["k_pitch"]) for r, p in enumerate(plans))
+
+
+def test_cluster_plan_rejects_bad_arguments():
+    for args in ((0, 0, 10, 10), (17, 0, 10, 10), (2, 2, 10, 10), (2, 0, 0, 10), (2, 0, 10, 0)):
+        with pytest.raises(cp.ChalametPIRError) as e:
+            cp.cluster_plan(*args)
+        assert e.value.variant == "InvalidArgument"
+
+
+def test_cluster_without_a_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.Cluster(n_gpus=2)
+    assert e.value.variant == "CudaDeviceNotFound"
