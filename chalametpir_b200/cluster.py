@@ -32,10 +32,28 @@ def cluster_plan(n_ranks: int, rank: int, rows_k: int, cols_n: int) -> dict:
     return {"col_begin": c0.value, "col_count": nc.value, "k_begin": k0.value, "k_count": kn.value, "k_pitch": ks.value}
 
 
+def _name_the_process_nccl() -> None:
+    """The dynamic loader keeps ONE instance per SONAME: whichever libnccl.so.2 is loaded first is the one every later user gets.
+    PyTorch ships its own (newer) NCCL and fails to import if an older system copy is already resident, so before the library
+    resolves NCCL (csrc/cluster.cu, dlopen at the first multi-GPU hint gather) point it at the copy a later ``import torch`` would
+    load -- $CHPIR_NCCL_LIB, honoured by the library; a no-op when the variable is set or no bundled copy exists."""
+    import os
+    import sys
+
+    if os.environ.get("CHPIR_NCCL_LIB"):
+        return
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["CHPIR_NCCL_LIB"] = cand
+            return
+
+
 class Cluster:
     """``n_gpus`` GPUs of this process with peer access between all of them (replaces gpu_utils::setup_gpu, gpu_utils.rs:25-79)."""
 
     def __init__(self, n_gpus: int = 0, devices: Optional[Sequence[int]] = None):
+        _name_the_process_nccl()
         h = C.c_void_p()
         if devices is not None:
             arr = (C.c_int * len(devices))(*devices)

@@ -57,7 +57,11 @@ NcclApi *nccl_api() {
     tried = true;
     // a copy the process already holds (e.g. the one a host framework loaded) wins over the system one: two NCCLs in one process
     // would each build their own topology and proxy threads
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    // (the loader shares one instance per SONAME, so the FIRST libnccl.so.2 a process loads is the one everybody gets: a host
+    // framework that ships its own NCCL must be given the chance to name it -- CHPIR_NCCL_LIB, set by chalametpir_b200/cluster.py)
+    void *h = nullptr;
+    if (const char *path = std::getenv("CHPIR_NCCL_LIB"); path && *path) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (h) {

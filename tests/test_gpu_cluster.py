@@ -164,7 +164,7 @@ def test_cluster_setup_from_db_pir_round(n, arity):
     assert hint == h1 and fbytes == f1
     b = O.find_mat_elem_bit_len(len(db))
     D, fo = O.from_kv_database(db, b, arity, rng_seed=21)
-    assert fbytes == fo
+    assert fbytes == fo.to_bytes()
     assert hint == O.Server.setup_from_matrix(SEED, D, b, lwe_rows=200)[1]
     client = O.Client.setup(SEED, hint, fbytes, lwe_rows=200)
     done = 0
