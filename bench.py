@@ -8,31 +8,34 @@ Workload (BASELINE.json configs[2], the configuration `metric` is quoted on): 2^
 3-wise XOR binary fuse filter  ->  D is K x N = 1 179 648 x 940 with 9-bit entries, LWE dimension 1774.
 D is synthetic (uniform 9-bit entries from a counter hash, generated directly in HBM; SURVEY.md section 8d "synthetic-D").
 
-A "step" is one pass of Server::respond over a batch of `--queries-per-step` independent queries: every query streams
-the whole resident D once (single-query GEMV, the reference's `server_respond`).  `value` is whole-job queries/s with
-queries already resident in HBM; `e2e` is the same metric through the C ABI call `chpir_server_respond` with HOST
-buffers (pinned), H2D of each query and D2H of each response inside the timed region.
-`Server::setup` (A expansion + hint GEMM + pack) runs once before the timed steps and is reported under "setup".
+A "step" is one pass of Server::respond over a batch of `--queries-per-step` independent queries: every query streams the whole
+resident D once (single-query GEMV, the reference's `server_respond`).  `value` is whole-job queries/s with the queries already
+resident in HBM; `e2e` is the same metric through the C ABI call the reference's `Server::respond` would bind
+(`chpir_cluster_server_respond`) with HOST buffers (pinned), H2D of each query and D2H of each response inside the timed region,
+called by concurrent native threads as the reference's example server does with one task per connection.
 
-With N > 1 the columns of D (and so of the hint and of every response) are sliced across the ranks; per step rank 0
-broadcasts the query batch over NCCL, every rank answers for its slice, and the response slices are gathered on rank 0.
-The database is the same size at every N, so `scaling` is "strong".
+N > 1: the server is ONE process driving N GPUs (chpir_cluster_*, csrc/cluster.cu) -- the reference's `Server::respond(&self, &[u8])`
+has no room for a rank argument, so the column sharding lives behind the handle.  Under torchrun every rank joins the process
+group (NCCL for the communicator, gloo for the CPU-side barriers around the timed regions); rank 0 is the server process and owns all N
+GPUs, ranks 1..N-1 hold no data and wait at the barriers.  Columns of D (and so of the hint and of every response) are sliced across
+the GPUs; queries are resident K-sliced over the GPUs exactly as the PCIe ingest leaves them and are all-gathered over NVLink by the
+copy engines; every GPU answers for its columns; the columns land in GPU 0's row-major result by strided peer copies.  The
+database is the same size at every N, so `scaling` is "strong".
 
-`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on the same
-workload; the Rust reference itself cannot be built in this image (no cargo/rustc), see DESIGN.md.
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on the same workload at FULL
+size; the Rust reference itself cannot be built in this image (no cargo/rustc), see DESIGN.md.
 """
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
-NO_BCAST = bool(os.environ.get("CHPIR_BENCH_NO_BCAST"))
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -44,15 +47,26 @@ LWE = 1774
 VALUE_BYTES = 1024
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 FALLBACK_BF16_TFLOPS = 1590.0
-
+PUBLISHED = {"server_respond_2^20_3wise_ms": {"m8g.8xlarge": 10.06, "m7i.8xlarge": 14.06},
+             "server_setup_2^20_3wise_s": {"m8g": 577, "m7i": 1282, "g6e(L40S offload)": 25.58}}
 
 _JSON_OUT = None
 
 
+def _jsonable(o):
+    if isinstance(o, np.generic):
+        return o.item()
+    raise TypeError(f"not JSON serialisable: {type(o).__name__}")
+
+
 def emit(line: dict) -> None:
     out = _JSON_OUT or sys.stdout
-    out.write(json.dumps(line) + "\n")
+    out.write(json.dumps(line, default=_jsonable) + "\n")
     out.flush()
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
 
 
 def shape_of(log2n: int, arity: int, use_oracle: bool = False):
@@ -77,20 +91,15 @@ def peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", FALLBACK_BF16_TFLOPS)), "source": "measured"}
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", FALLBACK_BF16_TFLOPS)),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", FALLBACK_BF16_TFLOPS))), "source": "measured"}
         except Exception:
             pass
-    return {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": FALLBACK_BF16_TFLOPS, "source": "fallback"}
-
-
-def slice_of(N: int, rank: int, world: int):
-    from chalametpir_b200.sharding import slice_of as f
-
-    return f(N, rank, world)
+    return {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": FALLBACK_BF16_TFLOPS, "bf16_tflops_sustained": FALLBACK_BF16_TFLOPS, "source": "fallback"}
 
 
 def gen_d_slice(torch, K: int, c0: int, nc: int, b: int, device, salt: int = 0x5EED):
-    """D[k][n] = hash(k, n) mod 2^b for n in [c0, c0+nc): every rank derives its own slice of the same matrix."""
+    """D[k][n] = hash(k, n) mod 2^b for n in [c0, c0+nc): every rank's slice of the same matrix, generated where it will live."""
     D = torch.empty((K, nc), dtype=torch.int32, device=device)
     cols = torch.arange(c0, c0 + nc, device=device, dtype=torch.int64)
     M32 = 0xFFFFFFFF
@@ -153,40 +162,77 @@ class ClockSampler:
                     reasons.add(nme)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # samples taken while the GPU was busy: the upper half of the clock readings
-        busy = sorted(sm)[len(sm) // 2 :]
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w": round(statistics.median(pw), 1), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        busy = sorted(sm)[len(sm) // 2:]  # samples taken while the GPU was busy: the upper half of the clock readings
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w": round(statistics.median(pw), 1), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def host_d(K: int, N: int, b: int, seed: int = 1234):
-    rng = np.random.default_rng(seed)
-    return rng.integers(0, 1 << b, size=(K, N), dtype=np.uint16).astype(np.uint32)
+def use_all_host_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is the reference's rayon pool = one thread per hardware thread.
+    Must run before the oracle library (libgomp) is loaded."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return n
 
 
-def cpu_respond_qps(K_full: int, N: int, b: int, frac: int, iters: int, min_iters: int = 3):
-    """Oracle (CPU restatement of Server::respond, matrix.rs:328-485) on a 1/frac row sample of the workload.
-    Respond is linear in K, so queries/s at full size = measured / frac."""
+def oracle_with_all_cores(want: int):
+    """The oracle module with its OpenMP pool sized to every usable host cpu (also when libgomp was loaded earlier by someone else)."""
     from oracle import oracle as O
 
-    Ks = max(3, K_full // frac)
-    D = host_d(Ks, N, b)
+    O.set_num_threads(want)
+    return O
+
+
+def host_d(K: int, N: int, b: int, seed: int = 1234):
+    rng = np.random.default_rng(seed)
+    D = np.empty((K, N), dtype=np.uint32)
+    step = 1 << 16
+    for r0 in range(0, K, step):  # chunked: no 2-byte temporary of the whole matrix
+        r1 = min(K, r0 + step)
+        D[r0:r1] = rng.integers(0, 1 << b, size=(r1 - r0, N), dtype=np.uint16)
+    return D
+
+
+def cpu_server(K: int, N: int, b: int):
+    """The CPU restatement of the reference's Server (transposed, row_wise_compress'ed D resident in host memory) at FULL size."""
+    from oracle import oracle as O
+
+    D = host_d(K, N, b)
     srv, _ = O.Server.setup_from_matrix(SEED_MU, D, b, want_hint=False)
     del D
-    rng = np.random.default_rng(99)
-    q = rng.integers(0, 2**32, size=Ks, dtype=np.uint64).astype(np.uint32)
-    qb = O.matrix_to_bytes(q.reshape(1, -1))
-    srv.respond(qb)
+    return srv
+
+
+def cpu_queries(K: int, n: int, seed: int):
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(seed)
+    return [O.matrix_to_bytes(rng.integers(0, 2**32, size=K, dtype=np.uint64).astype(np.uint32).reshape(1, -1)) for _ in range(n)]
+
+
+def cpu_respond_baseline(K: int, N: int, b: int, n_queries: int, want_threads: int):
+    """Oracle (CPU restatement of Server::respond, matrix.rs:328-485) on the FULL database, a bounded number of queries."""
+    O = oracle_with_all_cores(want_threads)
+    srv = cpu_server(K, N, b)
+    qs = cpu_queries(K, 4, 99)
+    for q in qs[:2]:
+        srv.respond(q)
     times = []
-    for _ in range(max(iters, min_iters)):
+    for i in range(n_queries):
         t = time.perf_counter()
-        srv.respond(qb)
+        srv.respond(qs[i % len(qs)])
         times.append(time.perf_counter() - t)
-    t_med = statistics.median(times)
-    scale = K_full / Ks
-    return {"qps_full": 1.0 / (t_med * scale), "ms_sample": t_med * 1e3, "rows_sample": Ks, "threads": O.num_threads(), "times": times,
-            "scale": scale}
+    threads = O.num_threads()
+    return {"value": 1.0 / statistics.median(times), "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"full database (K={K}, N={N}, reference layout: transposed + row_wise_compress'ed in host memory), {n_queries} single-query responds, "
+                      f"median {statistics.median(times) * 1e3:.2f} ms (min {min(times) * 1e3:.2f}); OpenMP threads={threads} of {want_threads} usable cpus",
+            "threads_expected": want_threads}
 
 
 def cpu_setup_extrapolated(K_full: int, N: int, b: int, frac: int, a_rows: int = 4):
@@ -219,38 +265,34 @@ def cpu_setup_extrapolated(K_full: int, N: int, b: int, frac: int, a_rows: int =
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the reference's Server::respond on the host cores (rank 0 only)."""
+    """--impl reference: the CPU restatement of the reference's Server::respond on ALL host cores, full database (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    want = use_all_host_cores()
     b, K, N = shape_of(args.log2n, args.arity, use_oracle=True)
-    frac = args.ref_sample_frac
-    from oracle import oracle as O
-
-    Ks = K // frac
-    D = host_d(Ks, N, b)
-    srv, _ = O.Server.setup_from_matrix(SEED_MU, D, b, want_hint=False)
-    del D
-    rng = np.random.default_rng(5)
-    qs = [O.matrix_to_bytes(rng.integers(0, 2**32, size=Ks, dtype=np.uint64).astype(np.uint32).reshape(1, -1)) for _ in range(args.queries_per_step)]
-    for _ in range(args.warmup):
-        for qb in qs[: max(1, args.queries_per_step // 4)]:
+    O = oracle_with_all_cores(want)
+    threads = O.num_threads()
+    assert threads == want, f"the CPU arm must use every host core: OpenMP has {threads} threads, {want} cpus are usable"
+    srv = cpu_server(K, N, b)
+    sample_q = max(1, min(args.ref_queries_per_step, args.queries_per_step))
+    qs = cpu_queries(K, sample_q, 5)
+    for _ in range(max(1, args.warmup)):
+        for qb in qs[: max(1, sample_q // 4)]:
             srv.respond(qb)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for qb in qs:
             srv.respond(qb)
     dt = time.perf_counter() - t0
-    scale = K / Ks
-    nq = args.steps * args.queries_per_step
-    qps = nq / (dt * scale)
-    threads = O.num_threads()
-    sample = (f"rows [0,{Ks}) of K={K} (1/{frac} of the database, all {N} columns); respond is linear in K, queries/s scaled by {scale:.3f}; "
-              f"{nq} queries; OpenMP threads={threads}")
+    nq = args.steps * sample_q
+    qps = nq / dt
+    sample = (f"full database (K={K}, N={N}); each step answers a {sample_q}-query sample of the {args.queries_per_step}-query step, one query at a time "
+              f"(the reference's server_respond); {nq} queries in {dt:.2f} s, measured, nothing extrapolated; OpenMP threads={threads} = all usable host cpus")
     line = {
         "impl": "reference", "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * scale, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "ms_per_step_covers_queries": sample_q, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, b, K, N),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -266,75 +308,130 @@ def workload_config(args, b, K, N):
                     {(16, 3): "configs[0]", (18, 3): "configs[1]", (20, 3): "configs[2]", (20, 4): "configs[3] shape", (22, 3): "configs[4]"}.get(
                         (args.log2n, args.arity), "shape outside configs") + ")",
         "K": K, "N": N, "mat_elem_bit_len": b, "lwe_dimension": LWE, "queries_per_step": args.queries_per_step,
-        "sharding": f"columns/{args.gpus}" if args.gpus > 1 else "none",
-        "l2": "inputs larger than L2 (resident packed D per GPU >> 126 MB at N<=4; every query streams all of it)",
+        "sharding": f"columns/{args.gpus}, one process, chpir_cluster_* (csrc/cluster.cu)" if args.gpus > 1 else "none (cluster of one GPU)",
+        "l2": "inputs larger than L2 (every query streams the resident packed D: 1.28 GB / n_gpus per GPU vs 126 MB of L2)",
     }
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+# ------------------------------------------------------------------------------------------------ GPU arm helpers
+class Ranks:
+    """torchrun plumbing: NCCL group (communicator of `world` ranks), gloo group for CPU-side barriers that do not occupy any GPU."""
 
-    import chalametpir_b200 as cp
+    def __init__(self, args):
+        import torch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE is 1)")
-        args.gpus = world
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    pg_out = None
-    if world > 1:
-        # NCCL's kernels run on a high-priority stream: the respond kernel fills every SM (one 175 KB-smem CTA each), and without
-        # priority the query broadcast of the next batch only gets SMs once the current batch has drained (no overlap)
-        pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-        if os.environ.get("CHPIR_NCCL_MAX_CTAS"):  # experiment knob: fewer NCCL CTAs leave more SMs to the respond kernel
-            pg_opts.config.max_ctas = int(os.environ["CHPIR_NCCL_MAX_CTAS"])
-        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
-        # A second communicator for the response gathers.  Collectives of one communicator run in issue order on one stream, and the
-        # gather of batch i-1 cannot finish before the SLOWEST rank has answered batch i-1; with a single communicator the query
-        # broadcast of batch i+1 sat behind it and started ~330 us late, leaving an ~85 us hole in front of every respond launch
-        # (timeline in profiles/r1_n8_timeline.txt).  CHPIR_BENCH_ONE_COMM=1 restores the single communicator.
-        if not os.environ.get("CHPIR_BENCH_ONE_COMM"):
-            pg_out_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            pg_out = dist.new_group(backend="nccl", pg_options=pg_out_opts)
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.cpu_pg = None
+        if self.world > 1:
+            import torch.distributed as dist
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            self.dist = dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank), timeout=datetime.timedelta(hours=1))
+            self.cpu_pg = dist.new_group(backend="gloo", timeout=datetime.timedelta(hours=1))
+            t = torch.ones(1, device=f"cuda:{self.local_rank}")
+            dist.all_reduce(t)  # every rank joins at once: the NCCL communicator exists, nobody spins on a GPU waiting for rank 0
+            torch.cuda.synchronize()
+            assert int(t.item()) == self.world
 
-    b, K, N = shape_of(args.log2n, args.arity)
-    c0, nc = slice_of(N, rank, world)
-    Q = args.queries_per_step
+    def barrier(self):
+        """CPU-side barrier (gloo): ranks 1..N-1 block in the kernel, not in a spinning NCCL kernel on their GPU."""
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_pg)
 
-    # ---------------- Server::setup on this rank's column slice (one-off; reported, not part of the timed steps)
-    D = gen_d_slice(torch, K, c0, nc, b, dev)
-    torch.cuda.synchronize()
+    def max_over_ranks(self, values):
+        if self.dist is None:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+N_SYNC_POINTS = 6  # barriers rank 0 passes in run_b200; ranks 1..N-1 pass the same number
+
+
+def sync_devices(torch, devices):
+    for d in devices:
+        torch.cuda.synchronize(d)
+
+
+def exact_columns(torch, q_row_dev, D_cols):
+    """q . D[:, cols] mod 2^32, exact: 16-bit halves of q times entries < 2^14 over K <= 2^23 rows stay below 2^53 in float64."""
+    q = q_row_dev.to(torch.int64) & 0xFFFFFFFF
+    lo, hi = (q & 0xFFFF).double(), (q >> 16).double()
+    Dd = D_cols.double()
+    a = (lo @ Dd).to(torch.int64)
+    c = (hi @ Dd).to(torch.int64)
+    return ((a + ((c & 0xFFFF) << 16)) & 0xFFFFFFFF).cpu().numpy().astype(np.uint64)
+
+
+def make_cluster_server(cp, torch, cluster, log2n, arity, skip_hint, keep_d=False, **opts):
+    """Synthetic D of the named shape, generated slice by slice on the GPU that will own it, then Server::setup on the cluster."""
+    b, K, N = shape_of(log2n, arity)
+    n = cluster.n_gpus
+    plans = [cp.cluster_plan(n, r, K, N) for r in range(n)]
+    Ds = [gen_d_slice(torch, K, p["col_begin"], p["col_count"], b, f"cuda:{cluster.devices[r]}") for r, p in enumerate(plans)]
+    sync_devices(torch, cluster.devices)
     t0 = time.perf_counter()
-    srv, hint = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, skip_hint=args.skip_hint,
-                                                   batch_tc=0 if args.no_batch_tc else 1, a_expand="host" if args.a_expand == "host" else "device",
-                                                   respond_coalesce=not args.no_coalesce)
-    setup_wall = time.perf_counter() - t0
-    tm = srv.setup_timing()
-    km = srv.last_kernel_ms()
-    setup = {"a_expand": "host" if args.a_expand == "host" else "device", "wall_s": setup_wall, **{k: round(v, 6) for k, v in tm.items()}, "gemm_kernel_ms": km["gemm_ms"], "skipped_hint": bool(args.skip_hint)}
-    if not args.skip_hint:
-        # tensor roofline of the hint GEMM: issued int8 ops = limb pairs x 2 x padded M x K x padded N, summed over the 128-row panels
-        nlimb = 7 if b > 8 else 4
-        m_pad, n_pad = -(-LWE // 128) * 128, -(-nc // 128) * 128 if nc > 128 else -(-nc // 16) * 16
-        issued = nlimb * 2 * m_pad * K * n_pad
-        useful = nlimb * 2 * LWE * K * nc
-        # MEASURED_PEAKS.json has no int8 figure: measure the library's dense int8 GEMM here (cuBLASLt through torch._int_mm, 8192^3,
-        # best of 10 -- 3.15 POP/s on the round-1 box, tools/int8_peak.py); fall back to 2 x the measured bf16 figure
-        int8_peak, int8_src = 2.0 * peaks()["bf16_tflops"], f"2 x bf16_tflops ({peaks()['source']})"
-        try:
+    srv, hint = cp.ClusterServer.setup_from_device_slices(cluster, SEED_MU, [d.data_ptr() for d in Ds], K, N, b, skip_hint=skip_hint, **opts)
+    wall = time.perf_counter() - t0
+    if not keep_d:
+        Ds = None
+        for d in cluster.devices:
+            with torch.cuda.device(d):
+                torch.cuda.empty_cache()
+    return srv, hint, Ds, plans, (b, K, N), wall
+
+
+def make_query_slices(torch, cluster, plans, K, ks, nq, seed, keep_full_rows=0):
+    """nq uniform u32 queries, resident K-sliced over the GPUs as the PCIe ingest would leave them; returns (slices, first rows on GPU 0)."""
+    dev0 = f"cuda:{cluster.devices[0]}"
+    g = torch.Generator(device=dev0)
+    g.manual_seed(seed)
+    slices = [torch.zeros((nq, ks), dtype=torch.int32, device=f"cuda:{cluster.devices[r]}") for r in range(cluster.n_gpus)]
+    head = torch.empty((min(keep_full_rows, nq), K), dtype=torch.int32, device=dev0) if keep_full_rows else None
+    step = 32
+    for r0 in range(0, nq, step):
+        r1 = min(nq, r0 + step)
+        q = torch.randint(-(2**31), 2**31, (r1 - r0, K), dtype=torch.int32, device=dev0, generator=g)
+        for r, p in enumerate(plans):
+            if p["k_count"]:
+                slices[r][r0:r1, : p["k_count"]] = q[:, p["k_begin"]: p["k_begin"] + p["k_count"]].to(slices[r].device)
+        if head is not None and r0 < head.shape[0]:
+            head[r0: min(r1, head.shape[0])] = q[: min(r1, head.shape[0]) - r0]
+    sync_devices(torch, cluster.devices)
+    return slices, head
+
+
+def check_against_exact(torch, cluster, plans, Ds, q_rows_dev0, out_rows_dev0, n_rows, cols_per_rank=3):
+    """Rows of the gathered (nq x N) result on GPU 0 against exact dot products on columns drawn from EVERY rank's slice."""
+    ok = True
+    for r, p in enumerate(plans):
+        nc = p["col_count"]
+        local = sorted({0, nc // 2, nc - 1})[:cols_per_rank]
+        Dc = Ds[r][:, local]
+        for i in range(n_rows):
+            want = exact_columns(torch, q_rows_dev0[i].to(Dc.device), Dc)
+            got = out_rows_dev0[i].cpu().numpy().view(np.uint32)[[p["col_begin"] + c for c in local]].astype(np.uint64)
+            ok = ok and bool(np.array_equal(got, want))
+    return ok
+
+
+def int8_peak_live(torch, dev):
+    """MEASURED_PEAKS.json has no int8 figure: measure the library's dense int8 GEMM here (cuBLASLt through torch._int_mm, 8192^3, best of
+    10); fall back to 2 x the measured bf16 figure."""
+    pk = peaks()
+    peak, src = 2.0 * pk["bf16_tflops"], f"2 x bf16_tflops ({pk['source']})"
+    try:
+        with torch.cuda.device(dev):
             ia = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device=dev)
             ib = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device=dev)
             for _ in range(3):
@@ -347,71 +444,140 @@ def run_b200(args):
                 i1.record()
                 torch.cuda.synchronize()
                 best = min(best, i0.elapsed_time(i1))
-            int8_peak, int8_src = 2 * 8192**3 / best / 1e9, "measured live: torch._int_mm 8192^3 (cuBLASLt int8), best of 10"
-            del ia, ib
-        except Exception:  # no int8 GEMM in this torch build: keep the fallback
-            pass
-        gs = km["gemm_ms"] * 1e-3
-        setup["gemm_roofline"] = {
-            "bound": "tensor", "kernel": "gemm_tc_kernel<2> (tcgen05 kind::i8 limb GEMM, 14 panel launches)", "achieved": issued / gs / 1e12, "useful": useful / gs / 1e12,
-            "peak": int8_peak, "peak_source": int8_src, "unit": "TOP/s", "frac": issued / gs / 1e12 / int8_peak,
-            "u32_mac_equivalent_tmacs": LWE * K * nc / gs / 1e12,
-        }
-        setup["xof_ns_per_permutation"] = tm["expand_a_s"] / (LWE * K * 4 / 168.0) * 1e9
-    # the same setup with the XOF chain walked by a host core and uploads + panel GEMMs pipelined behind it (a_expand = "host"):
-    # byte-identical hint, several times lower latency (the chain is serial; a CPU core runs it faster than a GPU warp)
-    if not args.skip_hint and args.a_expand == "both":
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        srv_h, hint_h = cp.Server.setup_from_device_matrix(SEED_MU, D.data_ptr(), K, nc, b, device=local_rank, batch_tc=2, a_expand="host")
-        wall_h = time.perf_counter() - t0
-        th = srv_h.setup_timing()
-        setup["host_pipelined"] = {"wall_s": wall_h, **{k: round(v, 6) for k, v in th.items()}, "gemm_kernel_ms": srv_h.last_kernel_ms()["gemm_ms"],
-                                   "xof_impl": cp.host_xof_impl(), "xof_ns_per_permutation": th["xof_host_busy_s"] / (LWE * K * 4 / 168.0) * 1e9,
-                                   "hint_identical_to_device_mode": bool(hint_h == hint)}
-        assert hint_h == hint, "host-pipelined setup produced a different hint"
-        del srv_h, hint_h
-    # the complete Server::setup(seed, db) (server.rs:103) from raw keys and values: host filter construction + row encoding,
-    # D upload, pack, A expansion (host-pipelined, started beside the encode phase), hint GEMM, hint download
-    if args.e2e_setup and world == 1 and not args.skip_hint:
+            peak, src = 2 * 8192**3 / best / 1e9, "measured live: torch._int_mm 8192^3 (cuBLASLt int8), best of 10"
+    except Exception:
+        pass
+    return peak, src
+
+
+def rank_timing(srv, n):
+    infos = [srv.shard_info(r) for r in range(n)]
+    tmax = {k: max(i["timing"][k] for i in infos) for k in infos[0]["timing"]}
+    return infos, tmax
+
+
+def batched_leg(cp, torch, cluster, srv, plans, K, N, b, BQ, iters, seed, Ds=None, label=""):
+    """Batched respond on the tensor cores (north_star (2)): BQ device-resident queries, one pass over every rank's byte planes."""
+    slices, head = make_query_slices(torch, cluster, plans, K, srv.k_pitch, BQ, seed, keep_full_rows=2)
+    dev0 = f"cuda:{cluster.devices[0]}"
+    out_tc = torch.zeros((BQ, N), dtype=torch.int32, device=dev0)
+    out_gv = torch.zeros((BQ, N), dtype=torch.int32, device=dev0)
+    ptrs = [s.data_ptr() for s in slices]
+    srv.respond_device(ptrs, BQ, out_tc.data_ptr(), mode=cp.RESPOND_TC, repeats=2)  # warm-up
+    nchk = min(BQ, 8)
+    srv.respond_device(ptrs, nchk, out_gv.data_ptr(), mode=cp.RESPOND_GEMV, repeats=1)
+    sync_devices(torch, cluster.devices)
+    parity = {"tc_equals_gemv": bool(torch.equal(out_tc[:nchk], out_gv[:nchk]))}
+    if Ds is not None:
+        parity["tc_equals_exact_on_columns_of_every_rank"] = check_against_exact(torch, cluster, plans, Ds, head, out_tc, 2)
+    ms = srv.respond_device(ptrs, BQ, out_tc.data_ptr(), mode=cp.RESPOND_TC, repeats=iters) / iters
+    nlimb = 7 if b > 8 else 4
+    tiles = -(-BQ // 128)
+    issued = sum(nlimb * 2 * 128 * K * (-(-p["col_count"] // 16) * 16 if p["col_count"] <= 128 else -(-p["col_count"] // 128) * 128) for p in plans) * tiles
+    plane_bytes = sum((2 if b > 8 else 1) * K * p["col_count"] for p in plans) * tiles
+    return {"label": label, "queries_per_batch": BQ, "ms_per_batch": ms, "queries_per_s": BQ / (ms * 1e-3),
+            "includes": "NVLink gather of the K-sliced queries fused with the limb split, int8-limb GEMM on every rank, strided peer copy of the columns to GPU 0",
+            "issued_int8_tops_all_gpus": issued / (ms * 1e-3) / 1e12, "d_plane_bytes_streamed_per_batch_all_gpus": plane_bytes,
+            "d_plane_gbs_per_gpu": plane_bytes / cluster.n_gpus / (ms * 1e-3) / 1e9, "parity": parity}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+
+    R = Ranks(args)
+    world, rank = R.world, R.rank
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1:
+        args.gpus = world
+    if rank != 0:
+        # the server is ONE process (rank 0) that owns every GPU; this rank holds no data and only keeps the barriers' count
+        for _ in range(N_SYNC_POINTS):
+            R.barrier()
+        R.max_over_ranks([0.0, 0.0, 0.0])
+        R.close()
+        return
+    n_gpus = args.gpus
+    if torch.cuda.device_count() < n_gpus:
+        raise SystemExit(f"--gpus {n_gpus}: only {torch.cuda.device_count()} CUDA devices are visible")
+    want_cpus = use_all_host_cores()  # for the cpu_baseline leg (libgomp reads it when the oracle is loaded)
+
+    import chalametpir_b200 as cp
+
+    cluster = cp.Cluster(n_gpus=n_gpus)
+    devices = cluster.devices
+    dev0 = f"cuda:{devices[0]}"
+    torch.cuda.set_device(devices[0])
+    Q = args.queries_per_step
+    parity = {}
+
+    # ---------------- Server::setup on the cluster (one-off; reported, not part of the timed steps)
+    a_expand = {"host": "host", "device": "device", "auto": "auto"}[args.a_expand]
+    srv, hint, Ds, plans, (b, K, N), setup_wall = make_cluster_server(cp, torch, cluster, args.log2n, args.arity, args.skip_hint, keep_d=True, batch_tc=1,
+                                                                     a_expand=a_expand, respond_coalesce=True)
+    info = srv.get_info()
+    shard_infos, tmax = rank_timing(srv, n_gpus)
+    setup = {"api": "chpir_cluster_server_setup_device (D synthetic, generated in HBM slice by slice)", "a_expand": a_expand, "wall_s": setup_wall,
+             **{k: round(v, 6) for k, v in tmax.items()}, "timing_is": "max over ranks of each phase", "gemm_kernel_ms": max(i["gemm_ms"] for i in shard_infos),
+             "hint_gather_s": info["hint_gather_s"], "hint_gather_uses_nccl": bool(info["gather_uses_nccl"]), "nccl_version": info["nccl_version"],
+             "skipped_hint": bool(args.skip_hint), "xof_impl": cp.host_xof_impl()}
+    if not args.skip_hint:
+        # tensor roofline of the hint GEMM on rank 0: issued int8 ops = limb pairs x 2 x padded M x K x padded N, summed over the 128-row panels
+        nc0 = plans[0]["col_count"]
+        nlimb = 7 if b > 8 else 4
+        m_pad = -(-LWE // 128) * 128
+        n_pad = -(-nc0 // 128) * 128 if nc0 > 128 else -(-nc0 // 16) * 16
+        issued, useful = nlimb * 2 * m_pad * K * n_pad, nlimb * 2 * LWE * K * nc0
+        int8_peak, int8_src = int8_peak_live(torch, dev0)
+        gs = shard_infos[0]["gemm_ms"] * 1e-3
+        setup["gemm_roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::i8 limb GEMM, 14 panel launches, rank 0's column slice)",
+                                  "achieved": issued / gs / 1e12, "useful": useful / gs / 1e12, "peak": int8_peak, "peak_source": int8_src, "unit": "TOP/s",
+                                  "frac": issued / gs / 1e12 / int8_peak, "u32_mac_equivalent_tmacs": LWE * K * nc0 / gs / 1e12}
+        busy = tmax["xof_host_busy_s"] if tmax["xof_host_busy_s"] > 0 else tmax["expand_a_s"]
+        setup["xof_ns_per_permutation"] = busy / (LWE * K * 4 / 168.0) * 1e9
+        # hint parity: rows 0..1 of the GATHERED hint against exact products with the head of the XOF stream, on columns of every rank
+        from oracle import oracle as O
+
+        a0 = torch.from_numpy(O.generate_rows_from_seed(K, SEED_MU, 0, 2).view(np.int32).copy()).to(dev0)
+        H = np.frombuffer(hint, dtype="<u4")
+        assert H[0] == LWE and H[1] == N and len(hint) == 8 + 4 * LWE * N, "hint header / length"
+        Hd = torch.from_numpy(H[2: 2 + 2 * N].view(np.int32).reshape(2, N).copy()).to(dev0)
+        parity["hint_rows_0_1_on_columns_of_every_rank"] = check_against_exact(torch, cluster, plans, Ds, a0, Hd, 2)
+        assert parity["hint_rows_0_1_on_columns_of_every_rank"], "gathered hint differs from the exact product"
+        del a0, Hd
+    R.barrier()  # sync point 1: setup done
+
+    # ---------------- Server::setup(seed, db) from raw keys and values (server.rs:103) + a complete PIR round
+    if args.e2e_setup and not args.skip_hint:
         n_db = 1 << args.log2n
         rs = np.random.default_rng(2024)
         keys = rs.integers(0, 256, size=(n_db, 32), dtype=np.uint8)
         keys[:, :8] = np.arange(n_db, dtype="<u8").view(np.uint8).reshape(n_db, 8)  # distinct by construction
         vals = rs.integers(0, 256, size=(n_db, VALUE_BYTES), dtype=np.uint8)
-        torch.cuda.synchronize()
+        sync_devices(torch, devices)
         t0 = time.perf_counter()
-        srv_e, hint_e, fb_e = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=7, batch_tc=2, a_expand="host")
+        srv_e, hint_e, fb_e = cp.ClusterServer.setup_from_arrays(cluster, SEED_MU, keys, vals, args.arity, filter_seed_rng=7, batch_tc=2, a_cache=True)
         wall_e = time.perf_counter() - t0
-        te = srv_e.setup_timing()
-        # the same with the row encoding + dependent fill on the GPU (values uploaded instead of D): identical hint and filter bytes
-        del srv_e
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        srv_g, hint_g, fb_g = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=7, batch_tc=2, a_expand="host",
-                                                          db_encode="device", a_cache=True)
-        wall_g = time.perf_counter() - t0
-        tg = srv_g.setup_timing()
-        assert hint_g == hint_e and fb_g == fb_e, "device row fill changed the hint or the filter parameters"
-        # a database UPDATE: same seed, same keys, new values.  A depends on (seed, K) only and was left resident in HBM by the
-        # setup above (a_cache), so this Server::setup runs no XOF chain: filter + row fill + pack + the tensor-core hint GEMM.
-        # Its hint is checked end to end below: the client set up from it recovers the NEW values.
-        del srv_g
+        _, te = rank_timing(srv_e, n_gpus)
+        ie = srv_e.get_info()
+        # a database UPDATE: same seed and keys, new values.  A depends on (seed, K) only and was left resident on every GPU (a_cache),
+        # so this Server::setup walks no XOF chain.  The PIR round below runs against THIS server and hint.
+        srv_e.close()
         vals = vals[::-1].copy()
-        torch.cuda.synchronize()
+        sync_devices(torch, devices)
         t0 = time.perf_counter()
-        srv_g, hint_g, fb_g = cp.Server.setup_from_arrays(SEED_MU, keys, vals, args.arity, device=local_rank, filter_seed_rng=8, batch_tc=2, a_expand="host",
-                                                          db_encode="device", a_cache=True)
+        srv_u, hint_u, fb_u = cp.ClusterServer.setup_from_arrays(cluster, SEED_MU, keys, vals, args.arity, filter_seed_rng=8, batch_tc=2, a_cache=True,
+                                                                 db_encode="device" if n_gpus == 1 else "host")
         wall_u = time.perf_counter() - t0
-        tu = srv_g.setup_timing()
+        _, tu = rank_timing(srv_u, n_gpus)
         assert tu["a_cache_hit"] == 1.0
-        cached_a_bytes = cp.drop_a_cache(local_rank)
-        # a complete PIR round on this real database: GPU client (A resident in HBM) -> Server::respond -> recover the value
+        cached = cluster.drop_a_cache()
         t0 = time.perf_counter()
-        client = cp.Client.setup(SEED_MU, hint_g, fb_g, device=local_rank, a_expand="host")
+        client = cp.Client.setup(SEED_MU, hint_u, fb_u, device=devices[0], a_expand="host")
         client_setup_s = time.perf_counter() - t0
         rounds, q_ms = 0, []
-        for j, i in enumerate([0, 1, n_db // 3, n_db // 2, n_db - 1, 777_777]):
+        for j, i in enumerate([0, 1, n_db // 3, n_db // 2, n_db - 1, 777_777 % n_db]):
             key = keys[i].tobytes()
             try:
                 t0 = time.perf_counter()
@@ -421,423 +587,279 @@ def run_b200(args):
                 if ex.variant != "ArithmeticOverflowAddingQueryIndicator":
                     raise
                 continue
-            assert client.process_response(key, srv_g.respond(qb)) == vals[i].tobytes(), "PIR round failed to recover the value"
+            assert client.process_response(key, srv_u.respond(qb)) == vals[i].tobytes(), "PIR round failed to recover the value"
             rounds += 1
         ci = client.info()
-        pir_round = {"values_recovered": rounds, "client_setup_s": client_setup_s, "client_query_ms_wall": statistics.median(q_ms),
-                     "client_query_kernel_ms": ci["last_query_kernel_ms"], "client_query_kernel_gbs": ci["pub_mat_a_bytes"] / (ci["last_query_kernel_ms"] * 1e-3) / 1e9,
-                     "pub_mat_a_bytes_resident": ci["pub_mat_a_bytes"]}
         assert rounds >= 3
+        parity["full_size_pir_round_values_recovered"] = rounds
+        setup["e2e_from_db"] = {
+            "api": "chpir_cluster_server_setup_from_db (keys + values in host memory -> resident sharded server + complete hint + filter params)",
+            "wall_s": wall_e, **{k: round(v, 6) for k, v in te.items()}, "hint_gather_s": ie["hint_gather_s"], "db_entries": n_db, "key_bytes": 32,
+            "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e),
+            "after_database_update_with_cached_a": {"wall_s": wall_u, **{k: round(v, 6) for k, v in tu.items()}, "cached_a_bytes_per_gpu": cached[0],
+                                                    "db_encode": "device" if n_gpus == 1 else "host"},
+            "pir_round_gpu_client": {"values_recovered": rounds, "client_setup_s": client_setup_s, "client_query_ms_wall": statistics.median(q_ms),
+                                     "client_query_kernel_ms": ci["last_query_kernel_ms"]}}
         client.close()
-        del srv_g, hint_g, client
-        # spot check on the real D: rows 0..1 of the hint against the exact product with the head of the XOF stream
-        setup["e2e_from_db"] = {"api": "chpir_server_setup_from_db (keys + values in host memory -> resident server + hint + filter params)",
-                                "wall_s": wall_e, **{k: round(v, 6) for k, v in te.items()}, "a_expand": "host", "db_entries": n_db, "key_bytes": 32,
-                                "value_bytes": VALUE_BYTES, "hint_bytes": len(hint_e), "filter_param_bytes": len(fb_e),
-                                "with_device_row_fill": {"wall_s": wall_g, **{k: round(v, 6) for k, v in tg.items()}, "identical_hint_and_filter_bytes": True},
-                                "after_database_update_with_cached_a": {
-                                    "wall_s": wall_u, **{k: round(v, 6) for k, v in tu.items()}, "cached_a_bytes": cached_a_bytes,
-                                    "note": "same seed and keys, new values; A (seed- and K-dependent only) reused from HBM (chpir_setup_opts.a_cache), "
-                                            "device row fill; the PIR round below runs against THIS server and hint"},
-                                "pir_round_gpu_client": pir_round}
-        del hint_e, keys, vals
-    if world > 1 and hint is not None:
-        # the only collective of setup: gather the hint column slices (NCCL), re-interleave on rank 0
-        from chalametpir_b200 import sharding
+        srv_u.close()
+        del hint_e, hint_u, keys, vals, client, srv_e, srv_u
+    del hint
 
-        dist.all_reduce(torch.zeros(1, device=dev))  # communicator set-up is not part of the gather
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        H = torch.from_numpy(np.frombuffer(hint, dtype=np.uint8)[8:].view(np.int32).reshape(LWE, nc).copy()).to(dev)
-        padw = max(sharding.slice_counts(N, world))
-        sendh = torch.zeros((LWE, padw), dtype=torch.int32, device=dev)
-        sendh[:, :nc] = H
-        allh = torch.empty((world, LWE, padw), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allh.view(-1), sendh.view(-1))
-        full_hint = sharding.unpad_gathered(torch, allh, sharding.slice_counts(N, world))
-        torch.cuda.synchronize()
-        setup["hint_gather_s"] = time.perf_counter() - t0
-        setup["hint_bytes_total"] = 8 + 4 * LWE * N
-        assert full_hint.shape == (LWE, N)
-        del H, sendh, allh, full_hint
+    # ---------------- queries: resident in HBM, K-sliced over the GPUs
+    ks = srv.k_pitch
+    KEEP = min(Q, 64)
+    q_slices, q_head = make_query_slices(torch, cluster, plans, K, ks, Q, 1000, keep_full_rows=KEEP)
+    q_ptrs = [t.data_ptr() for t in q_slices]
+    out0 = torch.zeros((Q, N), dtype=torch.int32, device=dev0)
 
-    # ---------------- parity spot checks (outside every timed region; numpy / oracle as the checker)
-    parity = {}
-    if "e2e_from_db" in setup:
-        parity["full_size_pir_round_values_recovered"] = setup["e2e_from_db"]["pir_round_gpu_client"]["values_recovered"]
-        parity["device_row_fill_identical_hint_and_filter_bytes"] = True
-    if "host_pipelined" in setup:
-        parity["host_pipelined_hint_identical_to_device_mode"] = True
-    cols = sorted(set(int(x) for x in np.linspace(0, nc - 1, num=min(nc, 6))))
-    Dcols = D[:, cols].cpu().numpy().astype(np.uint64)
-    if hint is not None and rank == 0:
-        from oracle import oracle as O
+    ms1 = srv.respond_device(q_ptrs, Q, out0.data_ptr(), mode=cp.RESPOND_GEMV, repeats=1)
+    sync_devices(torch, devices)
+    parity["respond_gathered_result_on_columns_of_every_rank"] = check_against_exact(torch, cluster, plans, Ds, q_head, out0, 2)
+    assert parity["respond_gathered_result_on_columns_of_every_rank"], "gathered response differs from the exact dot product"
+    Ds = None
+    for d in devices:
+        with torch.cuda.device(d):
+            torch.cuda.empty_cache()
 
-        a0 = O.generate_rows_from_seed(K, SEED_MU, 0, 2).astype(np.uint64)  # rows 0,1 of A: the head of the XOF stream
-        # exact mod-2^32 dot products without overflow: split A into 16-bit halves
-        lo, hi = a0 & 0xFFFF, a0 >> 16
-        want = ((lo @ Dcols) + (((hi @ Dcols) & 0xFFFF) << 16)) & 0xFFFFFFFF
-        H = np.frombuffer(hint, dtype="<u4")
-        assert H[0] == LWE and H[1] == nc, "hint header"
-        got = H[2:].reshape(LWE, nc)[:2][:, cols].astype(np.uint64)
-        parity["hint_rows_0_1"] = bool(np.array_equal(got, want))
-        assert parity["hint_rows_0_1"], "hint rows 0..1 differ from the oracle"
-    del D
-    torch.cuda.empty_cache()
-
-    g = torch.Generator(device=dev)
-    g.manual_seed(1000)
-    q_dev = torch.randint(-(2**31), 2**31, (Q, K), dtype=torch.int32, device=dev, generator=g)
-    if world > 1:
-        dist.broadcast(q_dev, 0)
-    resp_dev = torch.zeros((Q, nc), dtype=torch.int32, device=dev)
-    counts = [slice_of(N, r, world)[1] for r in range(world)]
-    pad = max(counts)
-    stream = torch.cuda.current_stream().cuda_stream
-    if world > 1:
-        # double-buffered so that the broadcast of batch i+1 and the gather of batch i-1 overlap the GEMVs of batch i
-        q_bufs = [q_dev, q_dev.clone()]
-        send_bufs = [torch.zeros((Q, pad), dtype=torch.int32, device=dev) for _ in range(2)]
-        gather_bufs = [torch.zeros((world, Q, pad), dtype=torch.int32, device=dev) for _ in range(2)]
-
-    def run_steps(n):
-        """n steps; per step: the query batch reaches every rank (broadcast from rank 0), every rank answers for its
-        column slice, the slices are gathered on every rank (rank 0 is the one that needs them)."""
-        if world == 1:
-            for _ in range(n):
-                srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
-            return
-        gw = [None, None]
-        if NO_BCAST:  # experiment (tools/README.md): queries already resident on every rank, isolates the cost of moving them
-            for i in range(n):
-                p = i & 1
-                srv.respond_device(q_bufs[p].data_ptr(), Q, resp_dev.data_ptr(), stream)
-                if gw[p] is not None:
-                    gw[p].wait()
-                send_bufs[p][:, :nc] = resp_dev
-                gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), group=pg_out, async_op=True)
-            for w in gw:
-                if w is not None:
-                    w.wait()
-            return
-        bw = dist.broadcast(q_bufs[0], 0, async_op=True)
-        for i in range(n):
-            p = i & 1
-            bw.wait()
-            if i + 1 < n:
-                bw = dist.broadcast(q_bufs[p ^ 1], 0, async_op=True)
-            srv.respond_device(q_bufs[p].data_ptr(), Q, resp_dev.data_ptr(), stream)
-            if gw[p] is not None:
-                gw[p].wait()
-            send_bufs[p][:, :nc] = resp_dev
-            gw[p] = dist.all_gather_into_tensor(gather_bufs[p].view(-1), send_bufs[p].view(-1), group=pg_out, async_op=True)
-        for w in gw:
-            if w is not None:
-                w.wait()
-
-    def step_device():
-        run_steps(1)
-
-    if os.environ.get("CHPIR_BENCH_PROFILE") and rank == 0:
-        # experiment: kernel timeline of a few steps on rank 0 (CUPTI through torch.profiler), summarised on stderr
-        from torch.profiler import ProfilerActivity, profile
-        run_steps(3)
-        torch.cuda.synchronize()
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            run_steps(int(os.environ["CHPIR_BENCH_PROFILE"]))
-            torch.cuda.synchronize()
-        try:
-            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60), file=sys.stderr)
-            evs = sorted((e for e in prof.events() if e.device_type.name == "CUDA"), key=lambda e: e.time_range.start)
-            for e in evs[: 40]:
-                print(f"  t={e.time_range.start - evs[0].time_range.start:9.1f} us  dur={e.time_range.end - e.time_range.start:8.1f} us  {e.name[:70]}", file=sys.stderr)
-            rk = [e for e in evs if "respond_ring" in e.name]
-            if len(rk) > 2:
-                period = [b.time_range.start - a.time_range.start for a, b in zip(rk, rk[1:])]
-                dur = [e.time_range.end - e.time_range.start for e in rk]
-                print(f"  respond kernels: n={len(rk)} period median {statistics.median(period):.1f} us (min {min(period):.1f}, max {max(period):.1f}); "
-                      f"duration median {statistics.median(dur):.1f} us", file=sys.stderr)
-        except Exception as ex:  # diagnostics only
-            print("profile summary failed:", ex, file=sys.stderr)
-    elif os.environ.get("CHPIR_BENCH_PROFILE"):
-        run_steps(3)
-        run_steps(int(os.environ["CHPIR_BENCH_PROFILE"]))
-
-    step_device()
-    torch.cuda.synchronize()
-    # response parity on sampled columns
-    qh = (q_dev[0].cpu().numpy().view(np.uint32)).astype(np.uint64)
-    lo, hi = qh & 0xFFFF, qh >> 16
-    want = ((lo @ Dcols) + (((hi @ Dcols) & 0xFFFF) << 16)) & 0xFFFFFFFF
-    got = resp_dev[0].cpu().numpy().view(np.uint32)[cols].astype(np.uint64)
-    parity["respond_sampled_columns"] = bool(np.array_equal(got, want))
-    assert parity["respond_sampled_columns"], "respond differs from the exact dot product on sampled columns"
-
-    # ---------------- timed region: K steps, device-resident
-    run_steps(max(args.warmup, 3))
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    # kernel-only timing of the dominant kernel (respond GEMV), same launches without the collectives
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
-        srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
-    k1.record()
-    torch.cuda.synchronize()
-    ms_kernel = k0.elapsed_time(k1) / (args.steps * Q)
-    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_kernel = float(t[0]), float(t[1])
+    # ---------------- timed region: K steps, device-resident (CUDA events on GPU 0 around everything every GPU does)
+    srv.respond_device(q_ptrs, Q, out0.data_ptr(), mode=cp.RESPOND_GEMV, repeats=max(args.warmup, 3))
+    sampler = ClockSampler(devices[0])
+    sampler.start()
+    sync_devices(torch, devices)
+    R.barrier()  # sync point 2
+    w0 = time.perf_counter()
+    ms_total = srv.respond_device(q_ptrs, Q, out0.data_ptr(), mode=cp.RESPOND_GEMV, repeats=args.steps)
+    sync_devices(torch, devices)
+    wall_total_ms = (time.perf_counter() - w0) * 1e3
+    R.barrier()  # sync point 3
     n_queries = args.steps * Q
-    qps = n_queries / (ms_total * 1e-3)
+    chunk = int(os.environ.get("CHPIR_CLUSTER_GEMV_CHUNK", "32"))
+    launches = args.steps * (-(-Q // chunk)) * n_gpus
 
-    # ---------------- e2e: C ABI with host (pinned) buffers, `--e2e-threads` concurrent callers as Arc<Server> sharing allows
-    qlen, rlen = 8 + 4 * K, 8 + 4 * nc
-    # page-locked through the library (cudaHostAlloc): on this box copies from torch's pin_memory() buffers ran at 16-28 GB/s for
-    # 5-75 MB transfers against 52-55 GB/s from cudaHostAlloc memory (tools/h2d_probe.*)
+    # kernel-only timing of the dominant kernel (the streaming GEMV on rank 0's slice): same launches, whole queries already in
+    # rank 0's HBM, no movement -- this is what the roofline is computed from
+    sh0 = srv.shard(0)
+    resp_k = torch.zeros((KEEP, plans[0]["col_count"]), dtype=torch.int32, device=dev0)
+    st = torch.cuda.current_stream(devices[0])
+    k_iters = max(1, min(args.steps * Q, 4096) // KEEP)
+    for _ in range(2):
+        sh0.respond_device(q_head.data_ptr(), KEEP, resp_k.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize(devices[0])
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(st)
+    for _ in range(k_iters):
+        sh0.respond_device(q_head.data_ptr(), KEEP, resp_k.data_ptr(), st.cuda_stream)
+    k1.record(st)
+    torch.cuda.synchronize(devices[0])
+    ms_kernel = k0.elapsed_time(k1) / (k_iters * KEEP)
+    launches += k_iters
+    parity["kernel_only_equals_cluster_result"] = bool(torch.equal(resp_k[:2], out0[:2, : plans[0]["col_count"]]))
+    assert parity["kernel_only_equals_cluster_result"]
+
+    # ---------------- e2e: the C ABI with HOST buffers, concurrent native callers of chpir_cluster_server_respond
+    qlen, rlen = 8 + 4 * K, 8 + 4 * N
     q_pin, r_pin = cp.PinnedBuffer(Q * qlen), cp.PinnedBuffer(Q * rlen)
-    q_host = torch.from_numpy(q_pin.array).view(Q, qlen)
-    r_host = torch.from_numpy(r_pin.array).view(Q, rlen)
-    qh_np = q_host.numpy()
+    qh = q_pin.array.reshape(Q, qlen)
     hdr = np.array([1, K], dtype="<u4").view(np.uint8)
-    qcpu = q_dev.cpu().numpy().view(np.uint8).reshape(Q, 4 * K)
-    for i in range(Q):
-        qh_np[i, :8] = hdr
-        qh_np[i, 8:] = qcpu[i]
+    for r0 in range(0, Q, 32):  # reassemble the whole queries on the host from the resident slices
+        r1 = min(Q, r0 + 32)
+        qh[r0:r1, :8] = hdr
+        for r, p in enumerate(plans):
+            if p["k_count"]:
+                qh[r0:r1, 8 + 4 * p["k_begin"]: 8 + 4 * (p["k_begin"] + p["k_count"])] = q_slices[r][r0:r1, : p["k_count"]].cpu().numpy().view(np.uint8)
+    threads = args.e2e_threads or min(256, 32 * n_gpus)
+    q_host_ptrs = [q_pin.ptr + i * qlen for i in range(Q)]
+    srv.respond_concurrent(q_host_ptrs, qlen, max(args.warmup, 3) * Q, r_pin.ptr, rlen, threads)
+    sync_devices(torch, devices)
+    R.barrier()  # sync point 4
+    e2e_s = srv.respond_concurrent(q_host_ptrs, qlen, n_queries, r_pin.ptr, rlen, threads)
+    sync_devices(torch, devices)
+    R.barrier()  # sync point 5
+    clocks = sampler.stop()
+    e2e_qps = n_queries / e2e_s
+    rh = r_pin.array.reshape(Q, rlen)
+    got = rh[:, 8:].view(np.uint32)
+    parity["e2e_bytes_equal_device_path"] = bool(np.array_equal(got, out0.cpu().numpy().view(np.uint32))) and bool(
+        np.array_equal(rh[:, :8].view("<u4"), np.tile(np.array([1, N], dtype="<u4"), (Q, 1))))
+    assert parity["e2e_bytes_equal_device_path"], "responses through the host-buffer C ABI differ from the device path"
+    co = srv.get_info()
+    # single-caller latency through the ABI: one 4.7 MB H2D (split over the GPUs' PCIe links), one GEMV per GPU, one D2H -- the reference's
+    # `server_respond` bench (integrations/benches/online_phase.rs) measures exactly this call
+    lat = []
+    for _ in range(30):
+        lat.append(srv.respond_concurrent(q_host_ptrs[:1], qlen, 1, r_pin.ptr, rlen, 1) * 1e3)
+    single_ms = statistics.median(lat[5:])
 
-    def e2e_steps_single(n):
-        """n steps = n*Q calls of chpir_server_respond from `--e2e-threads` concurrent callers (the reference shares Arc<Server>
-        across tasks the same way, examples/server.rs:45-85); caller t answers queries t, t+T, t+2T, ... of the n*Q."""
-        nthreads = max(1, min(args.e2e_threads, n * Q))
-        errs = []
-
-        def work(tid):
-            try:
-                for j in range(tid, n * Q, nthreads):
-                    i = j % Q
-                    srv.respond_into(q_host[i].data_ptr(), qlen, r_host[i].data_ptr(), rlen)
-            except Exception as ex:  # pragma: no cover
-                errs.append(ex)
-
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        if errs:
-            raise errs[0]
-
-    if world > 1:
-        # Sharded e2e (SURVEY.md section 8e): the query batch sits in pinned HOST memory; rank r uploads only rows' K/world slice
-        # over its own PCIe link, the slices are all-gathered over NVLink, every rank answers for its column slice through the
-        # C ABI's device entry point, the response slices are gathered and rank 0 reads them back to the host.
-        from chalametpir_b200 import sharding
-
-        k0, k1, ks = sharding.query_slice(K, rank, world)
-        q_words = q_host[:, 8:].view(torch.int32)  # Q x K, pinned
-        NB = 3  # batches in flight: with 2, the upload of batch i+1 could only start once batch i-1 had left the GPU
-        q_slice = [torch.zeros((Q, ks), dtype=torch.int32, device=dev) for _ in range(NB)]
-        q_all = [torch.empty((world, Q, ks), dtype=torch.int32, device=dev) for _ in range(NB)]
-        q_rows = [torch.empty((Q, K), dtype=torch.int32, device=dev) for _ in range(NB)]
-        resp2 = [torch.zeros((Q, nc), dtype=torch.int32, device=dev) for _ in range(NB)]
-        e_send = [torch.zeros((Q, pad), dtype=torch.int32, device=dev) for _ in range(NB)]
-        e_gather = [torch.zeros((world, Q, pad), dtype=torch.int32, device=dev) for _ in range(NB)]
-        r_all_host = [torch.empty((world, Q, pad), dtype=torch.int32).pin_memory() for _ in range(NB)]
-        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        s_main = torch.cuda.current_stream()
-
-        def e2e_steps(n):
-            """Software pipeline NB deep: the upload + all-gather of batches i+1 and i+2 are issued before the respond of batch i, so
-            PCIe, NVLink and HBM streaming overlap; every batch's gathered responses are copied to pinned host memory on rank 0."""
-            done, ready, sent = [None] * NB, [None] * NB, [None] * NB
-
-            def stage_in(i):
-                p = i % NB
-                with torch.cuda.stream(s_in):
-                    if done[p] is not None:
-                        s_in.wait_event(done[p])
-                    sharding.upload_query_slices(q_words, k0, k1, q_slice[p], s_in)  # one strided DMA for the 16 slices
-                    sharding.allgather_query_slices(dist, torch, q_slice[p], q_all[p], q_rows[p])
-                    ready[p] = torch.cuda.Event()
-                    ready[p].record(s_in)
-
-            for i in range(min(NB - 1, n)):
-                stage_in(i)
-            for i in range(n):
-                p = i % NB
-                if i + NB - 1 < n:
-                    stage_in(i + NB - 1)
-                s_main.wait_event(ready[p])
-                if sent[p] is not None:
-                    s_main.wait_event(sent[p])
-                srv.respond_device(q_rows[p].data_ptr(), Q, resp2[p].data_ptr(), stream)
-                done[p] = torch.cuda.Event()
-                done[p].record(s_main)
-                with torch.cuda.stream(s_out):  # the gather and the read-back never hold up the next batch's respond
-                    s_out.wait_event(done[p])
-                    e_send[p][:, :nc] = resp2[p]
-                    sent[p] = torch.cuda.Event()
-                    sent[p].record(s_out)
-                    dist.all_gather_into_tensor(e_gather[p].view(-1), e_send[p].view(-1), group=pg_out)
-                    if rank == 0:
-                        r_all_host[p].copy_(e_gather[p], non_blocking=True)
-            torch.cuda.synchronize()
-    else:
-        e2e_steps = e2e_steps_single
-
-    e2e_steps(max(args.warmup, 3))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    # one nvidia-smi sampler (100 ms period) spans all three timed respond regions: device-resident steps, kernel-only, e2e
-    clocks = sampler.stop() if rank == 0 else None
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_qps = n_queries / float(te[0])
-    # e2e parity: the host-path bytes equal the device-path result
-    if world > 1:
-        got = resp2[(args.steps - 1) % NB][0].cpu().numpy().view(np.uint32)
-    else:
-        got = r_host[0, 8:].numpy().view(np.uint32)
-    srv.respond_device(q_dev.data_ptr(), Q, resp_dev.data_ptr(), stream)
-    torch.cuda.synchronize()
-    parity["e2e_equals_device_path"] = bool(np.array_equal(got, resp_dev[0].cpu().numpy().view(np.uint32)))
-    assert parity["e2e_equals_device_path"]
-
-    # ---------------- batched respond on the tensor cores (BASELINE.json configs[3]: 64-query int8-limb GEMM; 128 fill one M tile)
+    # ---------------- batched respond on the tensor cores, device-resident (128 fill one M tile)
     batched = None
     if not args.no_batch_tc:
-        del q_host, r_host
-        BQ = args.batch_queries
-        qb_dev = torch.randint(-(2**31), 2**31, (BQ, K), dtype=torch.int32, device=dev, generator=g)
-        rb_dev = torch.empty((BQ, nc), dtype=torch.int32, device=dev)
-        srv.respond_device_tc(qb_dev.data_ptr(), BQ, rb_dev.data_ptr(), stream)
-        srv.respond_device(qb_dev.data_ptr(), min(BQ, 4), resp_dev.data_ptr() if Q >= 4 else rb_dev.data_ptr(), stream)
-        torch.cuda.synchronize()
-        if Q >= 4:
-            parity["batched_tc_equals_gemv"] = bool(torch.equal(rb_dev[: min(BQ, 4)], resp_dev[: min(BQ, 4)]))
-            assert parity["batched_tc_equals_gemv"]
-        for _ in range(2):
-            srv.respond_device_tc(qb_dev.data_ptr(), BQ, rb_dev.data_ptr(), stream)
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        nb = max(3, args.steps // 4)
-        for _ in range(nb):
-            srv.respond_device_tc(qb_dev.data_ptr(), BQ, rb_dev.data_ptr(), stream)
-        b1.record()
-        barrier()
-        tb = torch.tensor([b0.elapsed_time(b1) / nb], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        ms_b = float(tb[0])
-        nlimb = 7 if b > 8 else 4
-        int8_ops = nlimb * 2 * 128 * K * (-(-nc // 128) * 128)
-        batched = {"queries_per_batch": BQ, "ms_per_batch": ms_b, "queries_per_s": BQ / (ms_b * 1e-3), "includes": "limb split of the query block + int8-limb GEMM; device-resident queries, no collectives",
-                   "issued_int8_tops": int8_ops * -(-BQ // 128) / (ms_b * 1e-3) / 1e12, "d_plane_bytes_streamed_per_batch": (2 if b > 8 else 1) * K * nc * -(-BQ // 128)}
-        del qb_dev, rb_dev
+        batched = batched_leg(cp, torch, cluster, srv, plans, K, N, b, args.batch_queries, max(3, args.steps // 4), 77, label="this workload")
+        assert all(batched["parity"].values())
+        parity["batched_tc_equals_gemv"] = True
 
-    # ---------------- roofline of the dominant kernel
+    # ---------------- roofline of the dominant kernel (rank 0's slice)
     pk = peaks()
-    streamed = srv.packed_bytes + 4 * K + 4 * nc  # bytes one query on this rank must move: resident packed slice + query + response
-    ref_layout = 4 * nc * ((K + 2) // 3 if b in (9, 10) else (K + 1) // 2 if b >= 11 else (K + 3) // 4) + 4 * K + 4 * nc
+    pb0 = shard_infos[0]["packed_bytes"]
+    nc0 = plans[0]["col_count"]
+    streamed = pb0 + 4 * K + 4 * nc0  # bytes one query on this rank must move: resident packed slice + query + response
+    cf = 3 if b in (9, 10) else (2 if b >= 11 else 4)
+    ref_layout = 4 * nc0 * (-(-K // cf)) + 4 * K + 4 * nc0
     achieved = streamed / (ms_kernel * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "respond_ring_kernel<9,4> (persistent streaming u32 GEMV over K-major bit-packed D, cp.async.bulk smem ring)", "achieved": achieved, "peak": pk["hbm_gbs"],
-        "peak_source": pk["source"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
-        "queries_per_launch": Q, "bytes_per_launch": Q * streamed, "bytes_per_query": streamed, "bytes_per_query_reference_layout": ref_layout,
-        "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9, "us_per_launch": ms_kernel * 1e3 * Q,
+        "bound": "hbm", "kernel": f"respond_ring_kernel<{b},4> (persistent streaming u32 GEMV over K-major bit-packed D, cp.async.bulk smem ring), GPU 0's column slice",
+        "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+        "queries_per_launch": KEEP, "bytes_per_launch": KEEP * streamed, "bytes_per_query": streamed, "bytes_per_query_reference_layout": ref_layout,
+        "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9, "us_per_launch": ms_kernel * 1e3 * KEEP, "launches_timed": k_iters,
+        "timed_region_ms": ms_kernel * KEEP * k_iters, "columns": nc0, "row_pitch_bytes": shard_infos[0]["row_pitch_bytes"],
     }
     prof = os.path.join(ROOT, "profiles", "respond_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"2^{args.log2n}/{args.arity}/n{world}")
+            tr = json.load(open(prof)).get(f"2^{args.log2n}/{args.arity}/n{n_gpus}")
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_query"] * KEEP if isinstance(tr, dict) else tr
+                roofline["traffic_source"] = tr.get("source") if isinstance(tr, dict) else "profiles/respond_traffic.json"
         except Exception:
             pass
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    # ---------------- the other BASELINE.json configurations, each with its own parity flags (separate servers)
+    del q_slices, q_head, out0, resp_k, sh0
+    q_pin.close()
+    r_pin.close()
+    configs = {}
+    if args.configs:
+        srv.close()
+        for d in devices:
+            with torch.cuda.device(d):
+                torch.cuda.empty_cache()
+        configs = config_legs(cp, torch, cluster, args, n_gpus)
 
-    # ---------------- CPU baseline on the host cores (rank 0, N = 1 only)
+    # ---------------- CPU baseline on the host cores (N = 1 only): the full database
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_respond_qps(K, N, b, args.cpu_sample_frac, iters=25)
-        cpu_baseline = {
-            "value": r["qps_full"], "unit": "queries/s", "cores": r["threads"], "kind": "port",
-            "sample": f"rows [0,{r['rows_sample']}) of K={K} (1/{args.cpu_sample_frac} of the database, all {N} columns), median of {len(r['times'])} queries = "
-                      f"{r['ms_sample']:.2f} ms; respond is linear in K so queries/s is scaled by 1/{r['scale']:.2f}; OpenMP threads={r['threads']} of {os.cpu_count()} cpus",
-        }
-
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_respond_baseline(K, N, b, 20, want_cpus)
         try:  # the reference's setup cost on these host cores, extrapolated from a sample (a reported baseline, never a target)
-            setup["cpu_baseline_extrapolated"] = cpu_setup_extrapolated(K, N, b, frac=2, a_rows=2)  # half of D: well past the host's last-level cache
+            setup["cpu_baseline_extrapolated"] = cpu_setup_extrapolated(K, N, b, frac=2, a_rows=2)
         except Exception as ex:  # pragma: no cover -- diagnostics must never cost the bench line
             setup["cpu_baseline_extrapolated"] = {"error": repr(ex)}
 
+    R.barrier()  # sync point 6
+    ms_total, e2e_s_max, ms_kernel = R.max_over_ranks([ms_total, e2e_s, ms_kernel])
+    qps = n_queries / (ms_total * 1e-3)
     line = {
-        "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, b, K, N),
-        "e2e": ({"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * qlen, "d2h_bytes_per_step": Q * rlen,
-                 "threads": max(1, min(args.e2e_threads, args.steps * Q)), "coalesced": not args.no_coalesce,
-                 "pcie_bound_queries_per_s": 52.0e9 / qlen,
-                 "note": "with coalescing, whoever arrives while a batch is on the GPU shares ONE tensor-core pass over D (6..128 queries), so e2e is "
-                         "bounded by the H2D of 4.7 MB per query (52 GB/s measured, tools/h2d_probe.cu), not by `value`, which streams D once "
-                         "PER query (the HBM-roofline GEMV north_star names)",
-                 "api": "chpir_server_respond (C ABI, pinned host buffers), concurrent callers" +
-                        ("" if args.no_coalesce else " coalesced into shared launches (respond_coalesce = 1)")} if world == 1 else
-                {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * 4 * K, "d2h_bytes_per_step": world * Q * pad * 4, "threads": 1,
-                 "api": "pinned host queries -> per-rank H2D of a K/N slice -> NCCL all-gather -> chpir_server_respond_device -> NCCL gather -> D2H on rank 0",
-                 "h2d_bytes_per_step_per_rank": Q * 4 * (-(-K // world))}),
-        "gpu_launches": 2 * args.steps,  # the timed region and the kernel-only region each launch one respond kernel (grid.y = query) per step
+        "timing": {"device_ms_total": ms_total, "wall_ms_total": wall_total_ms, "first_pass_ms": ms1,
+                   "how": "CUDA events on GPU 0's stream: t0 before the first byte moves on any GPU, t1 after GPU 0 has waited for the last columns of every GPU "
+                          "(chpir_cluster_server_respond_device); wall clock of the same call beside it"},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * 4 * K, "d2h_bytes_per_step": Q * 4 * N, "threads": threads,
+                "api": "chpir_cluster_server_respond (C ABI, pinned host buffers): each caller DMAs its query's K/n slices to the n GPUs over their own PCIe "
+                       "links; concurrent callers are coalesced into shared launches (tensor-core limb GEMM from 6 queries up, GEMV below)",
+                "seconds": e2e_s, "coalesced_batches": co["batches"], "coalesced_tensor_core_batches": co["tc_batches"],
+                "mean_batch": co["queries"] / max(1, co["batches"]),
+                "single_caller_ms": single_ms, "single_caller_published_reference_ms": PUBLISHED["server_respond_2^20_3wise_ms"],
+                "pcie_bound_queries_per_s": n_gpus * 52.0e9 / (4 * K),
+                "pcie_bound_note": "4K bytes per query over n_gpus links at the 52 GB/s one link measured in round 1 (tools/h2d_probe.cu)"},
+        "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
         "setup": setup,
         "respond_us_per_query_kernel": ms_kernel * 1e3,
         "batched_respond_tc": batched,
+        "configs": configs,
         "parity": parity,
-        "published_reference": {"server_respond_2^20_3wise_ms": {"m8g.8xlarge": 10.06, "m7i.8xlarge": 14.06}, "server_setup_2^20_3wise_s": {"m8g": 577, "m7i": 1282, "g6e(L40S offload)": 25.58}},
+        "published_reference": PUBLISHED,
     }
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    R.close()
+
+
+def config_legs(cp, torch, cluster, args, n_gpus):
+    """BASELINE.json configs other than the headline one, as driver-visible numbers with their own parity flags."""
+    out = {}
+    devices = cluster.devices
+
+    def free():
+        for d in devices:
+            with torch.cuda.device(d):
+                torch.cuda.empty_cache()
+
+    def gemv_leg(log2n, arity, nq, with_hint, label):
+        srv, hint, Ds, plans, (b, K, N), wall = make_cluster_server(cp, torch, cluster, log2n, arity, not with_hint, keep_d=True, batch_tc=2)
+        infos, tmax = rank_timing(srv, n_gpus)
+        slices, head = make_query_slices(torch, cluster, plans, K, srv.k_pitch, nq, 31 + log2n, keep_full_rows=2)
+        dev0 = f"cuda:{devices[0]}"
+        o = torch.zeros((nq, N), dtype=torch.int32, device=dev0)
+        ptrs = [s.data_ptr() for s in slices]
+        srv.respond_device(ptrs, nq, o.data_ptr(), mode=cp.RESPOND_GEMV, repeats=2)
+        sync_devices(torch, devices)
+        par = {"respond_equals_exact_on_columns_of_every_rank": check_against_exact(torch, cluster, plans, Ds, head, o, 2)}
+        if with_hint:
+            from oracle import oracle as O
+
+            a0 = torch.from_numpy(O.generate_rows_from_seed(K, SEED_MU, 0, 1).view(np.int32).copy()).to(dev0)
+            H = np.frombuffer(hint, dtype="<u4")
+            Hd = torch.from_numpy(H[2: 2 + N].view(np.int32).reshape(1, N).copy()).to(dev0)
+            par["hint_row_0_on_columns_of_every_rank"] = check_against_exact(torch, cluster, plans, Ds, a0, Hd, 1) and H[0] == LWE and H[1] == N
+        iters = 5
+        ms = srv.respond_device(ptrs, nq, o.data_ptr(), mode=cp.RESPOND_GEMV, repeats=iters) / iters
+        gi = srv.get_info()
+        res = {"label": label, "K": K, "N": N, "mat_elem_bit_len": b, "queries_per_pass": nq, "ms_per_pass": ms, "queries_per_s": nq / (ms * 1e-3),
+               "us_per_query": ms * 1e3 / nq, "packed_bytes_max_rank": gi["packed_bytes_max_rank"],
+               "hbm_gbs_per_gpu": (gi["packed_bytes_max_rank"] + 4 * K) * nq / (ms * 1e-3) / 1e9, "parity": par}
+        if with_hint:
+            res["setup"] = {"wall_s": wall, **{k: round(v, 6) for k, v in tmax.items()}, "gemm_kernel_ms": max(i["gemm_ms"] for i in infos),
+                            "hint_gather_s": gi["hint_gather_s"], "hint_bytes": len(hint)}
+        srv.close()
+        del Ds, slices, head, o
+        free()
+        assert all(bool(v) for v in par.values()), (label, par)
+        return res
+
+    try:
+        if n_gpus == 1 and (args.log2n, args.arity) != (18, 3):
+            out["configs[1]"] = gemv_leg(18, 3, 64, True, "2^18 entries, 3-wise: setup hint GEMM + single-query respond on 1 B200")
+        if (args.log2n, args.arity) != (20, 4):
+            srv, _, Ds, plans, (b, K, N), wall = make_cluster_server(cp, torch, cluster, 20, 4, True, keep_d=True, batch_tc=1)
+            leg = batched_leg(cp, torch, cluster, srv, plans, K, N, b, 64, 10, 64, Ds=Ds, label=f"2^20 entries, 4-wise: batched respond, 64-query int8-limb GEMM on {n_gpus} B200")
+            leg128 = batched_leg(cp, torch, cluster, srv, plans, K, N, b, 128, 10, 65, label="the same with 128 queries (one full M tile)")
+            leg.update({"K": K, "N": N, "mat_elem_bit_len": b, "with_128_queries": {k: leg128[k] for k in ("ms_per_batch", "queries_per_s", "issued_int8_tops_all_gpus")}})
+            assert all(leg["parity"].values()), leg["parity"]
+            out["configs[3]"] = leg
+            srv.close()
+            del Ds
+            free()
+        if n_gpus == 8 and (args.log2n, args.arity) != (22, 3):
+            out["configs[4]"] = gemv_leg(22, 3, 32, not args.skip_hint, "2^22 entries, 3-wise: setup + respond column-sharded across 8 B200 (HBM-capacity sizing)")
+    except AssertionError:
+        raise
+    except Exception as ex:  # a secondary leg must never cost the headline line
+        out["error"] = repr(ex)
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--arity", type=int, default=3, choices=[3, 4])
-    ap.add_argument("--queries-per-step", type=int, default=16)
-    ap.add_argument("--e2e-threads", type=int, default=32, help="concurrent callers of chpir_server_respond in the e2e leg (N = 1)")
-    ap.add_argument("--no-coalesce", action="store_true", help="e2e leg: do not coalesce concurrent respond calls into shared launches")
+    ap.add_argument("--queries-per-step", type=int, default=256,
+                    help="queries per step; 256 keeps the driver's 20-step timed region near one second on one GPU (a sustained, not a burst, figure)")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="concurrent callers of chpir_cluster_server_respond in the e2e leg (0 = 32 per GPU, at most 256)")
     ap.add_argument("--skip-hint", action="store_true", help="make D resident only (no A expansion / hint GEMM) -- development shortcut")
-    ap.add_argument("--a-expand", default="both", choices=["device", "host", "both"],
-                    help="where Server::setup walks the TurboSHAKE128 chain of A: GPU warp, host core (pipelined), or both one after the other")
+    ap.add_argument("--a-expand", default="auto", choices=["auto", "device", "host"],
+                    help="where Server::setup walks the TurboSHAKE128 chain of A: the library's default (host core, pipelined), GPU warp, or host core")
     ap.add_argument("--no-e2e-setup", dest="e2e_setup", action="store_false", help="skip the Server::setup(seed, db) measurement from raw keys/values")
+    ap.add_argument("--no-configs", dest="configs", action="store_false", help="skip the legs for the other BASELINE.json configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch-tc", action="store_true", help="skip the tensor-core batched respond measurement")
     ap.add_argument("--batch-queries", type=int, default=128)
-    ap.add_argument("--cpu-sample-frac", type=int, default=8)
-    ap.add_argument("--ref-sample-frac", type=int, default=4)
+    ap.add_argument("--ref-queries-per-step", type=int, default=8, help="--impl reference: queries of each step the CPU arm answers (a bounded sample of the step)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything a library prints to fd 1 (e.g. NCCL's version banner) goes to stderr instead
     global _JSON_OUT

@@ -137,6 +137,7 @@ EXPORTS = [
     "chpir_cluster_server_respond",
     "chpir_cluster_server_respond_batch",
     "chpir_cluster_server_respond_device",
+    "chpir_cluster_server_respond_concurrent",
     "chpir_cluster_server_get_info",
     "chpir_server_respond",
     "chpir_server_respond_batch",
@@ -235,3 +236,4 @@ lib.chpir_cluster_server_respond.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size
 lib.chpir_cluster_server_respond_batch.argtypes = [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32, _vp, C.c_size_t]
 lib.chpir_cluster_server_respond_device.argtypes = [_vp, C.POINTER(_vp), C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
 lib.chpir_cluster_server_get_info.argtypes = [_vp, C.POINTER(ClusterServerInfo)]
+lib.chpir_cluster_server_respond_concurrent.argtypes = [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32, C.c_uint64, _vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_double)]

@@ -70,6 +70,21 @@ class Cluster:
             check(lib.chpir_cluster_ctx(self._h, r, None, C.byref(d)))
             self.devices.append(d.value)
 
+    def ctx(self, rank: int):
+        """The chpir_ctx of rank `rank` (borrowed)."""
+        h = C.c_void_p()
+        check(lib.chpir_cluster_ctx(self._h, rank, C.byref(h), None))
+        return h
+
+    def drop_a_cache(self) -> list:
+        """Free the LWE matrix a ``setup(..., a_cache=True)`` left resident on every GPU of the cluster; returns the bytes released per rank."""
+        out = []
+        for r in range(self.n_gpus):
+            n = C.c_uint64()
+            check(lib.chpir_ctx_drop_a_cache(self.ctx(r), C.byref(n)))
+            out.append(n.value)
+        return out
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             lib.chpir_cluster_destroy(self._h)
@@ -199,6 +214,25 @@ class ClusterServer:
         out = np.empty(nq * stride, dtype=np.uint8)
         check(lib.chpir_cluster_server_respond_batch(self._h, ptrs, lens, nq, out.ctypes.data, stride))
         return [out[i * stride : (i + 1) * stride].tobytes() for i in range(nq)]
+
+    def respond_concurrent(self, query_ptrs: Sequence[int], query_len: int, total_calls: int, resp_ptr: int, resp_stride: int, n_threads: int) -> float:
+        """`n_threads` native threads call chpir_cluster_server_respond concurrently (call j sends query j % len(query_ptrs)); returns the
+        wall seconds.  Host buffers by pointer, e.g. slices of a :class:`PinnedBuffer`."""
+        n = len(query_ptrs)
+        ptrs = (C.c_void_p * n)(*query_ptrs)
+        lens = (C.c_size_t * n)(*([query_len] * n))
+        sec = C.c_double()
+        check(lib.chpir_cluster_server_respond_concurrent(self._h, ptrs, lens, n, total_calls, resp_ptr, resp_stride, n_threads, C.byref(sec)))
+        return sec.value
+
+    def shard(self, rank: int) -> Server:
+        """Rank `rank`'s resident slice as a (borrowed, non-owning) single-GPU :class:`Server`."""
+        sh = C.c_void_p()
+        check(lib.chpir_cluster_server_shard(self._h, rank, C.byref(sh)))
+        s = Server(sh, self.cluster.devices[rank])
+        s._borrowed = True
+        s._keepalive = self
+        return s
 
     def respond_device(self, q_slice_ptrs: Sequence[int], nq: int, resp_ptr0: int, mode: int = RESPOND_GEMV, repeats: int = 1) -> float:
         """Device-resident respond; returns the device time (ms) of all `repeats` passes, measured on rank 0's GPU."""

@@ -80,6 +80,20 @@ NcclApi *nccl_api() {
   return api.handle ? &api : nullptr;
 }
 
+// The cluster calls switch the calling thread's current device; a host framework that tracks "its" device must find it unchanged.
+struct DeviceRestore {
+  int dev = -1;
+  DeviceRestore() {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      dev = -1;
+      (void)cudaGetLastError();
+    }
+  }
+  ~DeviceRestore() {
+    if (dev >= 0) cudaSetDevice(dev);
+  }
+};
+
 uint32_t env_u32(const char *name, uint32_t dflt) {
   const char *v = std::getenv(name);
   return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
@@ -668,6 +682,7 @@ int chpir_cluster_plan(uint32_t n_ranks, uint32_t rank, uint64_t rows_k, uint32_
 
 int chpir_cluster_create(int n_gpus, const int *device_ordinals, chpir_cluster **out) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (n_gpus == 0) n_gpus = int(env_u32("CHPIR_GPUS", 1));
@@ -714,7 +729,10 @@ int chpir_cluster_create(int n_gpus, const int *device_ordinals, chpir_cluster *
   CHPIR_GUARD_END
 }
 
-void chpir_cluster_destroy(chpir_cluster *cluster) { delete cluster; }
+void chpir_cluster_destroy(chpir_cluster *cluster) {
+  DeviceRestore restore_device;
+  delete cluster;
+}
 
 int chpir_cluster_size(const chpir_cluster *cluster, int *n_gpus) {
   if (!cluster || !n_gpus) return CHPIR_ERR_INVALID_ARGUMENT;
@@ -733,6 +751,7 @@ int chpir_cluster_server_setup_device(chpir_cluster *cl, const uint8_t seed[CHPI
                                       uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
                                       chpir_cluster_server **out) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (!cl || !seed || !d_slices) return CHPIR_ERR_INVALID_ARGUMENT;
@@ -759,6 +778,7 @@ int chpir_cluster_server_setup(chpir_cluster *cl, const uint8_t seed[CHPIR_SEED_
                                uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len,
                                chpir_cluster_server **out) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (!cl || !seed || !d_host) return CHPIR_ERR_INVALID_ARGUMENT;
@@ -785,6 +805,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
                                        const uint64_t *filter_seed_rng, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
                                        size_t *hint_len, uint8_t filter_params_out[CHPIR_FILTER_PARAM_BYTE_LEN], chpir_cluster_server **out) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (n == 0) return CHPIR_ERR_EMPTY_KV_DATABASE;  // server.rs:104-107
@@ -851,7 +872,10 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   CHPIR_GUARD_END
 }
 
-void chpir_cluster_server_destroy(chpir_cluster_server *srv) { delete srv; }
+void chpir_cluster_server_destroy(chpir_cluster_server *srv) {
+  DeviceRestore restore_device;
+  delete srv;
+}
 
 int chpir_cluster_server_shard(const chpir_cluster_server *srv, int rank, chpir_server **shard) {
   if (!srv || !shard || rank < 0 || uint32_t(rank) >= srv->n) return CHPIR_ERR_INVALID_ARGUMENT;
@@ -861,6 +885,7 @@ int chpir_cluster_server_shard(const chpir_cluster_server *srv, int rank, chpir_
 
 int chpir_cluster_server_save(chpir_cluster_server *srv, const char *path_prefix) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!srv || !path_prefix) return CHPIR_ERR_INVALID_ARGUMENT;
   for (uint32_t d = 0; d < srv->n; d++) {
     const std::string p = std::string(path_prefix) + ".rank" + std::to_string(d) + "of" + std::to_string(srv->n);
@@ -872,6 +897,7 @@ int chpir_cluster_server_save(chpir_cluster_server *srv, const char *path_prefix
 
 int chpir_cluster_server_load(chpir_cluster *cl, const char *path_prefix, const chpir_setup_opts *opts, chpir_cluster_server **out) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (!cl || !path_prefix) return CHPIR_ERR_INVALID_ARGUMENT;
@@ -916,6 +942,7 @@ int chpir_cluster_server_load(chpir_cluster *cl, const char *path_prefix, const 
 
 int chpir_cluster_server_respond(chpir_cluster_server *S, const uint8_t *query, size_t query_len, uint8_t *resp_out, size_t resp_cap, size_t *resp_len) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!S) return CHPIR_ERR_INVALID_ARGUMENT;
   if (S->n == 1) return chpir_server_respond(S->r[0].srv, query, query_len, resp_out, resp_cap, resp_len);
   if (int rc = validate_query_bytes(S->K, query, query_len); rc != CHPIR_OK) return rc;
@@ -931,6 +958,7 @@ int chpir_cluster_server_respond(chpir_cluster_server *S, const uint8_t *query, 
 int chpir_cluster_server_respond_batch(chpir_cluster_server *S, const uint8_t *const *queries, const size_t *query_lens, uint32_t nq, uint8_t *resp_out,
                                        size_t resp_stride) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!S || !queries || !query_lens || !resp_out) return CHPIR_ERR_INVALID_ARGUMENT;
   if (S->n == 1) return chpir_server_respond_batch(S->r[0].srv, queries, query_lens, nq, resp_out, resp_stride);
   const size_t need = 8 + size_t(S->N) * 4;
@@ -974,6 +1002,7 @@ int chpir_cluster_server_respond_batch(chpir_cluster_server *S, const uint8_t *c
 int chpir_cluster_server_respond_device(chpir_cluster_server *S, const uint32_t *const *q_slices, uint32_t nq, uint32_t *resp_device0, uint32_t mode,
                                         uint32_t repeats, float *device_ms) {
   CHPIR_GUARD_BEGIN
+  DeviceRestore restore_device;
   if (!S || !q_slices || !resp_device0 || mode > CHPIR_RESPOND_TC) return CHPIR_ERR_INVALID_ARGUMENT;
   if (device_ms) *device_ms = 0.f;
   if (nq == 0 || repeats == 0) return CHPIR_OK;
@@ -984,11 +1013,13 @@ int chpir_cluster_server_respond_device(chpir_cluster_server *S, const uint32_t 
   std::lock_guard<std::mutex> g(S->dev_mu);
   std::lock_guard<std::mutex> ex(S->exec_mu);  // shares the compute streams and the operand rings with the coalesced route
   const uint32_t chunk = tc ? kMaxBatch : std::max(1u, std::min(env_u32("CHPIR_CLUSTER_GEMV_CHUNK", kGemvChunk), 4096u));
+  // one rank whose slice IS the whole query (K a multiple of 32): the rows are already what the GEMV reads, nothing to gather
+  const bool direct = !tc && S->n == 1 && S->ks == S->K;
   // scratch: whole-query rows (GEMV route only) and the rank's response columns, double-buffered
   for (uint32_t d = 0; d < S->n; d++) {
     Rank &R = S->r[d];
     CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
-    if (!tc && R.q_rows < chunk) {
+    if (!tc && !direct && R.q_rows < chunk) {
       for (int p = 0; p < 2; p++) {
         if (R.q_full[p]) cudaFree(R.q_full[p]);
         R.q_full[p] = nullptr;
@@ -1033,7 +1064,7 @@ int chpir_cluster_server_respond_device(chpir_cluster_server *S, const uint32_t 
       const int p = int(it & 1);
       SrcTable src{};
       for (uint32_t s = 0; s < S->n; s++) src.p[s] = q_slices[s] + size_t(row0) * S->ks;
-      if (!tc) {
+      if (!tc && !direct) {
         // all-gather of the query rows on the gather streams: runs beside the previous chunk's GEMVs
         for (uint32_t d = 0; d < S->n && rc == CHPIR_OK; d++) {
           Rank &R = S->r[d];
@@ -1067,6 +1098,8 @@ int chpir_cluster_server_respond_device(chpir_cluster_server *S, const uint32_t 
           if ((rc = launch_gather(true, src, rows, S->ks, S->K, gemm_tc_kp(sv->gemm), planes, nullptr, R.ctx->sm_count, st)) != CHPIR_OK) break;
           if ((rc = gemm_tc_panel(sv->gemm, buf, rows, R.resp[p], st)) != CHPIR_OK) break;
           if ((rc = gemm_tc_buf_release(sv->gemm, buf, st)) != CHPIR_OK) break;
+        } else if (direct) {
+          if ((rc = launch_respond(sv->d_packed, sv->layout, sv->K, sv->plan, src.p[0], R.resp[p], rows, st)) != CHPIR_OK) break;
         } else {
           CHPIR_CUDA(cudaStreamWaitEvent(st, R.gathered[p], 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
           if ((rc = launch_respond(sv->d_packed, sv->layout, sv->K, sv->plan, R.q_full[p], R.resp[p], rows, st)) != CHPIR_OK) break;
@@ -1101,6 +1134,37 @@ int chpir_cluster_server_respond_device(chpir_cluster_server *S, const uint32_t 
     if (cudaEventElapsedTime(&ms, S->t0, S->t1) == cudaSuccess) *device_ms = ms;
   }
   return rc;
+  CHPIR_GUARD_END
+}
+
+int chpir_cluster_server_respond_concurrent(chpir_cluster_server *S, const uint8_t *const *queries, const size_t *query_lens, uint32_t n_distinct,
+                                            uint64_t total_calls, uint8_t *resp_out, size_t resp_stride, uint32_t n_threads, double *seconds) {
+  CHPIR_GUARD_BEGIN
+  if (!S || !queries || !query_lens || !resp_out || n_distinct == 0 || n_threads == 0) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (seconds) *seconds = 0.0;
+  if (total_calls == 0) return CHPIR_OK;
+  n_threads = uint32_t(std::min<uint64_t>(n_threads, total_calls));
+  std::vector<int> rcs(n_threads, CHPIR_OK);
+  std::vector<std::thread> th;
+  th.reserve(n_threads);
+  const double t0 = now_s();
+  for (uint32_t t = 0; t < n_threads; t++)
+    th.emplace_back([&, t] {
+      for (uint64_t j = t; j < total_calls; j += n_threads) {
+        const uint32_t i = uint32_t(j % n_distinct);
+        size_t len = 0;
+        const int rc = chpir_cluster_server_respond(S, queries[i], query_lens[i], resp_out + size_t(i) * resp_stride, resp_stride, &len);
+        if (rc != CHPIR_OK) {
+          rcs[t] = rc;
+          return;
+        }
+      }
+    });
+  for (auto &t : th) t.join();
+  if (seconds) *seconds = now_s() - t0;
+  for (int rc : rcs)
+    if (rc != CHPIR_OK) return rc;
+  return CHPIR_OK;
   CHPIR_GUARD_END
 }
 

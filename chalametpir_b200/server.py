@@ -332,7 +332,8 @@ class Server:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            lib.chpir_server_destroy(self._h)
+            if not getattr(self, "_borrowed", False):  # a cluster's shard belongs to the cluster server
+                lib.chpir_server_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -320,6 +320,15 @@ CHPIR_API int chpir_cluster_server_respond(chpir_cluster_server *srv, const uint
 CHPIR_API int chpir_cluster_server_respond_batch(chpir_cluster_server *srv, const uint8_t *const *queries, const size_t *query_lens,
                                                  uint32_t nq, uint8_t *resp_out, size_t resp_stride);
 
+/* Load generator: n_threads native threads call chpir_cluster_server_respond concurrently -- what the reference's example server does
+ * with one task per connection sharing an Arc<Server> (chalametpir_server/examples/server.rs:45-85).  Call j (0 <= j < total_calls)
+ * sends queries[j % n_distinct] and writes its response to resp_out + (j % n_distinct) * resp_stride; *seconds (may be NULL) is the
+ * wall time from the first thread's start to the last one's return.  Used by bench.py and the tests so that the caller side of the
+ * end-to-end measurement is native code too. */
+CHPIR_API int chpir_cluster_server_respond_concurrent(chpir_cluster_server *srv, const uint8_t *const *queries, const size_t *query_lens,
+                                                      uint32_t n_distinct, uint64_t total_calls, uint8_t *resp_out, size_t resp_stride,
+                                                      uint32_t n_threads, double *seconds);
+
 /* Device-resident respond (inputs already in the cluster's HBM): q_slices[r] = nq x k_pitch u32 on rank r's GPU holding words
  * [k_begin(r), +k_count(r)) of every query -- exactly what the PCIe ingest above leaves behind -- and resp_device0 = nq x N u32 on
  * rank 0's GPU.  mode CHPIR_RESPOND_GEMV: every query streams every rank's packed slice once (the HBM-bound path); mode

@@ -1060,3 +1060,16 @@ ORC_EXPORT int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* Size of the thread pool that stands in for the reference's rayon global pool (one worker per hardware thread,
+ * rayon =1.10.0 default).  Launchers such as torchrun export OMP_NUM_THREADS=1 to their workers; the benchmark's CPU
+ * arm calls this with the number of usable cpus so that the baseline is never starved. */
+ORC_EXPORT int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}

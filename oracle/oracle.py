@@ -416,3 +416,10 @@ class Client:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """Resize the OpenMP pool (the stand-in for rayon's one-worker-per-hardware-thread pool); returns the size in effect."""
+    lib().orc_set_num_threads.restype = C.c_int
+    lib().orc_set_num_threads.argtypes = [C.c_int]
+    return lib().orc_set_num_threads(int(n))
