@@ -60,7 +60,6 @@ struct RespondPlan {
   uint32_t ring_R;          // row lanes (multiple of 4)
   uint32_t ring_rpt;        // rows per thread per stage (1, 2 or 4)
   uint32_t ring_stages;
-  uint32_t ring_cps;        // CTAs per SM the launch is planned for (1 or 2)
   uint32_t ring_grid, ring_block;
   uint32_t ring_stage_bytes, ring_smem_bytes;
   uint64_t ring_rows_per_cta;

@@ -226,9 +226,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 constexpr int kRingMaxThreads = 1024;
-constexpr int kRingMaxThreads2 = 640;  // per CTA when two share an SM (register file: 2 x 640 x 48)
 constexpr int kMaxDevices = 64;
-constexpr uint32_t kRingTwoCtaMaxUnits = 0;  // rows of at most this many 16-byte units get two CTAs per SM by default (0 = never; see plan_ring)
 
 __device__ __forceinline__ void bar_sync_consumers(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
@@ -237,13 +235,8 @@ __device__ __forceinline__ void bar_sync_consumers(uint32_t nthreads) { asm vola
 // flattened -- and the epilogue of a query (fold the R row lanes, one atomic per column) borrows the last stage the consumers read
 // as scratch: two consumer-only barriers and a few shuffles instead of 2*FPW block-wide reduction rounds (at 8-way column sharding
 // a query is ~25 us of streaming per rank, and the old epilogue was ~3 us of it).
-// CPS = CTAs resident per SM the kernel is compiled for: 1 = one CTA with the whole shared memory (wide rows), 2 = two CTAs of at
-// most 640 threads and half the shared memory each -- consecutive queries (grid.y) then overlap on every SM: while one CTA drains its
-// pipeline, folds its accumulators and publishes them, the other keeps the memory system busy, and the two stream the same K range
-// of D within microseconds of each other, so the second mostly hits in L2.  On a 118-column slice (8-way sharding) a query is only
-// ~25 us of streaming per GPU, of which the pipeline fill and the epilogue are ~3 us that one CTA per SM leaves idle.
-template <int B, int RPT, bool TIGHT, int CPS>
-__global__ void __launch_bounds__(CPS == 1 ? kRingMaxThreads : kRingMaxThreads2, CPS)
+template <int B, int RPT, bool TIGHT>
+__global__ void __launch_bounds__(kRingMaxThreads, 1)
     respond_ring_kernel(const uint8_t *__restrict__ packed, const uint32_t *__restrict__ q_all, uint32_t *__restrict__ resp_all, uint64_t K,
                         uint32_t pitch, uint32_t units, uint32_t R, uint32_t stages, uint32_t stage_bytes, uint64_t rows_per_cta, uint32_t ncols, uint32_t q_bulk,
                         uint32_t nq, uint32_t q_per_cta) {
@@ -483,7 +476,6 @@ int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
     if (dev >= kMaxDevices || configured[dev] != reinterpret_cast<const void *>(kernel)) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-      (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (dev < kMaxDevices) configured[dev] = reinterpret_cast<const void *>(kernel);
     }
     // One grid row per query (q_per_cta = 1): the hardware scheduler hands the next query's CTAs to whichever SMs finish first.
@@ -497,21 +489,15 @@ int respond_ring_dispatch(const uint8_t *packed, const PackedLayout &L, uint64_t
   };
   if (L.tight) {
     switch (P.ring_rpt) {
-      case 1: return launch(respond_ring_kernel<B, 1, true, 1>);
-      case 2: return launch(respond_ring_kernel<B, 2, true, 1>);
-      default: return launch(respond_ring_kernel<B, 4, true, 1>);
-    }
-  }
-  if (P.ring_cps == 2) {
-    switch (P.ring_rpt) {
-      case 1: return launch(respond_ring_kernel<B, 1, false, 2>);
-      default: return launch(respond_ring_kernel<B, 2, false, 2>);
+      case 1: return launch(respond_ring_kernel<B, 1, true>);
+      case 2: return launch(respond_ring_kernel<B, 2, true>);
+      default: return launch(respond_ring_kernel<B, 4, true>);
     }
   }
   switch (P.ring_rpt) {
-    case 1: return launch(respond_ring_kernel<B, 1, false, 1>);
-    case 2: return launch(respond_ring_kernel<B, 2, false, 1>);
-    default: return launch(respond_ring_kernel<B, 4, false, 1>);
+    case 1: return launch(respond_ring_kernel<B, 1, false>);
+    case 2: return launch(respond_ring_kernel<B, 2, false>);
+    default: return launch(respond_ring_kernel<B, 4, false>);
   }
 }
 
@@ -562,12 +548,6 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
   if (env_u32("CHPIR_RESPOND_RING", 1) == 0) return;
   const uint32_t units = L.units;
   if (units == 0 || 4 * units > uint32_t(kRingMaxThreads) - 32) return;  // a row must fit the consumer threads of one CTA
-  // Two CTAs per SM (see respond_ring_kernel) for narrow rows -- the column slices of a sharded server -- where a query is short
-  // enough for the per-CTA fill/drain to matter; wide rows keep one CTA with all of the shared memory.  CHPIR_RING_CPS overrides.
-  uint32_t cps = env_u32("CHPIR_RING_CPS", 0);
-  if (cps == 0) cps = (units <= kRingTwoCtaMaxUnits && !L.tight) ? 2 : 1;
-  if (cps != 2 || L.tight || 4 * units > uint32_t(kRingMaxThreads2) - 32) cps = 1;
-  const uint32_t max_threads = cps == 2 ? kRingMaxThreads2 : kRingMaxThreads;
   uint32_t R = env_u32("CHPIR_RING_R", 0);
   if (R == 0) {
     R = (640 / units) & ~3u;
@@ -575,12 +555,11 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
     if (R > 64) R = 64;
   }
   R = (R + 3) & ~3u;
-  while (R > 4 && R * units > max_threads - 32) R -= 4;
-  uint32_t rpt = env_u32("CHPIR_RING_RPT", cps == 2 ? 2 : 4);
+  while (R > 4 && R * units > uint32_t(kRingMaxThreads) - 32) R -= 4;
+  uint32_t rpt = env_u32("CHPIR_RING_RPT", 4);
   if (rpt != 1 && rpt != 2) rpt = 4;
-  if (cps == 2 && rpt > 2) rpt = 2;  // 48 registers per thread when two CTAs share the register file
   const uint32_t pitch = uint32_t(L.pitch_bytes());
-  const uint32_t budget = std::min(env_u32("CHPIR_RING_BUDGET_KB", cps == 2 ? 110 : 200), cps == 2 ? 112u : 200u) * 1024;
+  const uint32_t budget = std::min(env_u32("CHPIR_RING_BUDGET_KB", 200), 200u) * 1024;
   while (rpt > 1 && 3 * R * rpt * (pitch + 4) > budget) rpt /= 2;
   const uint32_t S = R * rpt;
   const uint32_t stage_bytes = S * (pitch + 4);
@@ -590,7 +569,6 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
   if (stages > 32) stages = 32;
   if (stages < 2) return;
   P->ring = 1;
-  P->ring_cps = cps;
   P->ring_R = R;
   P->ring_rpt = rpt;
   P->ring_stages = stages;

@@ -13,7 +13,6 @@ Q = 16
 
 
 def run(ncols, env, iters=30):
-    global Q
     for k in list(os.environ):
         if k.startswith("CHPIR_R") or k.startswith("CHPIR_T"):
             del os.environ[k]
@@ -63,16 +62,6 @@ if __name__ == "__main__":
             for rep in range(2):
                 for R in Rs:
                     run(nc, {"CHPIR_RING_R": R}, iters=60)
-        sys.exit(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "cps":  # one CTA per SM against two co-resident CTAs (consecutive queries overlap on every SM)
-        Q = 64
-        for nc in (118, 117, 235, 470, 940):
-            ref = None
-            for rep in range(2):
-                for env in [{"CHPIR_RING_CPS": 1}, {"CHPIR_RING_CPS": 2}, {"CHPIR_RING_CPS": 2, "CHPIR_RING_RPT": 1}, {"CHPIR_RING_CPS": 2, "CHPIR_RING_BUDGET_KB": 96}]:
-                    got = run(nc, env, iters=20)
-                    ref = got if ref is None else ref
-                    assert torch.equal(got, ref), "the two launch shapes disagree"
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grid":
         for nc in (118, 235, 470, 940):
