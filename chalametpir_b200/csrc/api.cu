@@ -25,6 +25,32 @@ void set_last_cuda_error(cudaError_t e, const char *what) {
   (void)cudaGetLastError();  // clear the sticky-less error state
 }
 
+// Page-locked ranges handed out by chpir_host_alloc: memory every GPU of the process can read directly (portable + mapped), which
+// the cluster's query ingest uses to pull a whole batch with one kernel per GPU instead of one DMA call per query and GPU.
+namespace {
+std::mutex g_pinned_mu;
+std::vector<std::pair<uintptr_t, uintptr_t>> g_pinned;  // [begin, end), few entries
+}  // namespace
+void pinned_registry_add(const void *p, size_t bytes) {
+  std::lock_guard<std::mutex> g(g_pinned_mu);
+  g_pinned.emplace_back(reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes);
+}
+void pinned_registry_remove(const void *p) {
+  std::lock_guard<std::mutex> g(g_pinned_mu);
+  for (size_t i = 0; i < g_pinned.size(); i++)
+    if (g_pinned[i].first == reinterpret_cast<uintptr_t>(p)) {
+      g_pinned.erase(g_pinned.begin() + long(i));
+      return;
+    }
+}
+bool pinned_registry_contains(const void *p, size_t bytes) {
+  const uintptr_t b = reinterpret_cast<uintptr_t>(p), e = b + bytes;
+  std::lock_guard<std::mutex> g(g_pinned_mu);
+  for (const auto &r : g_pinned)
+    if (b >= r.first && e <= r.second) return true;
+  return false;
+}
+
 }  // namespace chpir
 
 using namespace chpir;
@@ -481,15 +507,18 @@ int chpir_ctx_drop_a_cache(chpir_ctx *ctx, uint64_t *bytes_freed) {
 int chpir_host_alloc(size_t bytes, void **out) {
   if (!out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
-  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
     set_last_cuda_error(cudaGetLastError(), "cudaHostAlloc");
     return CHPIR_ERR_HOST_ALLOCATION_FAILED;
   }
+  pinned_registry_add(*out, bytes ? bytes : 1);
   return CHPIR_OK;
 }
 
 void chpir_host_free(void *p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  pinned_registry_remove(p);
+  cudaFreeHost(p);
 }
 
 int chpir_upload_rows(void *dst_device, size_t dst_pitch, const void *src_host, size_t src_pitch, size_t width_bytes, size_t rows, void *cuda_stream) {

@@ -52,6 +52,10 @@ class HostAPipe;
 int server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k, uint32_t cols_n,
                                   uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out,
                                   HostAPipe *pipe);
+// registry of the page-locked ranges chpir_host_alloc handed out (device-readable from every GPU of the process)
+void pinned_registry_add(const void *p, size_t bytes);
+void pinned_registry_remove(const void *p);
+bool pinned_registry_contains(const void *p, size_t bytes);
 // Matrix::from_bytes validation + the 1 x K dimension check, in the reference's order (matrix.rs:973-1010, :329-331)
 int validate_query_bytes(uint64_t K, const uint8_t *query, size_t len);
 
