@@ -15,12 +15,13 @@ resident in HBM; `e2e` is the same metric through the C ABI call the reference's
 called by concurrent native threads as the reference's example server does with one task per connection.
 
 N > 1: the server is ONE process driving N GPUs (chpir_cluster_*, csrc/cluster.cu) -- the reference's `Server::respond(&self, &[u8])`
-has no room for a rank argument, so the column sharding lives behind the handle.  Under torchrun every rank joins the process
+has no room for a rank argument, so the sharding lives behind the handle.  Under torchrun every rank joins the process
 group (NCCL for the communicator, gloo for the CPU-side barriers around the timed regions); rank 0 is the server process and owns all N
-GPUs, ranks 1..N-1 hold no data and wait at the barriers.  Columns of D (and so of the hint and of every response) are sliced across
-the GPUs; queries are resident K-sliced over the GPUs exactly as the PCIe ingest leaves them and are all-gathered over NVLink by the
-copy engines; every GPU answers for its columns; the columns land in GPU 0's row-major result by strided peer copies.  The
-database is the same size at every N, so `scaling` is "strong".
+GPUs, ranks 1..N-1 hold no data and wait at the barriers.  Setup cuts D by COLUMNS (hint slices, gathered over NCCL); respond cuts it
+by ROWS: GPU r keeps rows [k0_r, k0_r + K/N) at full width and needs only the words of a query it ingested over its own PCIe link,
+so queries are resident K-sliced over the GPUs exactly as the ingest leaves them, no query word crosses NVLink, and GPU 0 adds the
+N partial responses (exact mod 2^32) with one small kernel reading peer memory.  The round-1 column cut for respond is timed beside
+it (`column_cut_comparison`).  The database is the same size at every N, so `scaling` is "strong".
 
 `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores) on the same workload at FULL
 size; the Rust reference itself cannot be built in this image (no cargo/rustc), see DESIGN.md.
@@ -302,13 +303,15 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, b, K, N):
+def workload_config(args, b, K, N, by_rows=True):
     return {
         "workload": f"2^{args.log2n} entries x 32B keys x {VALUE_BYTES}B values, {args.arity}-wise XOR filter (BASELINE.json " +
                     {(16, 3): "configs[0]", (18, 3): "configs[1]", (20, 3): "configs[2]", (20, 4): "configs[3] shape", (22, 3): "configs[4]"}.get(
                         (args.log2n, args.arity), "shape outside configs") + ")",
         "K": K, "N": N, "mat_elem_bit_len": b, "lwe_dimension": LWE, "queries_per_step": args.queries_per_step,
-        "sharding": f"columns/{args.gpus}, one process, chpir_cluster_* (csrc/cluster.cu)" if args.gpus > 1 else "none (cluster of one GPU)",
+        "sharding": (f"respond: rows of D (K)/{args.gpus}, partial responses summed on GPU 0; setup: columns/{args.gpus}; one process, chpir_cluster_* "
+                     f"(csrc/cluster.cu)" if by_rows else f"columns/{args.gpus}, one process, chpir_cluster_* (csrc/cluster.cu)") if args.gpus > 1
+        else "none (cluster of one GPU)",
         "l2": "inputs larger than L2 (every query streams the resident packed D: 1.28 GB / n_gpus per GPU vs 126 MB of L2)",
     }
 
@@ -473,10 +476,21 @@ def batched_leg(cp, torch, cluster, srv, plans, K, N, b, BQ, iters, seed, Ds=Non
     ms = srv.respond_device(ptrs, BQ, out_tc.data_ptr(), mode=cp.RESPOND_TC, repeats=iters) / iters
     nlimb = 7 if b > 8 else 4
     tiles = -(-BQ // 128)
-    issued = sum(nlimb * 2 * 128 * K * (-(-p["col_count"] // 16) * 16 if p["col_count"] <= 128 else -(-p["col_count"] // 128) * 128) for p in plans) * tiles
-    plane_bytes = sum((2 if b > 8 else 1) * K * p["col_count"] for p in plans) * tiles
+
+    def n_pad(nc):
+        return -(-nc // 16) * 16 if nc <= 128 else -(-nc // 128) * 128
+
+    by_rows = bool(srv.get_info()["respond_by_rows"])
+    if by_rows:  # every rank: 128 x N_pad x k_pitch
+        issued = nlimb * 2 * 128 * srv.k_pitch * n_pad(N) * cluster.n_gpus * tiles
+        plane_bytes = (2 if b > 8 else 1) * srv.k_pitch * N * cluster.n_gpus * tiles
+        inc = "limb split of each rank's own query words, int8-limb GEMM over its rows of D on every rank, sum of the partial responses on GPU 0 (peer reads)"
+    else:
+        issued = sum(nlimb * 2 * 128 * K * n_pad(p["col_count"]) for p in plans) * tiles
+        plane_bytes = sum((2 if b > 8 else 1) * K * p["col_count"] for p in plans) * tiles
+        inc = "NVLink gather of the K-sliced queries fused with the limb split, int8-limb GEMM on every rank, strided peer copy of the columns to GPU 0"
     return {"label": label, "queries_per_batch": BQ, "ms_per_batch": ms, "queries_per_s": BQ / (ms * 1e-3),
-            "includes": "NVLink gather of the K-sliced queries fused with the limb split, int8-limb GEMM on every rank, strided peer copy of the columns to GPU 0",
+            "includes": inc,
             "issued_int8_tops_all_gpus": issued / (ms * 1e-3) / 1e12, "d_plane_bytes_streamed_per_batch_all_gpus": plane_bytes,
             "d_plane_gbs_per_gpu": plane_bytes / cluster.n_gpus / (ms * 1e-3) / 1e9, "parity": parity}
 
@@ -634,27 +648,42 @@ def run_b200(args):
     R.barrier()  # sync point 3
     n_queries = args.steps * Q
     chunk = int(os.environ.get("CHPIR_CLUSTER_GEMV_CHUNK", "32"))
-    launches = args.steps * (-(-Q // chunk)) * n_gpus
 
-    # kernel-only timing of the dominant kernel (the streaming GEMV on rank 0's slice): same launches, whole queries already in
-    # rank 0's HBM, no movement -- this is what the roofline is computed from
+    # kernel-only timing of the dominant kernel (the streaming GEMV on rank 0's shard): same launches on rank 0's stream, nothing else
+    # running -- this is what the roofline is computed from.  Row cut: the shard is k_pitch x N and reads rank 0's own query words.
+    by_rows = bool(info["respond_by_rows"])
+    launches = args.steps * (n_gpus + 1) if by_rows else args.steps * (-(-Q // chunk)) * n_gpus
     sh0 = srv.shard(0)
-    resp_k = torch.zeros((KEEP, plans[0]["col_count"]), dtype=torch.int32, device=dev0)
+    sh0_cols = N if by_rows else plans[0]["col_count"]
+    q_k0 = q_slices[0] if by_rows else q_head
+    resp_k = torch.zeros((KEEP, sh0_cols), dtype=torch.int32, device=dev0)
     st = torch.cuda.current_stream(devices[0])
     k_iters = max(1, min(args.steps * Q, 4096) // KEEP)
     for _ in range(2):
-        sh0.respond_device(q_head.data_ptr(), KEEP, resp_k.data_ptr(), st.cuda_stream)
+        sh0.respond_device(q_k0.data_ptr(), KEEP, resp_k.data_ptr(), st.cuda_stream)
     torch.cuda.synchronize(devices[0])
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(st)
     for _ in range(k_iters):
-        sh0.respond_device(q_head.data_ptr(), KEEP, resp_k.data_ptr(), st.cuda_stream)
+        sh0.respond_device(q_k0.data_ptr(), KEEP, resp_k.data_ptr(), st.cuda_stream)
     k1.record(st)
     torch.cuda.synchronize(devices[0])
     ms_kernel = k0.elapsed_time(k1) / (k_iters * KEEP)
     launches += k_iters
-    parity["kernel_only_equals_cluster_result"] = bool(torch.equal(resp_k[:2], out0[:2, : plans[0]["col_count"]]))
-    assert parity["kernel_only_equals_cluster_result"]
+    if by_rows:
+        # the shards' own partial sums (each rank's kernel alone, its own stream) must add up to what the cluster call produced
+        acc = resp_k[:2].cpu().numpy().view(np.uint32).astype(np.uint64)
+        for r in range(1, n_gpus):
+            with torch.cuda.device(devices[r]):
+                part = torch.zeros((2, N), dtype=torch.int32, device=f"cuda:{devices[r]}")
+                srv.shard(r).respond_device(q_slices[r].data_ptr(), 2, part.data_ptr(), torch.cuda.current_stream(devices[r]).cuda_stream)
+                torch.cuda.synchronize(devices[r])
+                acc += part.cpu().numpy().view(np.uint32)
+        parity["kernel_only_partials_sum_to_cluster_result"] = bool(np.array_equal(acc & 0xFFFFFFFF, out0[:2].cpu().numpy().view(np.uint32)))
+        assert parity["kernel_only_partials_sum_to_cluster_result"]
+    else:
+        parity["kernel_only_equals_cluster_result"] = bool(torch.equal(resp_k[:2], out0[:2, : plans[0]["col_count"]]))
+        assert parity["kernel_only_equals_cluster_result"]
 
     # ---------------- e2e: the C ABI with HOST buffers, concurrent native callers of chpir_cluster_server_respond
     qlen, rlen = 8 + 4 * K, 8 + 4 * N
@@ -697,30 +726,55 @@ def run_b200(args):
         assert all(batched["parity"].values())
         parity["batched_tc_equals_gemv"] = True
 
-    # ---------------- roofline of the dominant kernel (rank 0's slice)
+    # ---------------- roofline of the dominant kernel (rank 0's shard)
     pk = peaks()
     pb0 = shard_infos[0]["packed_bytes"]
-    nc0 = plans[0]["col_count"]
-    streamed = pb0 + 4 * K + 4 * nc0  # bytes one query on this rank must move: resident packed slice + query + response
+    k_rank0 = srv.k_pitch if by_rows else K
+    streamed = pb0 + 4 * k_rank0 + 4 * sh0_cols  # bytes one query on this rank must move: resident packed shard + its query words + its result words
     cf = 3 if b in (9, 10) else (2 if b >= 11 else 4)
-    ref_layout = 4 * nc0 * (-(-K // cf)) + 4 * K + 4 * nc0
+    ref_layout = 4 * sh0_cols * (-(-k_rank0 // cf)) + 4 * k_rank0 + 4 * sh0_cols
     achieved = streamed / (ms_kernel * 1e-3) / 1e9
+    shard_desc = (f"GPU 0's row block ({k_rank0} of {K} rows x {N} columns)" if by_rows else "GPU 0's column slice") if n_gpus > 1 else "the whole matrix"
     roofline = {
-        "bound": "hbm", "kernel": f"respond_ring_kernel<{b},4> (persistent streaming u32 GEMV over K-major bit-packed D, cp.async.bulk smem ring), GPU 0's column slice",
+        "bound": "hbm", "kernel": f"respond_ring_kernel<{b},4> (persistent streaming u32 GEMV over K-major bit-packed D, cp.async.bulk smem ring), {shard_desc}",
         "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
         "queries_per_launch": KEEP, "bytes_per_launch": KEEP * streamed, "bytes_per_query": streamed, "bytes_per_query_reference_layout": ref_layout,
         "achieved_reference_layout_gbs": ref_layout / (ms_kernel * 1e-3) / 1e9, "us_per_launch": ms_kernel * 1e3 * KEEP, "launches_timed": k_iters,
-        "timed_region_ms": ms_kernel * KEEP * k_iters, "columns": nc0, "row_pitch_bytes": shard_infos[0]["row_pitch_bytes"],
+        "timed_region_ms": ms_kernel * KEEP * k_iters, "rows": k_rank0, "columns": sh0_cols, "row_pitch_bytes": shard_infos[0]["row_pitch_bytes"],
     }
     prof = os.path.join(ROOT, "profiles", "respond_traffic.json")
     if os.path.exists(prof):
         try:
-            tr = json.load(open(prof)).get(f"2^{args.log2n}/{args.arity}/n{n_gpus}")
+            tr = json.load(open(prof)).get(f"2^{args.log2n}/{args.arity}/n{n_gpus}" + ("/rows" if by_rows and n_gpus > 1 else ""))
             if tr:
                 roofline["traffic"] = tr["dram_bytes_per_query"] * KEEP if isinstance(tr, dict) else tr
                 roofline["traffic_source"] = tr.get("source") if isinstance(tr, dict) else "profiles/respond_traffic.json"
         except Exception:
             pass
+
+    # ---------------- the measured comparison SURVEY.md section 8e asks for: the same device-resident pass with respond cut by COLUMNS
+    # (every rank needs the whole query: NVLink all-gather by the copy engines, 118-column packed slivers at N = 8)
+    column_cut = None
+    if n_gpus > 1 and by_rows and not args.no_column_cut:
+        os.environ["CHPIR_CLUSTER_SHARD"] = "cols"
+        try:
+            srv_c, _, _, _, _, _ = make_cluster_server(cp, torch, cluster, args.log2n, args.arity, True)
+        finally:
+            os.environ.pop("CHPIR_CLUSTER_SHARD", None)
+        out_c = torch.zeros((Q, N), dtype=torch.int32, device=dev0)
+        c_steps = max(3, args.steps // 4)
+        srv_c.respond_device(q_ptrs, Q, out_c.data_ptr(), mode=cp.RESPOND_GEMV, repeats=3)
+        ms_c = srv_c.respond_device(q_ptrs, Q, out_c.data_ptr(), mode=cp.RESPOND_GEMV, repeats=c_steps)
+        sync_devices(torch, devices)
+        same = bool(torch.equal(out_c, out0))
+        ci = srv_c.get_info()
+        column_cut = {"value": c_steps * Q / (ms_c * 1e-3), "unit": "queries/s", "ms_per_step": ms_c / c_steps, "steps": c_steps,
+                      "respond_by_rows": ci["respond_by_rows"], "packed_bytes_max_rank": ci["packed_bytes_max_rank"],
+                      "row_cut_packed_bytes_max_rank": info["packed_bytes_max_rank"], "bytes_equal_row_cut": same}
+        parity["column_cut_bytes_equal_row_cut"] = same
+        assert same and ci["respond_by_rows"] == 0
+        srv_c.close()
+        del out_c, srv_c
 
     # ---------------- the other BASELINE.json configurations, each with its own parity flags (separate servers)
     del q_slices, q_head, out0, resp_k, sh0
@@ -749,13 +803,18 @@ def run_b200(args):
     line = {
         "metric": "server_respond_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args, b, K, N),
+        "config": workload_config(args, b, K, N, by_rows),
         "timing": {"device_ms_total": ms_total, "wall_ms_total": wall_total_ms, "first_pass_ms": ms1,
                    "how": "CUDA events on GPU 0's stream: t0 before the first byte moves on any GPU, t1 after GPU 0 has waited for the last columns of every GPU "
                           "(chpir_cluster_server_respond_device); wall clock of the same call beside it"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": Q * 4 * K, "d2h_bytes_per_step": Q * 4 * N, "threads": threads,
-                "api": "chpir_cluster_server_respond (C ABI, pinned host buffers): each caller DMAs its query's K/n slices to the n GPUs over their own PCIe "
-                       "links; concurrent callers are coalesced into shared launches (tensor-core limb GEMM from 6 queries up, GEMV below)",
+                "api": "chpir_cluster_server_respond (C ABI, page-locked host buffers from chpir_host_alloc): concurrent callers are coalesced; per batch "
+                       "every GPU fetches its K/n words of all member queries over its own PCIe link with one pull kernel, multiplies them with its rows "
+                       "of D (tensor-core limb GEMM from 6 queries up, GEMV below) and GPU 0 sums the partial responses; batches are pipelined "
+                       "(collect | PCIe | SMs)" if by_rows and n_gpus > 1 else
+                       "chpir_cluster_server_respond (C ABI, pinned host buffers): concurrent callers are coalesced into shared launches (tensor-core limb "
+                       "GEMM from 6 queries up, GEMV below)",
+                "pulled_queries": co["pulled_queries"],
                 "seconds": e2e_s, "coalesced_batches": co["batches"], "coalesced_tensor_core_batches": co["tc_batches"],
                 "mean_batch": co["queries"] / max(1, co["batches"]),
                 "single_caller_ms": single_ms, "single_caller_published_reference_ms": PUBLISHED["server_respond_2^20_3wise_ms"],
@@ -768,6 +827,8 @@ def run_b200(args):
         "setup": setup,
         "respond_us_per_query_kernel": ms_kernel * 1e3,
         "batched_respond_tc": batched,
+        "column_cut_comparison": column_cut,
+        "reshard_s": info["reshard_s"],
         "configs": configs,
         "parity": parity,
         "published_reference": PUBLISHED,
@@ -808,7 +869,8 @@ def config_legs(cp, torch, cluster, args, n_gpus):
         gi = srv.get_info()
         res = {"label": label, "K": K, "N": N, "mat_elem_bit_len": b, "queries_per_pass": nq, "ms_per_pass": ms, "queries_per_s": nq / (ms * 1e-3),
                "us_per_query": ms * 1e3 / nq, "packed_bytes_max_rank": gi["packed_bytes_max_rank"],
-               "hbm_gbs_per_gpu": (gi["packed_bytes_max_rank"] + 4 * K) * nq / (ms * 1e-3) / 1e9, "parity": par}
+               "hbm_gbs_per_gpu": (gi["packed_bytes_max_rank"] + 4 * (gi["k_pitch"] if gi["respond_by_rows"] else K)) * nq / (ms * 1e-3) / 1e9,
+               "respond_by_rows": gi["respond_by_rows"], "parity": par}
         if with_hint:
             res["setup"] = {"wall_s": wall, **{k: round(v, 6) for k, v in tmax.items()}, "gemm_kernel_ms": max(i["gemm_ms"] for i in infos),
                             "hint_gather_s": gi["hint_gather_s"], "hint_bytes": len(hint)}
@@ -832,7 +894,7 @@ def config_legs(cp, torch, cluster, args, n_gpus):
             del Ds
             free()
         if n_gpus == 8 and (args.log2n, args.arity) != (22, 3):
-            out["configs[4]"] = gemv_leg(22, 3, 32, not args.skip_hint, "2^22 entries, 3-wise: setup + respond column-sharded across 8 B200 (HBM-capacity sizing)")
+            out["configs[4]"] = gemv_leg(22, 3, 32, not args.skip_hint, "2^22 entries, 3-wise: setup + respond sharded across 8 B200 (HBM-capacity sizing)")
     except AssertionError:
         raise
     except Exception as ex:  # a secondary leg must never cost the headline line
@@ -857,6 +919,7 @@ def main():
     ap.add_argument("--no-e2e-setup", dest="e2e_setup", action="store_false", help="skip the Server::setup(seed, db) measurement from raw keys/values")
     ap.add_argument("--no-configs", dest="configs", action="store_false", help="skip the legs for the other BASELINE.json configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-column-cut", action="store_true", help="skip the column-cut comparison pass (N > 1)")
     ap.add_argument("--no-batch-tc", action="store_true", help="skip the tensor-core batched respond measurement")
     ap.add_argument("--batch-queries", type=int, default=128)
     ap.add_argument("--ref-queries-per-step", type=int, default=8, help="--impl reference: queries of each step the CPU arm answers (a bounded sample of the step)")

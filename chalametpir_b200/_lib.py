@@ -75,6 +75,10 @@ class ClusterServerInfo(C.Structure):
         ("batches", C.c_uint64),
         ("queries", C.c_uint64),
         ("tc_batches", C.c_uint64),
+        ("pulled_queries", C.c_uint64),
+        ("respond_by_rows", C.c_uint32),
+        ("reserved0", C.c_uint32),
+        ("reshard_s", C.c_double),
     ]
 
     def as_dict(self):

@@ -11,6 +11,8 @@
 #include <string>
 #include <thread>
 
+#include <unistd.h>
+
 #include "common.cuh"
 #include "host_encode.hpp"
 #include "host_pipe.cuh"
@@ -780,26 +782,46 @@ int chpir_server_save(chpir_server *srv, const char *path) {
   CHPIR_GUARD_BEGIN
   if (!srv || !path) return CHPIR_ERR_INVALID_ARGUMENT;
   CHPIR_CUDA(cudaSetDevice(srv->ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
-  std::unique_ptr<FILE, FileCloser> f(std::fopen(path, "wb"));
+  // written beside the target and renamed over it once complete and flushed: a crash never leaves a damaged file under `path`,
+  // and a good older snapshot survives a failed save
+  const std::string tmp = std::string(path) + ".tmp";
+  struct TmpGuard {
+    const std::string &name;
+    bool keep = false;
+    ~TmpGuard() {
+      if (!keep) std::remove(name.c_str());
+    }
+  } tmp_guard{tmp};
+  std::unique_ptr<FILE, FileCloser> f(std::fopen(tmp.c_str(), "wb"));
   if (!f) return CHPIR_ERR_IO_FAILED;
   SavedHeader h{};
   std::memcpy(h.magic, kSavedMagic, 8);
   h.version = 1, h.b = srv->b, h.K = srv->K, h.ncols = srv->ncols, h.col_begin = srv->col_begin;
   h.fpw = srv->layout.fpw, h.units = srv->layout.units, h.packed_bytes = srv->packed_bytes;
   h.reserved[0] = uint8_t(srv->layout.tight);  // 1 = tight rows (PackedLayout); 0 also in files written before they existed
+  if (srv->shard_k_total) {                     // a row block of a cluster's matrix: the rows of the whole matrix, 48 bits LE
+    h.reserved[1] = 1;
+    for (int i = 0; i < 6; i++) h.reserved[2 + i] = uint8_t(srv->shard_k_total >> (8 * i));
+  }
   if (std::fwrite(&h, sizeof h, 1, f.get()) != 1) return CHPIR_ERR_IO_FAILED;
   PinnedPair buf;
   if (cudaMallocHost(&buf.p[0], kIoChunk) != cudaSuccess) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
   uint64_t sum = 0xcbf29ce484222325ull;
-  std::lock_guard<std::mutex> g(srv->ctx->mu);
-  for (uint64_t off = 0; off < srv->packed_bytes; off += kIoChunk) {
-    const size_t n = size_t(std::min<uint64_t>(kIoChunk, srv->packed_bytes - off));
-    CHPIR_CUDA(cudaMemcpy(buf.p[0], srv->d_packed + off, n, cudaMemcpyDeviceToHost), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-    sum = fnv1a64(sum, buf.p[0], n);
-    if (std::fwrite(buf.p[0], 1, n, f.get()) != n) return CHPIR_ERR_IO_FAILED;
+  {
+    std::lock_guard<std::mutex> g(srv->ctx->mu);
+    for (uint64_t off = 0; off < srv->packed_bytes; off += kIoChunk) {
+      const size_t n = size_t(std::min<uint64_t>(kIoChunk, srv->packed_bytes - off));
+      CHPIR_CUDA(cudaMemcpy(buf.p[0], srv->d_packed + off, n, cudaMemcpyDeviceToHost), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      sum = fnv1a64(sum, buf.p[0], n);
+      if (std::fwrite(buf.p[0], 1, n, f.get()) != n) return CHPIR_ERR_IO_FAILED;
+    }
   }
   h.checksum = sum;
   if (std::fseek(f.get(), 0, SEEK_SET) != 0 || std::fwrite(&h, sizeof h, 1, f.get()) != 1 || std::fflush(f.get()) != 0) return CHPIR_ERR_IO_FAILED;
+  if (fsync(fileno(f.get())) != 0) return CHPIR_ERR_IO_FAILED;
+  f.reset();
+  if (std::rename(tmp.c_str(), path) != 0) return CHPIR_ERR_IO_FAILED;
+  tmp_guard.keep = true;
   return CHPIR_OK;
   CHPIR_GUARD_END
 }
@@ -816,7 +838,14 @@ int chpir_server_load(chpir_ctx *ctx, const char *path, const chpir_setup_opts *
   SavedHeader h{};
   if (std::fread(&h, sizeof h, 1, f.get()) != 1) return CHPIR_ERR_INVALID_SAVED_SERVER;
   if (std::memcmp(h.magic, kSavedMagic, 8) != 0 || h.version != 1) return CHPIR_ERR_INVALID_SAVED_SERVER;
-  if (validate_bits(h.b) != CHPIR_OK || h.K == 0 || h.ncols == 0) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  // K is bounded before it meets any multiplication (TMA coordinates are int32 anyway): a hostile header cannot wrap the size checks
+  if (validate_bits(h.b) != CHPIR_OK || h.K == 0 || h.K > 0x7fffffffull || h.ncols == 0 || h.reserved[0] > 1 || h.reserved[1] > 1)
+    return CHPIR_ERR_INVALID_SAVED_SERVER;
+  uint64_t k_total = 0;
+  if (h.reserved[1]) {
+    for (int i = 0; i < 6; i++) k_total |= uint64_t(h.reserved[2 + i]) << (8 * i);
+    if (k_total == 0 || k_total > 0x7fffffffull) return CHPIR_ERR_INVALID_SAVED_SERVER;
+  }
   // the file's own row layout (not whatever make_layout would choose today): the kernels read either
   PackedLayout L{};
   if (!make_layout_explicit(h.b, h.ncols, h.units, h.reserved[0], &L)) return CHPIR_ERR_INVALID_SAVED_SERVER;
@@ -827,6 +856,7 @@ int chpir_server_load(chpir_ctx *ctx, const char *path, const chpir_setup_opts *
   std::unique_ptr<chpir_server> srv(new chpir_server());
   srv->ctx = ctx, srv->K = h.K, srv->ncols = h.ncols, srv->col_begin = h.col_begin, srv->b = h.b;
   srv->layout = L, srv->packed_bytes = h.packed_bytes;
+  srv->shard_k_total = k_total;
   {
     void *p = nullptr;
     CHPIR_CUDA(cudaMalloc(&p, L.alloc_bytes(h.K)), CHPIR_ERR_CUDA_ALLOCATION_FAILED);

@@ -1,18 +1,26 @@
-// cluster.cu -- the column-sharded server on 1..8 GPUs of ONE process, behind the reference's two calls.
+// cluster.cu -- the sharded server on 1..8 GPUs of ONE process, behind the reference's two calls.
 //
 // The reference's public surface is `Server::setup(seed, db)` (chalametpir_server/src/server.rs:103) and `Server::respond(&self, query)`
 // (server.rs:184); neither can grow a rank argument, so the sharding of north_star (3) lives behind the handle: this translation
 // unit owns one chpir_ctx per GPU, the peer mappings between them, the per-GPU streams and the NCCL communicators, and exposes
-// chpir_cluster_server_{setup*,respond*} (include/chalamet_b200.h).  Column slices need no cross-rank arithmetic
-// (M[:, n0:n1] = A.D[:, n0:n1], resp[n0:n1] = q.D[:, n0:n1]); what has to move is
-//   * the query: every rank needs all K words of it.  Rank r ingests words [k0_r, k0_r + kn_r) over ITS OWN PCIe link (8 links in
-//     parallel) and the other ranks read them from its HBM over NVLink -- inside the limb-split kernel that builds the tensor-core
-//     operand (gather_q_kernel<true>: peer loads fused with the split) or, for the streaming GEMV, with copy-engine peer copies that
-//     run beside the previous chunk's kernels and use no SM;
-//   * the response: every rank writes its columns straight into the caller-visible row (strided D2H / peer copy), so there is no
-//     gather step at all;
-//   * the hint, once per setup: the slices are gathered on rank 0 over NCCL (ncclSend/ncclRecv, communicators from ncclCommInitAll)
-//     and downloaded as one wire-format matrix.
+// chpir_cluster_server_{setup*,respond*} (include/chalamet_b200.h).
+//
+// Two cuts of D = K x N are used, each where it moves the fewest bytes:
+//   * setup (hint M = A.D): COLUMN slices.  M[:, n0:n1] = A.D[:, n0:n1] needs no cross-rank arithmetic; the
+//     slices of the hint are gathered on rank 0 over NCCL (ncclSend/ncclRecv, communicators from ncclCommInitAll) and downloaded as
+//     one wire-format matrix.
+//   * respond (resp = q.D): ROW blocks (the K-sharded alternative of SURVEY.md section 8e, default for n > 1).  Rank r keeps rows
+//     [k0_r, k0_r + kn_r) of D at full width and needs only words [k0_r, k0_r + kn_r) of a query -- exactly the words it ingests over
+//     ITS OWN PCIe link.  No query word ever crosses NVLink; what crosses is each rank's N-word partial sum, added on rank 0 by one
+//     small kernel that reads the peers' partials (exact: addition mod 2^32 is order independent, matrix.rs:328-485).  Full-width rows
+//     also keep the packed row pitch of the one-GPU layout (1088 B at N = 940) instead of 118-column slivers padded to 144 B.
+//     After the hint gather every rank re-cuts its share of D (peer copies / one more upload) and frees the column slice.
+//   * CHPIR_CLUSTER_SHARD=cols keeps the column cut for respond as well (the round-1 design, kept as the measured comparison): every
+//     rank then needs the WHOLE query, gathered from the ranks that ingested its slices by NVLink peer reads fused with the limb
+//     split (gather_q_kernel<true>) or by copy-engine peer copies (GEMV route), and writes its columns straight into the result row.
+//   * ingest: a query buffer in page-locked memory (chpir_host_alloc, or anything cudaHostRegister'ed) is read by the GPUs
+//     themselves -- one pull kernel per GPU per coalesced batch fetches that GPU's words of up to 128 queries over its PCIe link --
+//     instead of one DMA call per query and GPU; pageable buffers take the per-query DMA route.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -33,7 +41,8 @@ namespace {
 constexpr uint32_t kMaxRanks = 16;
 constexpr uint32_t kMaxBatch = Coalescer::kMaxBatch;       // queries per coalesced batch = one M tile of the limb GEMM
 constexpr uint32_t kTcFrom = Coalescer::kTensorCoreFrom;   // below this many queries the streaming GEMV is cheaper
-constexpr uint32_t kGemvChunk = 32;                        // device-resident GEMV path: queries per all-gather / launch
+constexpr uint32_t kGemvChunk = 32;                        // device-resident GEMV path, column cut: queries per all-gather / launch
+constexpr uint32_t kSlots = 3;                             // coalescing slots: one collecting callers, one on PCIe, one on the SMs
 
 // ---- NCCL, resolved at run time (the library has no link-time dependency on it: single-GPU users never load it) -----------------
 struct NcclApi {
@@ -200,6 +209,103 @@ int launch_gather(bool split, const SrcTable &src, uint32_t rows, uint64_t ks, u
   return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
 }
 
+
+// ---- ingest: the GPU fetches its words of a batch of queries from page-locked host memory ------------------------------------------
+struct PullTable {
+  const uint8_t *src[kMaxBatch];  // query i's wire bytes (8-byte header + K u32), device-readable host memory; nullptr = not this way
+};
+
+template <class V>
+__device__ __forceinline__ void pull_row(const uint8_t *s, uint32_t *d, uint64_t words, uint64_t tid, uint64_t stride) {
+  constexpr uint64_t W = sizeof(V) / 4;
+  constexpr int kUnr = 4;
+  const V *sv = reinterpret_cast<const V *>(s);
+  V *dv = reinterpret_cast<V *>(d);
+  const uint64_t nv = words / W;
+  for (uint64_t i = tid; i < nv; i += stride * kUnr) {
+    V v[kUnr];
+#pragma unroll
+    for (int u = 0; u < kUnr; u++)
+      if (i + u * stride < nv) v[u] = __ldcv(sv + i + u * stride);  // host memory: never served from a cache line of an earlier batch
+#pragma unroll
+    for (int u = 0; u < kUnr; u++)
+      if (i + u * stride < nv) dv[i + u * stride] = v[u];
+  }
+  for (uint64_t i = nv * W + tid; i < words; i += stride) d[i] = __ldcv(reinterpret_cast<const uint32_t *>(s) + i);
+}
+
+// grid (x, row): words [0, words) of row `row` = bytes [byte_off, byte_off + 4 * words) of t.src[row]  ->  dst + row * ks.
+// byte_off = 8 + 4 * k0 is a multiple of 8, so the widest load the source allows depends only on the caller's buffer alignment;
+// 4-byte alignment of the buffer is the caller-side condition for taking this route at all.
+__global__ void __launch_bounds__(256) pull_slices_kernel(PullTable t, uint64_t byte_off, uint64_t words, uint64_t ks, uint32_t *__restrict__ dst) {
+  const uint8_t *s = t.src[blockIdx.y];
+  if (!s) return;
+  s += byte_off;
+  uint32_t *d = dst + uint64_t(blockIdx.y) * ks;
+  const uint64_t tid = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x, stride = uint64_t(gridDim.x) * blockDim.x;
+  const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(s) & 15u);
+  if (a == 0)
+    pull_row<uint4>(s, d, words, tid, stride);
+  else if ((a & 7u) == 0)
+    pull_row<uint2>(s, d, words, tid, stride);
+  else
+    pull_row<uint32_t>(s, d, words, tid, stride);
+}
+
+int launch_pull(const PullTable &t, uint32_t rows, uint64_t k0, uint64_t kn, uint64_t ks, uint32_t *dst, cudaStream_t st) {
+  if (rows == 0 || kn == 0) return CHPIR_OK;
+  const uint64_t per_block = 256ull * 4 * 4;  // words one block moves per sweep (16-byte loads, 4 in flight per thread)
+  const unsigned gx = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((kn + per_block - 1) / per_block, 64)));
+  pull_slices_kernel<<<dim3(gx, rows), 256, 0, st>>>(t, 8 + 4 * k0, kn, ks, dst);
+  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+// ---- row cut: rank 0 adds the ranks' partial responses -------------------------------------------------------------------------------
+struct PartTable {
+  const uint32_t *p[kMaxRanks];  // p[d] = rank d's partial sums (words u32), a peer-mapped address for d != 0
+};
+
+template <class V>
+__global__ void __launch_bounds__(256) reduce_parts_kernel(PartTable t, uint32_t n, uint64_t count, V *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x) {
+    V acc = reinterpret_cast<const V *>(t.p[0])[i];
+    for (uint32_t d = 1; d < n; d++) {
+      const V v = reinterpret_cast<const V *>(t.p[d])[i];
+      if constexpr (sizeof(V) == 16) {
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      } else {
+        acc += v;
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+int launch_reduce(const PartTable &t, uint32_t n, uint64_t words, uint32_t *out, int sm_count, cudaStream_t st) {
+  if (words == 0) return CHPIR_OK;
+  bool vec = words % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  for (uint32_t d = 0; d < n; d++) vec = vec && (reinterpret_cast<uintptr_t>(t.p[d]) & 15u) == 0;
+  const uint64_t count = vec ? words / 4 : words;
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((count + 255) / 256, uint64_t(sm_count) * 4)));
+  if (vec)
+    reduce_parts_kernel<uint4><<<grid, 256, 0, st>>>(t, n, count, reinterpret_cast<uint4 *>(out));
+  else
+    reduce_parts_kernel<uint32_t><<<grid, 256, 0, st>>>(t, n, count, out);
+  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+}
+
+// Is [p, p + bytes) page-locked host memory a kernel may read?  The library's own allocations are known; anything else is asked of
+// the driver (cudaHostRegister'ed or another allocator's pinned memory).
+bool device_readable_host(const void *p, size_t bytes) {
+  if (pinned_registry_contains(p, bytes)) return true;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost && at.devicePointer == p;
+}
+
 }  // namespace
 }  // namespace chpir
 
@@ -244,25 +350,29 @@ namespace {
 struct Rank {
   int dev = 0;
   chpir_ctx *ctx = nullptr;
-  chpir_server *srv = nullptr;
+  chpir_server *srv = nullptr;  // the shard respond runs on: the row block (row cut) or the column slice (column cut, n = 1)
+  chpir_server *col = nullptr;  // row cut, during setup only: the column slice the hint was computed on (freed after the gather)
   Plan pl{};
   cudaStream_t compute = nullptr, gather = nullptr;
   // device-resident path (chpir_cluster_server_respond_device): double-buffered scratch, allocated on first use
   uint32_t *q_full[2] = {nullptr, nullptr};
-  uint32_t *resp[2] = {nullptr, nullptr};
+  uint32_t *resp[2] = {nullptr, nullptr};  // column cut: this rank's columns of a chunk; row cut: its partial sums of a whole pass
   uint32_t q_rows = 0, resp_rows = 0;
-  cudaEvent_t gathered[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr};
+  cudaEvent_t gathered[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr}, reduced[2] = {nullptr, nullptr};
   uint32_t tc_buf = 0;  // next buffer of this rank's GEMM operand ring
 };
 
-// One coalescing slot: the members' slices on every rank, every rank's response columns, and the pinned rows they land in.
+// One coalescing slot: the members' slices on every rank, every rank's share of the result, and the pinned rows they land in.
 struct CBatch {
   uint32_t *q_slice[kMaxRanks] = {};  // [kMaxBatch][ks] on rank d
-  uint32_t *q_full[kMaxRanks] = {};   // [gemv_rows][K] on rank d: whole queries for the GEMV route
-  uint32_t *resp[kMaxRanks] = {};     // [kMaxBatch][nc_d] on rank d
+  uint32_t *q_full[kMaxRanks] = {};   // column cut: [gemv_rows][K] on rank d, whole queries for the GEMV route
+  uint32_t *resp[kMaxRanks] = {};     // column cut: [kMaxBatch][nc_d], rank d's columns; row cut: [kMaxBatch][N], rank d's partial sums
+  uint32_t *resp0 = nullptr;          // row cut: [kMaxBatch][N] on rank 0, the sum of the partials
   cudaStream_t copy[kMaxRanks] = {};
   cudaEvent_t uploaded[kMaxRanks] = {}, done[kMaxRanks] = {};
   uint32_t *h_resp = nullptr;  // pinned [kMaxBatch][N]
+  PullTable pull{};            // members whose query the GPUs fetch themselves (page-locked source)
+  uint32_t n_pull = 0;
   uint32_t count = 0, issued = 0, picked = 0;
   bool closed = false, finished = false;
   int rc = CHPIR_OK;
@@ -276,23 +386,25 @@ struct chpir_cluster_server {
   uint64_t K = 0, ks = 0;
   uint32_t N = 0, b = 0, lwe = 0;
   std::vector<Rank> r;
+  bool rows = false;        // respond runs on row blocks of D (see the head of this file); false: column slices
   bool tc = false;          // every rank keeps its limb planes: batches of >= kTcFrom queries take the tensor-core route
-  uint32_t gemv_rows = 0;   // capacity of CBatch::q_full
-  // coalescer (n > 1; a one-GPU cluster delegates to the shard's own)
+  uint32_t gemv_rows = 0;   // queries one GEMV-route batch may hold (column cut: capacity of CBatch::q_full)
+  // coalescer (n > 1; a one-GPU cluster delegates to the shard's own).  A batch passes two stages, each held by one batch at a time:
+  // ingest (its queries cross PCIe) and exec (kernels + result download); a third slot collects callers meanwhile.
   std::mutex mu;
   std::condition_variable cv;
-  std::mutex exec_mu;  // one batch on the GPUs at a time
-  CBatch cb[2];
+  std::mutex ingest_mu, exec_mu;
+  CBatch cb[kSlots];
   int open = 0;
   bool co_ready = false;
-  uint64_t batches = 0, queries = 0, tc_batches = 0;
+  uint64_t batches = 0, queries = 0, tc_batches = 0, pulled = 0;
   // chpir_cluster_server_respond_batch
   std::mutex batch_mu;
   std::unique_ptr<CBatch> bb;
   // device-resident path
   std::mutex dev_mu;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
-  double setup_total_s = 0, hint_gather_s = 0;
+  double setup_total_s = 0, hint_gather_s = 0, reshard_s = 0;
   uint32_t gather_uses_nccl = 0;
 
   void free_batch(CBatch &B) {
@@ -308,6 +420,10 @@ struct chpir_cluster_server {
       if (B.q_full[d]) cudaFree(B.q_full[d]);
       if (B.resp[d]) cudaFree(B.resp[d]);
     }
+    if (B.resp0) {
+      cudaSetDevice(r[0].dev);
+      cudaFree(B.resp0);
+    }
     if (B.h_resp) cudaFreeHost(B.h_resp);
     B = CBatch{};
   }
@@ -315,12 +431,22 @@ struct chpir_cluster_server {
   int init_batch(CBatch &B) {
     for (uint32_t d = 0; d < n; d++) {
       if (cudaSetDevice(r[d].dev) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+      const size_t resp_words = size_t(kMaxBatch) * (rows ? N : r[d].pl.nc);
       if (cudaMalloc(&B.q_slice[d], size_t(kMaxBatch) * ks * 4) != cudaSuccess ||
-          cudaMalloc(&B.q_full[d], size_t(gemv_rows) * K * 4) != cudaSuccess ||
-          cudaMalloc(&B.resp[d], size_t(kMaxBatch) * r[d].pl.nc * 4) != cudaSuccess ||
+          (!rows && cudaMalloc(&B.q_full[d], size_t(gemv_rows) * K * 4) != cudaSuccess) ||
+          cudaMalloc(&B.resp[d], resp_words * 4) != cudaSuccess ||
           cudaStreamCreateWithFlags(&B.copy[d], cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&B.uploaded[d], cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&B.done[d], cudaEventDisableTiming) != cudaSuccess) {
+        set_last_cuda_error(cudaGetLastError(), "cluster respond batch allocation");
+        return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+      }
+      // the words behind a short last slice (and whole rows of ranks that ingest nothing) face zero rows of D, but must be defined
+      if (cudaMemset(B.q_slice[d], 0, size_t(kMaxBatch) * ks * 4) != cudaSuccess) return CHPIR_ERR_CUDA_TRANSFER_FAILED;
+    }
+    if (rows) {
+      if (cudaSetDevice(r[0].dev) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+      if (cudaMalloc(&B.resp0, size_t(kMaxBatch) * N * 4) != cudaSuccess) {
         set_last_cuda_error(cudaGetLastError(), "cluster respond batch allocation");
         return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
       }
@@ -349,10 +475,12 @@ struct chpir_cluster_server {
         if (r[d].resp[p]) cudaFree(r[d].resp[p]);
         if (r[d].gathered[p]) cudaEventDestroy(r[d].gathered[p]);
         if (r[d].computed[p]) cudaEventDestroy(r[d].computed[p]);
+        if (r[d].reduced[p]) cudaEventDestroy(r[d].reduced[p]);
       }
       if (r[d].compute) cudaStreamDestroy(r[d].compute);
       if (r[d].gather) cudaStreamDestroy(r[d].gather);
       if (r[d].srv) chpir_server_destroy(r[d].srv);
+      if (r[d].col) chpir_server_destroy(r[d].col);
     }
     if (!r.empty()) cudaSetDevice(r[0].dev);
     if (t0) cudaEventDestroy(t0);
@@ -372,11 +500,8 @@ namespace {
     return CHPIR_ERR_INVALID_ARGUMENT;       \
   }
 
-// Streams, events and (for n > 1) the coalescing slots, once every shard exists.
-int finish_server(chpir_cluster_server *S) {
-  S->tc = true;
-  for (uint32_t d = 0; d < S->n; d++) S->tc = S->tc && S->r[d].srv->gemm != nullptr;
-  S->gemv_rows = S->tc ? kTcFrom - 1 : kMaxBatch;
+// Streams and events of every rank: needed by the hint gather, so they come first.
+int make_streams(chpir_cluster_server *S) {
   for (uint32_t d = 0; d < S->n; d++) {
     Rank &R = S->r[d];
     CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
@@ -385,11 +510,20 @@ int finish_server(chpir_cluster_server *S) {
     for (int p = 0; p < 2; p++) {
       CHPIR_CUDA(cudaEventCreateWithFlags(&R.gathered[p], cudaEventDisableTiming), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
       CHPIR_CUDA(cudaEventCreateWithFlags(&R.computed[p], cudaEventDisableTiming), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+      CHPIR_CUDA(cudaEventCreateWithFlags(&R.reduced[p], cudaEventDisableTiming), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
     }
   }
   CHPIR_CUDA(cudaSetDevice(S->r[0].dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
   CHPIR_CUDA(cudaEventCreate(&S->t0), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
   CHPIR_CUDA(cudaEventCreate(&S->t1), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+  return CHPIR_OK;
+}
+
+// The coalescing slots (n > 1), once the shards respond runs on exist.
+int make_slots(chpir_cluster_server *S) {
+  S->tc = true;
+  for (uint32_t d = 0; d < S->n; d++) S->tc = S->tc && S->r[d].srv->gemm != nullptr;
+  S->gemv_rows = S->rows ? kMaxBatch : (S->tc ? kTcFrom - 1 : kMaxBatch);
   if (S->n > 1) {
     for (CBatch &B : S->cb)
       if (int rc = S->init_batch(B); rc != CHPIR_OK) return rc;
@@ -398,18 +532,10 @@ int finish_server(chpir_cluster_server *S) {
   return CHPIR_OK;
 }
 
-// The GPU half of one batch of `nq` queries whose slices sit in B.q_slice: every rank pulls the slices it did not ingest, answers
-// for its columns and writes them into the pinned rows; returns when all ranks have.
-int run_batch(chpir_cluster_server *S, CBatch &B, uint32_t nq, bool *used_tc) {
-  const bool tc = S->tc && nq >= kTcFrom;
-  if (used_tc) *used_tc = tc;
-  if (!tc && nq > S->gemv_rows) return CHPIR_ERR_INVALID_ARGUMENT;
+// Column cut: every rank pulls the slices it did not ingest, answers for its columns and writes them into the pinned rows.
+int enqueue_batch_cols(chpir_cluster_server *S, CBatch &B, uint32_t nq, bool tc) {
   SrcTable src{};
   for (uint32_t d = 0; d < S->n; d++) src.p[d] = B.q_slice[d];
-  for (uint32_t d = 0; d < S->n; d++) {
-    CHPIR_CUDA(cudaSetDevice(S->r[d].dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
-    CHPIR_CUDA(cudaEventRecord(B.uploaded[d], B.copy[d]), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
-  }
   int rc = CHPIR_OK;
   for (uint32_t d = 0; d < S->n && rc == CHPIR_OK; d++) {
     Rank &R = S->r[d];
@@ -435,19 +561,65 @@ int run_batch(chpir_cluster_server *S, CBatch &B, uint32_t nq, bool *used_tc) {
                CHPIR_ERR_CUDA_TRANSFER_FAILED);
     CHPIR_CUDA(cudaEventRecord(B.done[d], st), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
   }
-  // wait for every rank that was given work, also on the error path: the slot must be quiet before it is reused
-  for (uint32_t d = 0; d < S->n; d++) {
-    cudaSetDevice(S->r[d].dev);
-    const cudaError_t e = cudaStreamSynchronize(S->r[d].compute);
-    if (e != cudaSuccess && rc == CHPIR_OK) {
-      set_last_cuda_error(e, "cluster respond");
-      rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
-    }
-  }
   return rc;
 }
 
-// A member's (or the batch call's) upload of one query: its K/n words go to each rank over that rank's own PCIe link.
+// Row cut: every rank multiplies the words it ingested itself with its rows of D (no query word crosses NVLink); rank 0 adds the n
+// partial sums and downloads the finished rows.
+int enqueue_batch_rows(chpir_cluster_server *S, CBatch &B, uint32_t nq, bool tc) {
+  int rc = CHPIR_OK;
+  PartTable parts{};
+  for (uint32_t d = 0; d < S->n && rc == CHPIR_OK; d++) {
+    Rank &R = S->r[d];
+    chpir_server *sv = R.srv;
+    parts.p[d] = B.resp[d];
+    CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    cudaStream_t st = R.compute;
+    CHPIR_CUDA(cudaStreamWaitEvent(st, B.uploaded[d], 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+    CHPIR_CUDA(cudaMemsetAsync(B.resp[d], 0, size_t(nq) * S->N * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    if (tc) {
+      std::lock_guard<std::mutex> g(sv->gemm_mu);
+      const int buf = int(R.tc_buf++ & 1);
+      if ((rc = gemm_tc_buf_acquire(sv->gemm, buf, st)) != CHPIR_OK) break;
+      if ((rc = gemm_tc_load_panel_u32(sv->gemm, buf, B.q_slice[d], nq, st)) != CHPIR_OK) break;
+      if ((rc = gemm_tc_panel(sv->gemm, buf, nq, B.resp[d], st)) != CHPIR_OK) break;
+      if ((rc = gemm_tc_buf_release(sv->gemm, buf, st)) != CHPIR_OK) break;
+    } else {
+      if ((rc = launch_respond(sv->d_packed, sv->layout, sv->K, sv->plan, B.q_slice[d], B.resp[d], nq, st)) != CHPIR_OK) break;
+    }
+    CHPIR_CUDA(cudaEventRecord(B.done[d], st), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+  }
+  if (rc != CHPIR_OK) return rc;
+  Rank &R0 = S->r[0];
+  CHPIR_CUDA(cudaSetDevice(R0.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  for (uint32_t d = 1; d < S->n; d++) CHPIR_CUDA(cudaStreamWaitEvent(R0.compute, B.done[d], 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+  if ((rc = launch_reduce(parts, S->n, uint64_t(nq) * S->N, B.resp0, R0.ctx->sm_count, R0.compute)) != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemcpyAsync(B.h_resp, B.resp0, size_t(nq) * S->N * 4, cudaMemcpyDeviceToHost, R0.compute), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  return CHPIR_OK;
+}
+
+// The GPU half of one batch of `nq` queries whose slices are on their way into B.q_slice (stream-ordered behind B.uploaded[d]);
+// returns when the pinned rows hold the responses.
+int run_batch(chpir_cluster_server *S, CBatch &B, uint32_t nq, bool *used_tc) {
+  const bool tc = S->tc && nq >= kTcFrom;
+  if (used_tc) *used_tc = tc;
+  if (!tc && nq > S->gemv_rows) return CHPIR_ERR_INVALID_ARGUMENT;
+  const int rc = S->rows ? enqueue_batch_rows(S, B, nq, tc) : enqueue_batch_cols(S, B, nq, tc);
+  // wait for every rank that was given work, also on the error path: the slot must be quiet before it is reused
+  int out = rc;
+  for (uint32_t d = 0; d < S->n; d++) {
+    cudaSetDevice(S->r[d].dev);
+    const cudaError_t e = cudaStreamSynchronize(S->r[d].compute);
+    if (e != cudaSuccess && out == CHPIR_OK) {
+      set_last_cuda_error(e, "cluster respond");
+      out = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+    }
+  }
+  return out;
+}
+
+// A member's (or the batch call's) upload of one query from pageable memory: its K/n words go to each rank over that rank's own
+// PCIe link, one DMA per rank.
 int upload_query(chpir_cluster_server *S, CBatch &B, uint32_t row, const uint8_t *query) {
   for (uint32_t d = 0; d < S->n; d++) {
     const Plan &pl = S->r[d].pl;
@@ -461,8 +633,39 @@ int upload_query(chpir_cluster_server *S, CBatch &B, uint32_t row, const uint8_t
   return CHPIR_OK;
 }
 
-// One caller's share of a coalesced batch: the protocol of api.cu's respond_coalesced with n GPUs behind it.
-int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, uint8_t *resp_out) {
+// Can the GPUs fetch this query themselves?  (page-locked, device-readable, 4-byte aligned; CHPIR_CLUSTER_INGEST=dma turns it off)
+bool pullable(const uint8_t *query, size_t len) {
+  return !env_is("CHPIR_CLUSTER_INGEST", "dma") && (reinterpret_cast<uintptr_t>(query) & 3u) == 0 && device_readable_host(query, len);
+}
+
+// Ingest stage of a closed batch: one pull kernel per GPU for the members that registered a page-locked source, then the PCIe
+// stage is over when every copy stream (pulls and the members' own DMAs) has drained; B.uploaded[d] marks that point for the kernels.
+int ingest_batch(chpir_cluster_server *S, CBatch &B, uint32_t nq) {
+  int rc = CHPIR_OK;
+  for (uint32_t d = 0; d < S->n; d++) {
+    const Plan &pl = S->r[d].pl;
+    if (cudaSetDevice(S->r[d].dev) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+    if (B.n_pull && rc == CHPIR_OK) rc = launch_pull(B.pull, nq, pl.k0, pl.kn, S->ks, B.q_slice[d], B.copy[d]);
+    if (cudaEventRecord(B.uploaded[d], B.copy[d]) != cudaSuccess && rc == CHPIR_OK) rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+  }
+  for (uint32_t d = 0; d < S->n; d++) {
+    cudaSetDevice(S->r[d].dev);
+    const cudaError_t e = cudaStreamSynchronize(B.copy[d]);
+    if (e != cudaSuccess && rc == CHPIR_OK) {
+      set_last_cuda_error(e, "cluster respond: query ingest");
+      rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+    }
+  }
+  return rc;
+}
+
+// One caller's share of a coalesced batch: the protocol of api.cu's respond_coalesced with n GPUs behind it and two pipeline
+// stages.  The first caller of a batch is its leader.  It waits for the ingest stage -- that wait IS the batching window: an idle
+// server means a batch of one and no added latency, a busy one means everybody who arrives while the previous batch is crossing
+// PCIe shares this one -- closes the batch, moves its queries, waits for the exec stage and runs the kernels while the next batch
+// is already being ingested.
+int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t query_len, uint8_t *resp_out) {
+  const bool pull = pullable(query, query_len);
   CBatch *B = nullptr;
   uint32_t row = 0;
   {
@@ -470,9 +673,11 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, uint8_t *re
     S->cv.wait(lk, [&] { return !S->cb[S->open].closed && S->cb[S->open].count < kMaxBatch; });
     B = &S->cb[S->open];
     row = B->count++;
+    B->pull.src[row] = pull ? query : nullptr;
+    B->n_pull += pull ? 1 : 0;
   }
   const bool leader = row == 0;
-  const int up = upload_query(S, *B, row, query);
+  const int up = pull ? CHPIR_OK : upload_query(S, *B, row, query);
   {
     std::lock_guard<std::mutex> lk(S->mu);
     B->issued++;
@@ -480,7 +685,7 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, uint8_t *re
   }
   S->cv.notify_all();
   if (leader) {
-    std::lock_guard<std::mutex> ex(S->exec_mu);  // the previous batch leaves the GPUs: everyone who arrived meanwhile is in this one
+    std::unique_lock<std::mutex> ingest(S->ingest_mu);
     uint32_t nq = 0;
     int rc = CHPIR_OK;
     {
@@ -489,22 +694,22 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, uint8_t *re
       nq = B->count;
       S->cv.wait(lk, [&] { return B->issued == nq; });
       rc = B->rc;
-      S->cv.wait(lk, [&] { return S->cb[S->open ^ 1].count == 0 && !S->cb[S->open ^ 1].closed; });
-      S->open ^= 1;
+      const int next = (S->open + 1) % int(kSlots);
+      S->cv.wait(lk, [&] { return S->cb[next].count == 0 && !S->cb[next].closed; });
+      S->open = next;
     }
     S->cv.notify_all();
+    const int in = ingest_batch(S, *B, nq);  // also on the error path: the members' DMAs must have drained
+    if (rc == CHPIR_OK) rc = in;
     bool tc = false;
-    if (rc == CHPIR_OK) {
-      rc = run_batch(S, *B, nq, &tc);
-    } else {
-      for (uint32_t d = 0; d < S->n; d++) {
-        cudaSetDevice(S->r[d].dev);
-        cudaStreamSynchronize(B->copy[d]);
-      }
+    {
+      std::lock_guard<std::mutex> ex(S->exec_mu);
+      ingest.unlock();
+      if (rc == CHPIR_OK) rc = run_batch(S, *B, nq, &tc);
     }
     {
       std::lock_guard<std::mutex> lk(S->mu);
-      S->batches++, S->queries += nq, S->tc_batches += tc ? 1 : 0;
+      S->batches++, S->queries += nq, S->tc_batches += tc ? 1 : 0, S->pulled += B->n_pull;
       B->rc = rc;
       B->finished = true;
     }
@@ -524,7 +729,7 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, uint8_t *re
   {
     std::lock_guard<std::mutex> lk(S->mu);
     if (++B->picked == B->count) {  // last one out resets the slot
-      B->count = B->issued = B->picked = 0;
+      B->count = B->issued = B->picked = B->n_pull = 0;
       B->closed = B->finished = false;
       B->rc = CHPIR_OK;
     }
@@ -607,40 +812,6 @@ int check_opts(const chpir_cluster *cl, const chpir_setup_opts *opts, chpir_setu
   return CHPIR_OK;
 }
 
-// Common tail of every setup flavour: per-rank servers exist in S->r[*].srv.
-int complete_setup(chpir_cluster_server *S, const chpir_setup_opts &o, uint8_t *hint_out, size_t hint_cap, size_t *hint_len) {
-  for (uint32_t d = 0; d < S->n; d++) S->r[d].srv->col_begin = S->r[d].pl.c0;  // logical position of a compact slice
-  if (int rc = finish_server(S); rc != CHPIR_OK) return rc;
-  if (hint_len) *hint_len = 0;
-  if (!o.skip_hint) {
-    if (int rc = gather_hint(S, hint_out, hint_cap, hint_len); rc != CHPIR_OK) return rc;
-  }
-  return CHPIR_OK;
-}
-
-chpir_cluster_server *new_server(chpir_cluster *cl, uint64_t K, uint32_t N, uint32_t b, const chpir_setup_opts &o) {
-  chpir_cluster_server *S = new chpir_cluster_server();
-  S->cl = cl, S->n = uint32_t(cl->n), S->K = K, S->N = N, S->b = b;
-  S->lwe = o.lwe_rows ? o.lwe_rows : CHPIR_LWE_DIMENSION;
-  S->r.resize(S->n);
-  for (uint32_t d = 0; d < S->n; d++) {
-    S->r[d].dev = cl->dev[d], S->r[d].ctx = cl->ctx[d];
-    S->r[d].pl = plan_of(S->n, d, K, N);
-  }
-  S->ks = S->r[0].pl.ks;
-  return S;
-}
-
-// per-rank options: the rank's columns, hint slice kept in HBM for the gather, no per-shard coalescer (the cluster has its own)
-chpir_setup_opts rank_opts(const chpir_setup_opts &o, const Plan &pl, bool compact, uint32_t n) {
-  chpir_setup_opts ro = o;
-  ro.col_begin = compact ? 0 : pl.c0;
-  ro.col_count = compact ? 0 : pl.nc;
-  ro.hint_on_device = 1;
-  if (n > 1) ro.respond_coalesce = 0;
-  return ro;
-}
-
 template <class F>
 int for_each_rank_parallel(uint32_t n, F f) {
   std::vector<int> rcs(n, CHPIR_OK);
@@ -662,6 +833,190 @@ int for_each_rank_parallel(uint32_t n, F f) {
   for (int rc : rcs)
     if (rc != CHPIR_OK) return rc;
   return CHPIR_OK;
+}
+
+// Where a setup flavour left D: the whole matrix in host memory, or the ranks' compact column slices in their HBM.
+struct DSource {
+  const uint32_t *host = nullptr;
+  const uint32_t *const *dev_slices = nullptr;
+};
+
+// Row cut: every rank assembles rows [k0, k0 + kn) of D at full width (zero rows up to the common pitch ks, so that every shard is
+// ks x N and a query slice is a whole row of it), packs them (and splits the limb planes when the column slice had them), and the
+// column slices go away.  The shards are ordinary single-GPU servers without a hint.
+int reshard_rows(chpir_cluster_server *S, const uint8_t *seed, const DSource &src) {
+  const double t0 = now_s();
+  const uint64_t N = S->N, ks = S->ks;
+  int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
+    Rank &R = S->r[d];
+    const Plan &pl = R.pl;
+    CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    DevBuf blk;
+    if (int rc = blk.alloc(ks * N * 4); rc != CHPIR_OK) return rc;
+    cudaStream_t st = R.compute;
+    uint32_t *rows = blk.as<uint32_t>();
+    if (pl.kn < ks) CHPIR_CUDA(cudaMemsetAsync(rows + pl.kn * N, 0, (ks - pl.kn) * N * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    if (pl.kn > 0) {
+      if (src.host) {
+        CHPIR_CUDA(cudaMemcpyAsync(rows, src.host + pl.k0 * N, pl.kn * N * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      } else {
+        for (uint32_t s0 = 0; s0 < S->n; s0++) {
+          const uint32_t s = (d + s0) % S->n;  // every rank starts with a different peer
+          const Plan &ps = S->r[s].pl;
+          CHPIR_CUDA(cudaMemcpy2DAsync(rows + ps.c0, N * 4, src.dev_slices[s] + pl.k0 * ps.nc, size_t(ps.nc) * 4, size_t(ps.nc) * 4, pl.kn, cudaMemcpyDefault, st),
+                     CHPIR_ERR_CUDA_TRANSFER_FAILED);
+        }
+      }
+    }
+    CHPIR_CUDA(cudaStreamSynchronize(st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+    chpir_setup_opts ro{};
+    ro.skip_hint = 1;
+    ro.batch_tc = R.srv->gemm ? 1 : 2;
+    chpir_server *row = nullptr;
+    if (int rc = chpir_server_setup_device(R.ctx, seed, rows, ks, uint32_t(N), S->b, &ro, nullptr, 0, nullptr, &row); rc != CHPIR_OK) return rc;
+    // what the caller reads through chpir_cluster_server_shard: the setup phases of this rank (measured on the column slice) and the
+    // resident row block
+    const double pack_s = row->timing.pack_s;
+    row->timing = R.srv->timing;
+    row->timing.pack_s += pack_s;
+    row->last_gemm_ms = R.srv->last_gemm_ms, row->last_expand_ms = R.srv->last_expand_ms;
+    row->shard_k_total = S->K;
+    R.col = R.srv;
+    R.srv = row;
+    return CHPIR_OK;
+  });
+  for (uint32_t d = 0; d < S->n; d++) {
+    if (!S->r[d].col) continue;
+    cudaSetDevice(S->r[d].dev);
+    chpir_server_destroy(S->r[d].col);
+    S->r[d].col = nullptr;
+  }
+  S->reshard_s = now_s() - t0;
+  return rc;
+}
+
+// Common tail of every setup flavour: per-rank column-slice servers exist in S->r[*].srv.
+int complete_setup(chpir_cluster_server *S, const chpir_setup_opts &o, const uint8_t *seed, const DSource &src, uint8_t *hint_out, size_t hint_cap,
+                   size_t *hint_len) {
+  for (uint32_t d = 0; d < S->n; d++) S->r[d].srv->col_begin = S->r[d].pl.c0;  // logical position of a compact slice
+  if (int rc = make_streams(S); rc != CHPIR_OK) return rc;
+  if (hint_len) *hint_len = 0;
+  if (!o.skip_hint) {
+    if (int rc = gather_hint(S, hint_out, hint_cap, hint_len); rc != CHPIR_OK) return rc;
+  }
+  if (S->rows) {
+    if (int rc = reshard_rows(S, seed, src); rc != CHPIR_OK) return rc;
+  }
+  return make_slots(S);
+}
+
+chpir_cluster_server *new_server(chpir_cluster *cl, uint64_t K, uint32_t N, uint32_t b, const chpir_setup_opts &o) {
+  chpir_cluster_server *S = new chpir_cluster_server();
+  S->cl = cl, S->n = uint32_t(cl->n), S->K = K, S->N = N, S->b = b;
+  S->lwe = o.lwe_rows ? o.lwe_rows : CHPIR_LWE_DIMENSION;
+  S->r.resize(S->n);
+  for (uint32_t d = 0; d < S->n; d++) {
+    S->r[d].dev = cl->dev[d], S->r[d].ctx = cl->ctx[d];
+    S->r[d].pl = plan_of(S->n, d, K, N);
+  }
+  S->ks = S->r[0].pl.ks;
+  S->rows = S->n > 1 && !env_is("CHPIR_CLUSTER_SHARD", "cols");
+  return S;
+}
+
+// per-rank options: the rank's columns, hint slice kept in HBM for the gather, no per-shard coalescer (the cluster has its own)
+chpir_setup_opts rank_opts(const chpir_setup_opts &o, const Plan &pl, bool compact, uint32_t n) {
+  chpir_setup_opts ro = o;
+  ro.col_begin = compact ? 0 : pl.c0;
+  ro.col_count = compact ? 0 : pl.nc;
+  ro.hint_on_device = 1;
+  if (n > 1) ro.respond_coalesce = 0;
+  return ro;
+}
+
+// Device-resident respond on the row cut: every rank streams its own rows against the query words resident on it, nothing is
+// gathered; rank 0's second stream adds the partial sums of pass i while the compute streams are already in pass i + 1.
+int respond_device_rows(chpir_cluster_server *S, const uint32_t *const *q_slices, uint32_t nq, uint32_t *resp_device0, bool tc, uint32_t repeats,
+                        float *device_ms) {
+  for (uint32_t d = 0; d < S->n; d++) {
+    Rank &R = S->r[d];
+    CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    if (R.resp_rows < nq) {
+      for (int p = 0; p < 2; p++) {
+        if (R.resp[p]) cudaFree(R.resp[p]);
+        R.resp[p] = nullptr;
+      }
+      R.resp_rows = 0;
+      for (int p = 0; p < 2; p++)
+        if (cudaMalloc(&R.resp[p], size_t(nq) * S->N * 4) != cudaSuccess) {
+          set_last_cuda_error(cudaGetLastError(), "cluster device-path scratch (partial sums)");
+          return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+        }
+      R.resp_rows = nq;
+    }
+  }
+  Rank &R0 = S->r[0];
+  CHPIR_CUDA(cudaSetDevice(R0.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  CHPIR_CUDA(cudaEventRecord(S->t0, R0.compute), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+  CHPIR_CUDA(cudaStreamWaitEvent(R0.gather, S->t0, 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+  for (uint32_t d = 1; d < S->n; d++) {
+    CHPIR_CUDA(cudaSetDevice(S->r[d].dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    CHPIR_CUDA(cudaStreamWaitEvent(S->r[d].compute, S->t0, 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+  }
+  int rc = CHPIR_OK;
+  for (uint32_t rep = 0; rep < repeats && rc == CHPIR_OK; rep++) {
+    const int p = int(rep & 1);
+    PartTable parts{};
+    for (uint32_t d = 0; d < S->n && rc == CHPIR_OK; d++) {
+      Rank &R = S->r[d];
+      chpir_server *sv = R.srv;
+      parts.p[d] = R.resp[p];
+      CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+      cudaStream_t st = R.compute;
+      CHPIR_CUDA(cudaStreamWaitEvent(st, R0.reduced[p], 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);  // pass rep-2 has been summed out of this buffer
+      CHPIR_CUDA(cudaMemsetAsync(R.resp[p], 0, size_t(nq) * S->N * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      if (tc) {
+        std::lock_guard<std::mutex> gg(sv->gemm_mu);
+        for (uint32_t row0 = 0; row0 < nq && rc == CHPIR_OK; row0 += kMaxBatch) {
+          const uint32_t rows = std::min(kMaxBatch, nq - row0);
+          const int buf = int(R.tc_buf++ & 1);
+          if ((rc = gemm_tc_buf_acquire(sv->gemm, buf, st)) != CHPIR_OK) break;
+          if ((rc = gemm_tc_load_panel_u32(sv->gemm, buf, q_slices[d] + size_t(row0) * S->ks, rows, st)) != CHPIR_OK) break;
+          if ((rc = gemm_tc_panel(sv->gemm, buf, rows, R.resp[p] + size_t(row0) * S->N, st)) != CHPIR_OK) break;
+          if ((rc = gemm_tc_buf_release(sv->gemm, buf, st)) != CHPIR_OK) break;
+        }
+      } else {
+        rc = launch_respond(sv->d_packed, sv->layout, sv->K, sv->plan, q_slices[d], R.resp[p], nq, st);
+      }
+      if (rc != CHPIR_OK) break;
+      CHPIR_CUDA(cudaEventRecord(R.computed[p], st), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+    }
+    if (rc != CHPIR_OK) break;
+    CHPIR_CUDA(cudaSetDevice(R0.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    for (uint32_t d = 0; d < S->n; d++) CHPIR_CUDA(cudaStreamWaitEvent(R0.gather, S->r[d].computed[p], 0), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+    if ((rc = launch_reduce(parts, S->n, uint64_t(nq) * S->N, resp_device0, R0.ctx->sm_count, R0.gather)) != CHPIR_OK) break;
+    CHPIR_CUDA(cudaEventRecord(R0.reduced[p], R0.gather), CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+  }
+  if (rc == CHPIR_OK) {
+    cudaSetDevice(R0.dev);
+    for (int p = 0; p < 2; p++) cudaStreamWaitEvent(R0.compute, R0.reduced[p], 0);
+    cudaEventRecord(S->t1, R0.compute);
+  }
+  for (uint32_t d = 0; d < S->n; d++) {
+    cudaSetDevice(S->r[d].dev);
+    cudaError_t e = cudaStreamSynchronize(S->r[d].gather);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S->r[d].compute);
+    if (e != cudaSuccess && rc == CHPIR_OK) {
+      set_last_cuda_error(e, "cluster respond (device-resident, row cut)");
+      rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
+    }
+  }
+  cudaSetDevice(R0.dev);
+  if (rc == CHPIR_OK && device_ms) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, S->t0, S->t1) == cudaSuccess) *device_ms = ms;
+  }
+  return rc;
 }
 
 }  // namespace
@@ -767,7 +1122,9 @@ int chpir_cluster_server_setup_device(chpir_cluster *cl, const uint8_t seed[CHPI
     return chpir_server_setup_device(S->r[d].ctx, seed, d_slices[d], rows_k, S->r[d].pl.nc, b, &ro, nullptr, 0, nullptr, &S->r[d].srv);
   });
   if (rc != CHPIR_OK) return rc;
-  if ((rc = complete_setup(S.get(), o, hint_out, hint_cap, hint_len)) != CHPIR_OK) return rc;
+  DSource dsrc;
+  dsrc.dev_slices = d_slices;
+  if ((rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len)) != CHPIR_OK) return rc;
   S->setup_total_s = now_s() - t0;
   *out = S.release();
   return CHPIR_OK;
@@ -793,7 +1150,9 @@ int chpir_cluster_server_setup(chpir_cluster *cl, const uint8_t seed[CHPIR_SEED_
     return server_setup_from_host_matrix(S->r[d].ctx, seed, d_host, rows_k, cols_n, b, &ro, nullptr, 0, nullptr, &S->r[d].srv, nullptr);
   });
   if (rc != CHPIR_OK) return rc;
-  if ((rc = complete_setup(S.get(), o, hint_out, hint_cap, hint_len)) != CHPIR_OK) return rc;
+  DSource dsrc;
+  dsrc.host = d_host;
+  if ((rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len)) != CHPIR_OK) return rc;
   S->setup_total_s = now_s() - t0;
   *out = S.release();
   return CHPIR_OK;
@@ -823,6 +1182,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   if (N < uint64_t(cl->n)) return CHPIR_ERR_INVALID_ARGUMENT;
   const double t0 = now_s();
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, K, uint32_t(N), b, o));
+  std::unique_ptr<uint32_t[]> d_store;  // n > 1: D, encoded once on the host; lives until the row blocks have been cut from it
   if (S->n == 1) {
     // one GPU: the single-GPU call as it is (device row fill, its own early XOF start, its coalescer), hint slice = whole hint
     chpir_setup_opts ro = o;
@@ -849,7 +1209,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
         if (int rc = pipes[d]->start(S->r[d].dev, seed, S->lwe, K, o.host_chunk_rows, (S->lwe + 127) / 128); rc != CHPIR_OK) return rc;
       }
     }
-    std::unique_ptr<uint32_t[]> d_store(new (std::nothrow) uint32_t[K * N]);
+    d_store.reset(new (std::nothrow) uint32_t[K * N]);
     if (!d_store) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     if (host_a) set_encode_threads(hw > S->n + 2 ? hw - S->n - 1 : 1);  // the producer cores stay free for the chains
@@ -865,7 +1225,10 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
     if (rc != CHPIR_OK) return rc;
     for (uint32_t d = 0; d < S->n; d++) S->r[d].srv->timing.host_encode_s = t1 - t0;
   }
-  if (int rc = complete_setup(S.get(), o, hint_out, hint_cap, hint_len); rc != CHPIR_OK) return rc;
+  DSource dsrc;
+  dsrc.host = d_store.get();
+  if (int rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len); rc != CHPIR_OK) return rc;
+  d_store.reset();
   S->setup_total_s = now_s() - t0;
   *out = S.release();
   return CHPIR_OK;
@@ -919,22 +1282,37 @@ int chpir_cluster_server_load(chpir_cluster *cl, const char *path_prefix, const 
     return chpir_server_load(cl->ctx[d], p.c_str(), &ro, &shards[d]);
   });
   if (rc != CHPIR_OK) return rc;
-  // the files must describe ONE matrix cut by this cluster's plan
-  uint64_t ncols = 0;
-  for (uint32_t d = 0; d < n; d++) ncols += shards[d]->ncols;
-  if (ncols > 0xffffffffull) return CHPIR_ERR_INVALID_SAVED_SERVER;
-  for (uint32_t d = 0; d < n; d++) {
-    const Plan pl = plan_of(n, d, shards[0]->K, uint32_t(ncols));
-    if (shards[d]->K != shards[0]->K || shards[d]->b != shards[0]->b || shards[d]->ncols != pl.nc || shards[d]->col_begin != pl.c0)
-      return CHPIR_ERR_INVALID_SAVED_SERVER;
+  // the files must describe ONE matrix cut by this cluster's plan: row blocks (written by an n > 1 cluster in the default cut)
+  // or column slices
+  const bool by_rows = shards[0]->shard_k_total != 0;
+  uint64_t K = 0, ncols = 0;
+  if (by_rows) {
+    K = shards[0]->shard_k_total, ncols = shards[0]->ncols;
+    if (n < 2) return CHPIR_ERR_INVALID_SAVED_SERVER;
+    for (uint32_t d = 0; d < n; d++) {
+      const Plan pl = plan_of(n, d, K, uint32_t(ncols));
+      if (shards[d]->shard_k_total != K || shards[d]->K != pl.ks || shards[d]->b != shards[0]->b || shards[d]->ncols != ncols)
+        return CHPIR_ERR_INVALID_SAVED_SERVER;
+    }
+  } else {
+    K = shards[0]->K;
+    for (uint32_t d = 0; d < n; d++) ncols += shards[d]->ncols;
+    if (ncols > 0xffffffffull) return CHPIR_ERR_INVALID_SAVED_SERVER;
+    for (uint32_t d = 0; d < n; d++) {
+      const Plan pl = plan_of(n, d, K, uint32_t(ncols));
+      if (shards[d]->shard_k_total != 0 || shards[d]->K != K || shards[d]->b != shards[0]->b || shards[d]->ncols != pl.nc || shards[d]->col_begin != pl.c0)
+        return CHPIR_ERR_INVALID_SAVED_SERVER;
+    }
   }
-  std::unique_ptr<chpir_cluster_server> S(new_server(cl, shards[0]->K, uint32_t(ncols), shards[0]->b, o));
-  S->lwe = 0;  // no hint travels with a saved server
+  std::unique_ptr<chpir_cluster_server> S(new_server(cl, K, uint32_t(ncols), shards[0]->b, o));
+  S->rows = by_rows;  // the files decide, not the environment
+  S->lwe = 0;         // no hint travels with a saved server
   for (uint32_t d = 0; d < n; d++) {
     S->r[d].srv = shards[d];
     shards[d] = nullptr;
   }
-  if ((rc = finish_server(S.get())) != CHPIR_OK) return rc;
+  if ((rc = make_streams(S.get())) != CHPIR_OK) return rc;
+  if ((rc = make_slots(S.get())) != CHPIR_OK) return rc;
   *out = S.release();
   return CHPIR_OK;
   CHPIR_GUARD_END
@@ -949,7 +1327,7 @@ int chpir_cluster_server_respond(chpir_cluster_server *S, const uint8_t *query, 
   const size_t need = 8 + size_t(S->N) * 4;
   if (!resp_out || resp_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
   if (!S->co_ready) return CHPIR_ERR_INVALID_ARGUMENT;
-  const int rc = respond_coalesced(S, query, resp_out);
+  const int rc = respond_coalesced(S, query, query_len, resp_out);
   if (rc == CHPIR_OK && resp_len) *resp_len = need;
   return rc;
   CHPIR_GUARD_END
@@ -981,10 +1359,17 @@ int chpir_cluster_server_respond_batch(chpir_cluster_server *S, const uint8_t *c
   const uint32_t hdr[2] = {1u, S->N};
   for (uint32_t q0 = 0; q0 < nq; q0 += group) {
     const uint32_t cnt = std::min(group, nq - q0);
-    for (uint32_t i = 0; i < cnt; i++)
-      if (int rc = upload_query(S, B, i, queries[q0 + i]); rc != CHPIR_OK) return rc;
-    int rc;
-    {
+    B.n_pull = 0;
+    int rc = CHPIR_OK;
+    for (uint32_t i = 0; i < cnt && rc == CHPIR_OK; i++) {
+      const bool pull = pullable(queries[q0 + i], query_lens[q0 + i]);
+      B.pull.src[i] = pull ? queries[q0 + i] : nullptr;
+      B.n_pull += pull ? 1 : 0;
+      if (!pull) rc = upload_query(S, B, i, queries[q0 + i]);
+    }
+    const int in = ingest_batch(S, B, cnt);
+    if (rc == CHPIR_OK) rc = in;
+    if (rc == CHPIR_OK) {
       std::lock_guard<std::mutex> ex(S->exec_mu);
       rc = run_batch(S, B, cnt, nullptr);
     }
@@ -1012,6 +1397,7 @@ int chpir_cluster_server_respond_device(chpir_cluster_server *S, const uint32_t 
     if (!q_slices[d] || (reinterpret_cast<uintptr_t>(q_slices[d]) & 15u)) return CHPIR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(S->dev_mu);
   std::lock_guard<std::mutex> ex(S->exec_mu);  // shares the compute streams and the operand rings with the coalesced route
+  if (S->rows) return respond_device_rows(S, q_slices, nq, resp_device0, tc, repeats, device_ms);
   const uint32_t chunk = tc ? kMaxBatch : std::max(1u, std::min(env_u32("CHPIR_CLUSTER_GEMV_CHUNK", kGemvChunk), 4096u));
   // one rank whose slice IS the whole query (K a multiple of 32): the rows are already what the GEMV reads, nothing to gather
   const bool direct = !tc && S->n == 1 && S->ks == S->K;
@@ -1179,6 +1565,9 @@ int chpir_cluster_server_get_info(const chpir_cluster_server *S, chpir_cluster_s
   out->setup_total_s = S->setup_total_s, out->hint_gather_s = S->hint_gather_s;
   out->gather_uses_nccl = S->gather_uses_nccl;
   out->nccl_version = uint32_t(S->cl->nccl_version);
+  out->respond_by_rows = S->rows ? 1u : 0u;
+  out->reshard_s = S->reshard_s;
+  out->pulled_queries = S->pulled;
   if (S->n == 1) {
     const Coalescer &co = S->r[0].srv->co;
     out->batches = co.batches, out->queries = co.queries, out->tc_batches = co.tc_batches;

@@ -286,14 +286,14 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
           mbar_wait(bar_base + 8 * (stages + s), ph ^ 1);
           const uint64_t kc = k0 + uint64_t(c) * S;
           const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
-          const bool qb = q_bulk && rows == S;
+          const bool qb = q_bulk && (rows & 3u) == 0;  // 16-byte granules; a partial chunk's q slice travels the same way
           const uint32_t full = bar_base + 8 * s;
           // tight rows are 8 (mod 16) bytes long: copy an even number of them (S is even; past row K lies the zeroed pad row)
           const uint32_t rows_cp = TIGHT ? rows + (rows & 1u) : rows;
-          mbar_expect_tx(full, rows_cp * pitch + (qb ? S * 4 : 0));
+          mbar_expect_tx(full, rows_cp * pitch + (qb ? rows * 4 : 0));
           const uint32_t dst = ring_base + s * stage_bytes;
           bulk_g2s(dst, packed + kc * pitch, rows_cp * pitch, full, policy);
-          if (qb) bulk_g2s(dst + d_bytes, q + kc, S * 4, full);
+          if (qb) bulk_g2s(dst + d_bytes, q + kc, rows * 4, full);
         }
       }
     }
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
       const uint32_t s = g % stages, ph = (g / stages) & 1;
       const uint64_t kc = k0 + uint64_t(c) * S;
       const uint32_t rows = uint32_t(k1 - kc < S ? k1 - kc : S);
-      const bool qb = q_bulk && rows == S;
+      const bool qb = q_bulk && (rows & 3u) == 0;
       mbar_wait(bar_base + 8 * s, ph);
       if (active) {
         const uint32_t base = ring_base + s * stage_bytes + u * 16 + r * pitch;
@@ -340,6 +340,11 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
         if (qb) {
 #pragma unroll
           for (int j = 0; j < RPT; j++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qk[j]) : "r"(qbase + j * R * 4));
+          if (rows != S) {  // partial chunk (uniform per CTA): the words past its end are stale
+#pragma unroll
+            for (int j = 0; j < RPT; j++)
+              if (r + j * R >= rows) qk[j] = 0u;
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < RPT; j++) {
@@ -577,6 +582,10 @@ static void plan_ring(const PackedLayout &L, uint64_t K, int sm_count, RespondPl
   P->ring_grid = uint32_t(sm_count) * std::max(1u, env_u32("CHPIR_RING_GRID_MULT", 1));
   const uint64_t per = (K + P->ring_grid - 1) / P->ring_grid;
   P->ring_rows_per_cta = (per + S - 1) / S * S;
+  // Short K-ranges (the row blocks of an 8-way cluster: ~1000 rows per CTA) lose whole SMs to that rounding -- 147 456 rows in
+  // units of 32 are 144 CTAs of 1024 -- so when it costs more than 1 % the range is rounded to 4 rows instead (16-byte granules of
+  // q, an even row count for tight rows) and every CTA ends on a partial stage.
+  if (P->ring_rows_per_cta * 100 > per * 101 && env_u32("CHPIR_RING_FINE_SPLIT", 1) != 0) P->ring_rows_per_cta = (per + 3) / 4 * 4;
   if (P->ring_rows_per_cta == 0) P->ring_rows_per_cta = S;
   P->ring_block = ((R * units + 31) / 32 + 1) * 32;
 }

@@ -69,6 +69,7 @@ struct chpir_server {
   chpir_ctx *ctx = nullptr;
   uint64_t K = 0;
   uint32_t ncols = 0, col_begin = 0, b = 0;
+  uint64_t shard_k_total = 0;  // != 0: this server is a ROW block of a cluster's D (csrc/cluster.cu); the rows of the whole matrix
   chpir::PackedLayout layout{};
   chpir::RespondPlan plan{};
   uint8_t *d_packed = nullptr;

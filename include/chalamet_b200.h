@@ -355,6 +355,10 @@ typedef struct chpir_cluster_server_info {
   uint32_t nccl_version;          /* ncclGetVersion, 0 if NCCL was not needed */
   /* coalescer statistics of chpir_cluster_server_respond since setup */
   uint64_t batches, queries, tc_batches;
+  uint64_t pulled_queries;        /* of `queries`: fetched by the GPUs themselves from page-locked caller memory (no per-query DMA call) */
+  uint32_t respond_by_rows;       /* 1 = respond runs on ROW blocks of D (default for n_gpus > 1), 0 = on column slices */
+  uint32_t reserved0;
+  double reshard_s;               /* of setup_total_s: re-cutting D from column slices into row blocks */
 } chpir_cluster_server_info;
 CHPIR_API int chpir_cluster_server_get_info(const chpir_cluster_server *srv, chpir_cluster_server_info *out);
 

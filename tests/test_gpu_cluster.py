@@ -1,5 +1,6 @@
-"""GPU parity for the cluster layer (csrc/cluster.cu): the column-sharded server on 1..8 GPUs of one process behind the reference's
-two calls, Server::setup (server.rs:103) and Server::respond (server.rs:184).
+"""GPU parity for the cluster layer (csrc/cluster.cu): the sharded server on 1..8 GPUs of one process behind the reference's
+two calls, Server::setup (server.rs:103) and Server::respond (server.rs:184).  Respond runs on row blocks of D by default and on
+column slices with CHPIR_CLUSTER_SHARD=cols; both cuts are held to the same bytes.
 
 Bit-exact: the complete hint and every response of an n-GPU cluster must equal the single-GPU bytes and the CPU oracle's bytes
 ("1-GPU vs 2/4/8-GPU outputs must be byte-identical").  Tests parametrised over the cluster size skip the sizes
@@ -18,6 +19,25 @@ from conftest import make_db
 
 SEED = bytes((5 * i + 1) & 0xFF for i in range(32))
 SIZES = [1, 2, 3, 4, 8]
+CUTS = ["rows", "cols"]
+
+
+class cut_env:
+    """CHPIR_CLUSTER_SHARD for the setups inside the block (read by the library at every cluster setup)."""
+
+    def __init__(self, cut):
+        self.cut = cut
+
+    def __enter__(self):
+        os.environ["CHPIR_CLUSTER_SHARD"] = self.cut
+
+    def __exit__(self, *a):
+        os.environ.pop("CHPIR_CLUSTER_SHARD", None)
+
+
+def skip_redundant(n, cut):
+    if n == 1 and cut == "cols":
+        pytest.skip("a one-GPU cluster has one cut")
 
 
 def rand_u32(rng, shape):
@@ -40,9 +60,11 @@ def exact_respond(D, q):
     return (((lo @ D64) + (((hi @ D64) & 0xFFFF) << 16)) & 0xFFFFFFFF).astype(np.uint32)
 
 
+@pytest.mark.parametrize("cut", CUTS)
 @pytest.mark.parametrize("n", SIZES)
-def test_cluster_hint_and_responses_equal_oracle_and_single_gpu(n):
+def test_cluster_hint_and_responses_equal_oracle_and_single_gpu(n, cut):
     need(n)
+    skip_redundant(n, cut)
     rng = np.random.default_rng(100 + n)
     K, N, b, lwe = 4099, 133, 10, 150  # ragged K (not a multiple of 4), column count not divisible by n
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
@@ -55,11 +77,13 @@ def test_cluster_hint_and_responses_equal_oracle_and_single_gpu(n):
         os.environ["CHPIR_CLUSTER_GATHER"] = gather
         try:
             cl = cp.Cluster(n_gpus=n)
-            srv, hint = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, lwe_rows=lwe, batch_tc=1)
+            with cut_env(cut):
+                srv, hint = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, lwe_rows=lwe, batch_tc=1)
         finally:
             os.environ.pop("CHPIR_CLUSTER_GATHER", None)
         info = srv.get_info()
         assert info["n_gpus"] == n and info["cols_n"] == N and info["rows_k"] == K
+        assert info["respond_by_rows"] == (1 if (n > 1 and cut == "rows") else 0)
         assert info["gather_uses_nccl"] == (1 if (n > 1 and gather == "nccl") else 0)
         assert hint == ohint, f"{n}-GPU hint ({gather} gather) differs from the oracle"
         for _ in range(3):  # a lone caller: the GEMV route
@@ -74,14 +98,17 @@ def test_cluster_hint_and_responses_equal_oracle_and_single_gpu(n):
         cl.close()
 
 
+@pytest.mark.parametrize("cut", CUTS)
 @pytest.mark.parametrize("n", SIZES)
-def test_cluster_concurrent_callers_are_coalesced_and_exact(n):
+def test_cluster_concurrent_callers_are_coalesced_and_exact(n, cut):
     need(n)
+    skip_redundant(n, cut)
     rng = np.random.default_rng(200 + n)
     K, N, b = 20011, 301, 9
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
     cl = cp.Cluster(n_gpus=n)
-    srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True, batch_tc=1, respond_coalesce=True)
+    with cut_env(cut):
+        srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True, batch_tc=1, respond_coalesce=True)
     T, per = 24, 6
     qs = rand_u32(rng, (T * per, K))
     want = [O.matrix_to_bytes(exact_respond(D, q).reshape(1, -1)) for q in qs]
@@ -109,20 +136,23 @@ def test_cluster_concurrent_callers_are_coalesced_and_exact(n):
     cl.close()
 
 
+@pytest.mark.parametrize("cut", CUTS)
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("b", [4, 9, 14])
-def test_cluster_device_resident_paths(n, b):
+def test_cluster_device_resident_paths(n, b, cut):
     """chpir_cluster_server_respond_device: query slices resident on the ranks' GPUs exactly as the PCIe ingest leaves them, result
     gathered in rank 0's HBM; GEMV route (copy-engine all-gather and the pull kernel) and tensor-core route."""
     need(n)
+    skip_redundant(n, cut)
     import torch
 
     rng = np.random.default_rng(300 + 10 * n + b)
     K, N = 9001, 95
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
     cl = cp.Cluster(n_gpus=n)
-    srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True, batch_tc=1)
-    nq = 71  # not a multiple of the GEMV chunk (32); one partial tensor-core tile
+    with cut_env(cut):
+        srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True, batch_tc=1)
+    nq = 171 if cut == "rows" else 71  # not a multiple of the GEMV chunk (32) / more than one tensor-core tile, the last one partial
     q = rand_u32(rng, (nq, K))
     want = np.stack([exact_respond(D, row) for row in q])
     ks = srv.k_pitch
@@ -180,15 +210,19 @@ def test_cluster_setup_from_db_pir_round(n, arity):
     cl.close()
 
 
+@pytest.mark.parametrize("cut", CUTS)
 @pytest.mark.parametrize("n", [1, 2, 4])
-def test_cluster_tiny_matrix_with_empty_query_slices(n):
-    """K smaller than the slice pitch: the last ranks ingest no query words at all; N barely covers the ranks."""
+def test_cluster_tiny_matrix_with_empty_query_slices(n, cut):
+    """K smaller than the slice pitch: the last ranks ingest no query words at all (and, in the row cut, hold only zero rows); N barely
+    covers the ranks."""
     need(n)
+    skip_redundant(n, cut)
     rng = np.random.default_rng(400 + n)
     K, N, b = 7, max(n, 5), 11
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
     cl = cp.Cluster(n_gpus=n)
-    srv, hint = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, lwe_rows=20, batch_tc=1)
+    with cut_env(cut):
+        srv, hint = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, lwe_rows=20, batch_tc=1)
     osrv, ohint = O.Server.setup_from_matrix(SEED, D, b, lwe_rows=20)
     assert hint == ohint
     qs = [qbytes(rand_u32(rng, K)) for _ in range(9)]
@@ -196,6 +230,74 @@ def test_cluster_tiny_matrix_with_empty_query_slices(n):
     assert srv.respond_batch(qs) == [osrv.respond(q) for q in qs]
     srv.close()
     cl.close()
+
+
+@pytest.mark.parametrize("cut", CUTS)
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_cluster_page_locked_queries_are_fetched_by_the_gpus(n, cut):
+    """Queries in chpir_host_alloc memory (any 4-byte alignment) are pulled by one kernel per GPU and batch instead of one DMA per query
+    and GPU; pageable queries in the same batches take the DMA route; CHPIR_CLUSTER_INGEST=dma turns the pull off.  Same bytes always."""
+    need(n)
+    rng = np.random.default_rng(800 + n)
+    K, N, b = 30011, 203, 9
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    cl = cp.Cluster(n_gpus=n)
+    with cut_env(cut):
+        srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True, batch_tc=1, respond_coalesce=True)
+    Q = 40
+    qs = rand_u32(rng, (Q, K))
+    want = [O.matrix_to_bytes(exact_respond(D, q).reshape(1, -1)) for q in qs]
+    qlen, rlen = 8 + 4 * K, 8 + 4 * N
+    pad = 0  # qlen = 4 (mod 16): query i starts 4 * i bytes past a 16-byte boundary, which exercises the 16-, 8- and 4-byte load paths
+    assert qlen % 16 == 4
+    q_pin, r_pin = cp.PinnedBuffer(Q * (qlen + pad) + 64), cp.PinnedBuffer(Q * rlen)
+    ptrs = []
+    for i in range(Q):
+        off = i * (qlen + pad)
+        q_pin.array[off: off + qlen] = np.frombuffer(qbytes(qs[i]), dtype=np.uint8)
+        ptrs.append(q_pin.ptr + off)
+    assert {p % 16 for p in ptrs} >= {0, 4, 8, 12}
+    # a lone caller (GEMV route), then 16 concurrent native callers (tensor-core route)
+    assert srv.respond_into(ptrs[1], qlen, r_pin.ptr, rlen) == rlen
+    assert r_pin.array[:rlen].tobytes() == want[1]
+    before = srv.get_info()["pulled_queries"]
+    assert before == 1
+    srv.respond_concurrent(ptrs, qlen, 3 * Q, r_pin.ptr, rlen, 16)
+    got = [r_pin.array[i * rlen: (i + 1) * rlen].tobytes() for i in range(Q)]
+    assert got == want
+    info = srv.get_info()
+    assert info["pulled_queries"] == before + 3 * Q
+    # pageable callers (Python bytes) beside page-locked ones
+    errs, out = [], {}
+
+    def pageable(i):
+        try:
+            out[i] = srv.respond(qbytes(qs[i]))
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+
+    ths = [threading.Thread(target=pageable, args=(i,)) for i in range(8)]
+    for th in ths:
+        th.start()
+    srv.respond_concurrent(ptrs[8:], qlen, Q - 8, r_pin.ptr + 8 * rlen, rlen, 8)
+    for th in ths:
+        th.join()
+    assert not errs and [out[i] for i in range(8)] == want[:8]
+    assert [r_pin.array[i * rlen: (i + 1) * rlen].tobytes() for i in range(8, Q)] == want[8:]
+    # the batch call and the switch
+    assert srv.respond_batch([qbytes(q) for q in qs[:9]]) == want[:9]
+    os.environ["CHPIR_CLUSTER_INGEST"] = "dma"
+    try:
+        pulled = srv.get_info()["pulled_queries"]
+        srv.respond_concurrent(ptrs, qlen, Q, r_pin.ptr, rlen, 8)
+        assert srv.get_info()["pulled_queries"] == pulled
+        assert [r_pin.array[i * rlen: (i + 1) * rlen].tobytes() for i in range(Q)] == want
+    finally:
+        os.environ.pop("CHPIR_CLUSTER_INGEST", None)
+    srv.close()
+    cl.close()
+    q_pin.close()
+    r_pin.close()
 
 
 @pytest.mark.parametrize("n", [1, 2])
@@ -231,20 +333,25 @@ def test_cluster_error_behaviour_matches_reference(n):
     cl.close()
 
 
-@pytest.mark.parametrize("n", [1, 2])
-def test_cluster_save_and_load(n, tmp_path):
+@pytest.mark.parametrize("cut", CUTS)
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_cluster_save_and_load(n, cut, tmp_path):
     need(n)
+    skip_redundant(n, cut)
     rng = np.random.default_rng(600 + n)
     K, N, b = 3001, 77, 10
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
     cl = cp.Cluster(n_gpus=n)
-    srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True)
+    with cut_env(cut):
+        srv, _ = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, skip_hint=True)
     qs = [qbytes(rand_u32(rng, K)) for _ in range(8)]
     want = [srv.respond(q) for q in qs]
     prefix = str(tmp_path / "srv")
     srv.save(prefix)
     srv.close()
-    back = cp.ClusterServer.load(cl, prefix, batch_tc=1)
+    back = cp.ClusterServer.load(cl, prefix, batch_tc=1)  # the files, not the environment, decide the cut
+    assert back.get_info()["respond_by_rows"] == (1 if (n > 1 and cut == "rows") else 0)
+    assert back.get_info()["rows_k"] == K and back.get_info()["cols_n"] == N
     assert [back.respond(q) for q in qs[:2]] == want[:2]
     assert back.respond_batch(qs) == want  # tensor-core route on planes rebuilt from the packed rows
     back.close()
