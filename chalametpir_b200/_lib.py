@@ -79,6 +79,10 @@ class ClusterServerInfo(C.Structure):
         ("respond_by_rows", C.c_uint32),
         ("reserved0", C.c_uint32),
         ("reshard_s", C.c_double),
+        ("ingest_wait_s", C.c_double),
+        ("ingest_s", C.c_double),
+        ("exec_wait_s", C.c_double),
+        ("exec_s", C.c_double),
     ]
 
     def as_dict(self):

@@ -25,6 +25,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <memory>
 #include <string>
@@ -234,29 +235,38 @@ __device__ __forceinline__ void pull_row(const uint8_t *s, uint32_t *d, uint64_t
   for (uint64_t i = nv * W + tid; i < words; i += stride) d[i] = __ldcv(reinterpret_cast<const uint32_t *>(s) + i);
 }
 
-// grid (x, row): words [0, words) of row `row` = bytes [byte_off, byte_off + 4 * words) of t.src[row]  ->  dst + row * ks.
-// byte_off = 8 + 4 * k0 is a multiple of 8, so the widest load the source allows depends only on the caller's buffer alignment;
-// 4-byte alignment of the buffer is the caller-side condition for taking this route at all.
-__global__ void __launch_bounds__(256) pull_slices_kernel(PullTable t, uint64_t byte_off, uint64_t words, uint64_t ks, uint32_t *__restrict__ dst) {
-  const uint8_t *s = t.src[blockIdx.y];
-  if (!s) return;
-  s += byte_off;
-  uint32_t *d = dst + uint64_t(blockIdx.y) * ks;
-  const uint64_t tid = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x, stride = uint64_t(gridDim.x) * blockDim.x;
-  const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(s) & 15u);
-  if (a == 0)
-    pull_row<uint4>(s, d, words, tid, stride);
-  else if ((a & 7u) == 0)
-    pull_row<uint2>(s, d, words, tid, stride);
-  else
-    pull_row<uint32_t>(s, d, words, tid, stride);
+// A fixed, small grid walks the (row, segment) pairs of the batch: words [0, words) of row r = bytes [byte_off, byte_off + 4 * words)
+// of t.src[r]  ->  dst + r * ks.  The kernel is bound by the PCIe round trip, not by threads: one block per SM with four 16-byte loads
+// in flight per thread keeps ~2.4 MB outstanding, far more than the link needs, and leaves the SMs' thread slots to the previous
+// batch's kernels that run beside it.  byte_off = 8 + 4 * k0 is a multiple of 8, so the widest load the source allows depends only on
+// the caller's buffer alignment; 4-byte alignment of the buffer is the caller-side condition for taking this route at all.
+constexpr uint32_t kPullSegWords = 256 * 4 * 4;  // one block-wide sweep of 16-byte loads, 4 per thread
+__global__ void __launch_bounds__(256) pull_slices_kernel(PullTable t, uint32_t rows, uint64_t byte_off, uint64_t words, uint64_t ks,
+                                                          uint32_t *__restrict__ dst) {
+  const uint64_t segs = (words + kPullSegWords - 1) / kPullSegWords;
+  for (uint64_t item = blockIdx.x; item < uint64_t(rows) * segs; item += gridDim.x) {
+    const uint32_t row = uint32_t(item / segs);
+    const uint64_t w0 = (item - uint64_t(row) * segs) * kPullSegWords;
+    const uint8_t *s = t.src[row];
+    if (!s) continue;
+    s += byte_off + 4 * w0;
+    uint32_t *d = dst + uint64_t(row) * ks + w0;
+    const uint64_t n = words - w0 < kPullSegWords ? words - w0 : kPullSegWords;
+    const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(s) & 15u);
+    if (a == 0)
+      pull_row<uint4>(s, d, n, threadIdx.x, blockDim.x);
+    else if ((a & 7u) == 0)
+      pull_row<uint2>(s, d, n, threadIdx.x, blockDim.x);
+    else
+      pull_row<uint32_t>(s, d, n, threadIdx.x, blockDim.x);
+  }
 }
 
-int launch_pull(const PullTable &t, uint32_t rows, uint64_t k0, uint64_t kn, uint64_t ks, uint32_t *dst, cudaStream_t st) {
+int launch_pull(const PullTable &t, uint32_t rows, uint64_t k0, uint64_t kn, uint64_t ks, uint32_t *dst, int sm_count, cudaStream_t st) {
   if (rows == 0 || kn == 0) return CHPIR_OK;
-  const uint64_t per_block = 256ull * 4 * 4;  // words one block moves per sweep (16-byte loads, 4 in flight per thread)
-  const unsigned gx = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((kn + per_block - 1) / per_block, 64)));
-  pull_slices_kernel<<<dim3(gx, rows), 256, 0, st>>>(t, 8 + 4 * k0, kn, ks, dst);
+  const uint64_t items = uint64_t(rows) * ((kn + kPullSegWords - 1) / kPullSegWords);
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(items, uint64_t(sm_count) * env_u32("CHPIR_PULL_BLOCKS_PER_SM", 1))));
+  pull_slices_kernel<<<grid, 256, 0, st>>>(t, rows, 8 + 4 * k0, kn, ks, dst);
   return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
 }
 
@@ -392,12 +402,16 @@ struct chpir_cluster_server {
   // coalescer (n > 1; a one-GPU cluster delegates to the shard's own).  A batch passes two stages, each held by one batch at a time:
   // ingest (its queries cross PCIe) and exec (kernels + result download); a third slot collects callers meanwhile.
   std::mutex mu;
-  std::condition_variable cv;
+  // one condition per reason to wait, so that a wake-up reaches only threads it concerns (hundreds of callers share this object):
+  // callers waiting for a slot that takes members, a leader waiting for its members' uploads / for the next slot to be vacated,
+  // members waiting for their batch's responses
+  std::condition_variable cv_open, cv_free, cv_issued[kSlots], cv_done[kSlots];
   std::mutex ingest_mu, exec_mu;
   CBatch cb[kSlots];
   int open = 0;
   bool co_ready = false;
   uint64_t batches = 0, queries = 0, tc_batches = 0, pulled = 0;
+  double ingest_wait_s = 0, ingest_s = 0, exec_wait_s = 0, exec_s = 0;  // leaders' wall time per pipeline stage, summed over batches
   // chpir_cluster_server_respond_batch
   std::mutex batch_mu;
   std::unique_ptr<CBatch> bb;
@@ -505,8 +519,11 @@ int make_streams(chpir_cluster_server *S) {
   for (uint32_t d = 0; d < S->n; d++) {
     Rank &R = S->r[d];
     CHPIR_CUDA(cudaSetDevice(R.dev), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
-    CHPIR_CUDA(cudaStreamCreateWithFlags(&R.compute, cudaStreamNonBlocking), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
-    CHPIR_CUDA(cudaStreamCreateWithFlags(&R.gather, cudaStreamNonBlocking), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+    // the kernels of the batch on the SMs outrank the next batch's ingest kernel, which shares the GPU with them
+    int prio_lo = 0, prio_hi = 0;
+    CHPIR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+    CHPIR_CUDA(cudaStreamCreateWithPriority(&R.compute, cudaStreamNonBlocking, prio_hi), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
+    CHPIR_CUDA(cudaStreamCreateWithPriority(&R.gather, cudaStreamNonBlocking, prio_hi), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
     for (int p = 0; p < 2; p++) {
       CHPIR_CUDA(cudaEventCreateWithFlags(&R.gathered[p], cudaEventDisableTiming), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
       CHPIR_CUDA(cudaEventCreateWithFlags(&R.computed[p], cudaEventDisableTiming), CHPIR_ERR_CUDA_ALLOCATION_FAILED);
@@ -633,19 +650,59 @@ int upload_query(chpir_cluster_server *S, CBatch &B, uint32_t row, const uint8_t
   return CHPIR_OK;
 }
 
-// Can the GPUs fetch this query themselves?  (page-locked, device-readable, 4-byte aligned; CHPIR_CLUSTER_INGEST=dma turns it off)
-bool pullable(const uint8_t *query, size_t len) {
-  return !env_is("CHPIR_CLUSTER_INGEST", "dma") && (reinterpret_cast<uintptr_t>(query) & 3u) == 0 && device_readable_host(query, len);
+// How the queries of a batch cross PCIe (CHPIR_CLUSTER_INGEST):
+//   batch (default)  page-locked sources are moved by the copy engines, ONE cudaMemcpyBatchAsync per GPU and batch (CUDA 12.8+);
+//   pull             ... by one kernel per GPU and batch that reads the host memory itself (measured: ~36 GB/s per link against
+//                    ~50 GB/s for the copy engines, profiles/r2_e2e_probe_n2.txt; kept for drivers without the batch call);
+//   dma              one cudaMemcpyAsync per query and GPU, issued by the calling thread -- also the route of pageable sources.
+enum IngestRoute { kIngestBatch, kIngestPull, kIngestDma };
+std::atomic<bool> g_batch_copy_broken{false};  // cudaMemcpyBatchAsync refused once: use the pull kernel from then on
+IngestRoute ingest_route() {
+  if (env_is("CHPIR_CLUSTER_INGEST", "dma")) return kIngestDma;
+  if (env_is("CHPIR_CLUSTER_INGEST", "pull") || g_batch_copy_broken.load(std::memory_order_relaxed)) return kIngestPull;
+  return kIngestBatch;
 }
 
-// Ingest stage of a closed batch: one pull kernel per GPU for the members that registered a page-locked source, then the PCIe
-// stage is over when every copy stream (pulls and the members' own DMAs) has drained; B.uploaded[d] marks that point for the kernels.
+// Can the GPUs / copy engines fetch this query from where it lies?  (page-locked, device-readable, 4-byte aligned)
+bool pullable(const uint8_t *query, size_t len) {
+  return ingest_route() != kIngestDma && (reinterpret_cast<uintptr_t>(query) & 3u) == 0 && device_readable_host(query, len);
+}
+
+// Ingest stage of a closed batch: the members that registered a page-locked source are moved now, one call per GPU; the PCIe stage is
+// over when every copy stream (these transfers and the other members' own DMAs) has drained; B.uploaded[d] marks that point for
+// the kernels.
 int ingest_batch(chpir_cluster_server *S, CBatch &B, uint32_t nq) {
   int rc = CHPIR_OK;
+  const IngestRoute route = ingest_route();
+  std::vector<void *> dsts, srcs;
+  std::vector<size_t> sizes;
   for (uint32_t d = 0; d < S->n; d++) {
     const Plan &pl = S->r[d].pl;
     if (cudaSetDevice(S->r[d].dev) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
-    if (B.n_pull && rc == CHPIR_OK) rc = launch_pull(B.pull, nq, pl.k0, pl.kn, S->ks, B.q_slice[d], B.copy[d]);
+    if (B.n_pull && pl.kn && rc == CHPIR_OK) {
+      bool moved = false;
+      if (route == kIngestBatch) {
+        dsts.clear(), srcs.clear(), sizes.clear();
+        for (uint32_t i = 0; i < nq; i++)
+          if (B.pull.src[i]) {
+            dsts.push_back(B.q_slice[d] + size_t(i) * S->ks);
+            srcs.push_back(const_cast<uint8_t *>(B.pull.src[i]) + 8 + pl.k0 * 4);
+            sizes.push_back(size_t(pl.kn) * 4);
+          }
+        cudaMemcpyAttributes at{};
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;  // the callers' buffers stay put until their call returns
+        at.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+        size_t first = 0, fail = 0;
+        const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &first, 1, &fail, B.copy[d]);
+        if (e == cudaSuccess) {
+          moved = true;
+        } else {
+          (void)cudaGetLastError();
+          g_batch_copy_broken.store(true, std::memory_order_relaxed);
+        }
+      }
+      if (!moved) rc = launch_pull(B.pull, nq, pl.k0, pl.kn, S->ks, B.q_slice[d], S->r[d].ctx->sm_count, B.copy[d]);
+    }
     if (cudaEventRecord(B.uploaded[d], B.copy[d]) != cudaSuccess && rc == CHPIR_OK) rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   }
   for (uint32_t d = 0; d < S->n; d++) {
@@ -668,57 +725,70 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
   const bool pull = pullable(query, query_len);
   CBatch *B = nullptr;
   uint32_t row = 0;
+  int si = 0;
   {
     std::unique_lock<std::mutex> lk(S->mu);
-    S->cv.wait(lk, [&] { return !S->cb[S->open].closed && S->cb[S->open].count < kMaxBatch; });
-    B = &S->cb[S->open];
+    S->cv_open.wait(lk, [&] { return !S->cb[S->open].closed && S->cb[S->open].count < kMaxBatch; });
+    si = S->open;
+    B = &S->cb[si];
     row = B->count++;
     B->pull.src[row] = pull ? query : nullptr;
-    B->n_pull += pull ? 1 : 0;
+    if (pull) B->n_pull++, B->issued++;  // nothing to upload from this thread: the leader moves it
   }
   const bool leader = row == 0;
-  const int up = pull ? CHPIR_OK : upload_query(S, *B, row, query);
-  {
-    std::lock_guard<std::mutex> lk(S->mu);
-    B->issued++;
-    if (up != CHPIR_OK && B->rc == CHPIR_OK) B->rc = up;
+  if (!pull) {
+    const int up = upload_query(S, *B, row, query);
+    bool last = false;
+    {
+      std::lock_guard<std::mutex> lk(S->mu);
+      B->issued++;
+      if (up != CHPIR_OK && B->rc == CHPIR_OK) B->rc = up;
+      last = B->closed && B->issued == B->count;
+    }
+    if (last) S->cv_issued[si].notify_one();
   }
-  S->cv.notify_all();
   if (leader) {
+    const double w0 = now_s();
     std::unique_lock<std::mutex> ingest(S->ingest_mu);
+    const double w1 = now_s();
     uint32_t nq = 0;
     int rc = CHPIR_OK;
     {
       std::unique_lock<std::mutex> lk(S->mu);
       B->closed = true;
       nq = B->count;
-      S->cv.wait(lk, [&] { return B->issued == nq; });
+      S->cv_issued[si].wait(lk, [&] { return B->issued == nq; });
       rc = B->rc;
       const int next = (S->open + 1) % int(kSlots);
-      S->cv.wait(lk, [&] { return S->cb[next].count == 0 && !S->cb[next].closed; });
+      S->cv_free.wait(lk, [&] { return S->cb[next].count == 0 && !S->cb[next].closed; });
       S->open = next;
     }
-    S->cv.notify_all();
+    S->cv_open.notify_all();
     const int in = ingest_batch(S, *B, nq);  // also on the error path: the members' DMAs must have drained
     if (rc == CHPIR_OK) rc = in;
+    const double w2 = now_s();
+    double w3 = w2;
     bool tc = false;
     {
       std::lock_guard<std::mutex> ex(S->exec_mu);
       ingest.unlock();
+      w3 = now_s();
       if (rc == CHPIR_OK) rc = run_batch(S, *B, nq, &tc);
     }
+    const double w4 = now_s();
     {
       std::lock_guard<std::mutex> lk(S->mu);
       S->batches++, S->queries += nq, S->tc_batches += tc ? 1 : 0, S->pulled += B->n_pull;
+      S->ingest_wait_s += w1 - w0, S->ingest_s += w2 - w1, S->exec_wait_s += w3 - w2, S->exec_s += w4 - w3;
       B->rc = rc;
       B->finished = true;
     }
-    S->cv.notify_all();
+    S->cv_done[si].notify_all();
   }
   int rc = CHPIR_OK;
   {
     std::unique_lock<std::mutex> lk(S->mu);
-    S->cv.wait(lk, [&] { return B->finished; });
+    S->cv_done[si].wait(lk, [&] { return B->finished; });
     rc = B->rc;
   }
   if (rc == CHPIR_OK) {
@@ -726,15 +796,17 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
     std::memcpy(resp_out, hdr, 8);
     std::memcpy(resp_out + 8, B->h_resp + size_t(row) * S->N, size_t(S->N) * 4);
   }
+  bool vacated = false;
   {
     std::lock_guard<std::mutex> lk(S->mu);
     if (++B->picked == B->count) {  // last one out resets the slot
       B->count = B->issued = B->picked = B->n_pull = 0;
       B->closed = B->finished = false;
       B->rc = CHPIR_OK;
+      vacated = true;
     }
   }
-  S->cv.notify_all();
+  if (vacated) S->cv_free.notify_all();
   return rc;
 }
 
@@ -1568,6 +1640,7 @@ int chpir_cluster_server_get_info(const chpir_cluster_server *S, chpir_cluster_s
   out->respond_by_rows = S->rows ? 1u : 0u;
   out->reshard_s = S->reshard_s;
   out->pulled_queries = S->pulled;
+  out->ingest_wait_s = S->ingest_wait_s, out->ingest_s = S->ingest_s, out->exec_wait_s = S->exec_wait_s, out->exec_s = S->exec_s;
   if (S->n == 1) {
     const Coalescer &co = S->r[0].srv->co;
     out->batches = co.batches, out->queries = co.queries, out->tc_batches = co.tc_batches;

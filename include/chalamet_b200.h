@@ -359,6 +359,9 @@ typedef struct chpir_cluster_server_info {
   uint32_t respond_by_rows;       /* 1 = respond runs on ROW blocks of D (default for n_gpus > 1), 0 = on column slices */
   uint32_t reserved0;
   double reshard_s;               /* of setup_total_s: re-cutting D from column slices into row blocks */
+  /* wall time the batch leaders spent per pipeline stage of chpir_cluster_server_respond, summed over all batches since setup:
+   * waiting for the ingest stage (= collecting callers), moving the queries over PCIe, waiting for the SMs, kernels + download */
+  double ingest_wait_s, ingest_s, exec_wait_s, exec_s;
 } chpir_cluster_server_info;
 CHPIR_API int chpir_cluster_server_get_info(const chpir_cluster_server *srv, chpir_cluster_server_info *out);
 

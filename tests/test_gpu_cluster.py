@@ -235,8 +235,9 @@ def test_cluster_tiny_matrix_with_empty_query_slices(n, cut):
 @pytest.mark.parametrize("cut", CUTS)
 @pytest.mark.parametrize("n", [2, 3, 8])
 def test_cluster_page_locked_queries_are_fetched_by_the_gpus(n, cut):
-    """Queries in chpir_host_alloc memory (any 4-byte alignment) are pulled by one kernel per GPU and batch instead of one DMA per query
-    and GPU; pageable queries in the same batches take the DMA route; CHPIR_CLUSTER_INGEST=dma turns the pull off.  Same bytes always."""
+    """Queries in chpir_host_alloc memory (any 4-byte alignment) are moved with one call per GPU and batch (cudaMemcpyBatchAsync, or the
+    pull kernel with CHPIR_CLUSTER_INGEST=pull) instead of one DMA per query and GPU; pageable queries in the same batches take the
+    DMA route; CHPIR_CLUSTER_INGEST=dma is the per-query route for everything.  Same bytes always."""
     need(n)
     rng = np.random.default_rng(800 + n)
     K, N, b = 30011, 203, 9
@@ -284,16 +285,18 @@ def test_cluster_page_locked_queries_are_fetched_by_the_gpus(n, cut):
         th.join()
     assert not errs and [out[i] for i in range(8)] == want[:8]
     assert [r_pin.array[i * rlen: (i + 1) * rlen].tobytes() for i in range(8, Q)] == want[8:]
-    # the batch call and the switch
+    # the batch call and the switch: the pull kernel instead of the copy engines' batch call, then per-query DMA
     assert srv.respond_batch([qbytes(q) for q in qs[:9]]) == want[:9]
-    os.environ["CHPIR_CLUSTER_INGEST"] = "dma"
-    try:
-        pulled = srv.get_info()["pulled_queries"]
-        srv.respond_concurrent(ptrs, qlen, Q, r_pin.ptr, rlen, 8)
-        assert srv.get_info()["pulled_queries"] == pulled
-        assert [r_pin.array[i * rlen: (i + 1) * rlen].tobytes() for i in range(Q)] == want
-    finally:
-        os.environ.pop("CHPIR_CLUSTER_INGEST", None)
+    for route in ("pull", "dma"):
+        os.environ["CHPIR_CLUSTER_INGEST"] = route
+        try:
+            r_pin.array[:] = 0
+            pulled = srv.get_info()["pulled_queries"]
+            srv.respond_concurrent(ptrs, qlen, Q, r_pin.ptr, rlen, 8)
+            assert srv.get_info()["pulled_queries"] == pulled + (Q if route == "pull" else 0)
+            assert [r_pin.array[i * rlen: (i + 1) * rlen].tobytes() for i in range(Q)] == want
+        finally:
+            os.environ.pop("CHPIR_CLUSTER_INGEST", None)
     srv.close()
     cl.close()
     q_pin.close()
