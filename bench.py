@@ -428,6 +428,34 @@ def check_against_exact(torch, cluster, plans, Ds, q_rows_dev0, out_rows_dev0, n
     return ok
 
 
+def h2d_bound_live(cp, torch, cluster, plans, q_ptr0, qlen, Q, ks, reps=4):
+    """The PCIe ceiling of the e2e leg, measured on this box with the e2e leg's own traffic: every GPU copies its K/n words of the Q
+    page-locked queries (one strided copy-engine transfer per GPU and pass, all GPUs at once) -- no kernels, no batching logic.
+    Returns (aggregate GB/s, queries/s that rate allows)."""
+    from chalametpir_b200._lib import lib
+    from chalametpir_b200.errors import check
+
+    devs = cluster.devices
+    dsts = [torch.empty((Q, ks), dtype=torch.int32, device=f"cuda:{d}") for d in devs]
+    streams = [torch.cuda.Stream(device=d) for d in devs]
+
+    def one_pass():
+        for r, p in enumerate(plans):
+            if p["k_count"]:
+                with torch.cuda.device(devs[r]):
+                    check(lib.chpir_upload_rows(dsts[r].data_ptr(), ks * 4, q_ptr0 + 8 + 4 * p["k_begin"], qlen, p["k_count"] * 4, Q, streams[r].cuda_stream))
+
+    one_pass()
+    sync_devices(torch, devs)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    sync_devices(torch, devs)
+    dt = time.perf_counter() - t0
+    nbytes = reps * Q * 4 * sum(p["k_count"] for p in plans)
+    return nbytes / dt / 1e9, reps * Q / dt
+
+
 def int8_peak_live(torch, dev):
     """MEASURED_PEAKS.json has no int8 figure: measure the library's dense int8 GEMM here (cuBLASLt through torch._int_mm, 8192^3, best of
     10); fall back to 2 x the measured bf16 figure."""
@@ -718,6 +746,7 @@ def run_b200(args):
     for _ in range(30):
         lat.append(srv.respond_concurrent(q_host_ptrs[:1], qlen, 1, r_pin.ptr, rlen, 1) * 1e3)
     single_ms = statistics.median(lat[5:])
+    h2d_gbs, h2d_qps = h2d_bound_live(cp, torch, cluster, plans, q_pin.ptr, qlen, Q, ks)
 
     # ---------------- batched respond on the tensor cores, device-resident (128 fill one M tile)
     batched = None
@@ -818,8 +847,10 @@ def run_b200(args):
                 "seconds": e2e_s, "coalesced_batches": co["batches"], "coalesced_tensor_core_batches": co["tc_batches"],
                 "mean_batch": co["queries"] / max(1, co["batches"]),
                 "single_caller_ms": single_ms, "single_caller_published_reference_ms": PUBLISHED["server_respond_2^20_3wise_ms"],
-                "pcie_bound_queries_per_s": n_gpus * 52.0e9 / (4 * K),
-                "pcie_bound_note": "4K bytes per query over n_gpus links at the 52 GB/s one link measured in round 1 (tools/h2d_probe.cu)"},
+                "pcie_bound_queries_per_s": h2d_qps, "pcie_aggregate_h2d_gbs": h2d_gbs,
+                "pcie_bound_note": "measured in this run: the same page-locked query buffers copied to the GPUs' HBM (each GPU its K/n words of every query, all "
+                                   "GPUs at once, copy engines only) -- the rate at which this host can feed 4K bytes per query to the n GPUs",
+                "stage_ms_per_batch": {k: round(co[k] / max(1, co["batches"]) * 1e3, 3) for k in ("ingest_wait_s", "ingest_s", "exec_wait_s", "exec_s")}},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -43,7 +43,9 @@ constexpr uint32_t kMaxRanks = 16;
 constexpr uint32_t kMaxBatch = Coalescer::kMaxBatch;       // queries per coalesced batch = one M tile of the limb GEMM
 constexpr uint32_t kTcFrom = Coalescer::kTensorCoreFrom;   // below this many queries the streaming GEMV is cheaper
 constexpr uint32_t kGemvChunk = 32;                        // device-resident GEMV path, column cut: queries per all-gather / launch
-constexpr uint32_t kSlots = 3;                             // coalescing slots: one collecting callers, one on PCIe, one on the SMs
+constexpr uint32_t kIngestDepth = 2;                       // batches whose queries may be crossing PCIe at once: the second one's copies
+                                                           // are queued while the first one's run, so the links never wait for a host thread
+constexpr uint32_t kSlots = 2 + kIngestDepth;              // coalescing slots: one collecting callers, kIngestDepth on PCIe, one on the SMs
 
 // ---- NCCL, resolved at run time (the library has no link-time dependency on it: single-GPU users never load it) -----------------
 struct NcclApi {
@@ -406,7 +408,12 @@ struct chpir_cluster_server {
   // callers waiting for a slot that takes members, a leader waiting for its members' uploads / for the next slot to be vacated,
   // members waiting for their batch's responses
   std::condition_variable cv_open, cv_free, cv_issued[kSlots], cv_done[kSlots];
-  std::mutex ingest_mu, exec_mu;
+  std::mutex exec_mu;
+  // the ingest stage admits kIngestDepth batches (tickets handed out in arrival order)
+  std::mutex ingest_mu;
+  std::condition_variable ingest_cv;
+  uint32_t ingest_busy = 0;
+  uint64_t ingest_next = 0, ingest_serving = 0;
   CBatch cb[kSlots];
   int open = 0;
   bool co_ready = false;
@@ -717,10 +724,10 @@ int ingest_batch(chpir_cluster_server *S, CBatch &B, uint32_t nq) {
 }
 
 // One caller's share of a coalesced batch: the protocol of api.cu's respond_coalesced with n GPUs behind it and two pipeline
-// stages.  The first caller of a batch is its leader.  It waits for the ingest stage -- that wait IS the batching window: an idle
-// server means a batch of one and no added latency, a busy one means everybody who arrives while the previous batch is crossing
-// PCIe shares this one -- closes the batch, moves its queries, waits for the exec stage and runs the kernels while the next batch
-// is already being ingested.
+// stages.  The first caller of a batch is its leader.  It waits for a place in the ingest stage -- that wait IS the batching window:
+// an idle server means a batch of one and no added latency, a busy one means everybody who arrives while the previous batches are
+// crossing PCIe shares this one -- closes the batch, moves its queries, waits for the exec stage and runs the kernels while the next
+// batches are already being ingested.
 int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t query_len, uint8_t *resp_out) {
   const bool pull = pullable(query, query_len);
   CBatch *B = nullptr;
@@ -749,7 +756,13 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
   }
   if (leader) {
     const double w0 = now_s();
-    std::unique_lock<std::mutex> ingest(S->ingest_mu);
+    {
+      std::unique_lock<std::mutex> lk(S->ingest_mu);
+      const uint64_t ticket = S->ingest_next++;
+      S->ingest_cv.wait(lk, [&] { return S->ingest_serving == ticket && S->ingest_busy < kIngestDepth; });
+      S->ingest_serving++, S->ingest_busy++;
+    }
+    S->ingest_cv.notify_all();
     const double w1 = now_s();
     uint32_t nq = 0;
     int rc = CHPIR_OK;
@@ -771,7 +784,11 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
     bool tc = false;
     {
       std::lock_guard<std::mutex> ex(S->exec_mu);
-      ingest.unlock();
+      {
+        std::lock_guard<std::mutex> lk(S->ingest_mu);
+        S->ingest_busy--;
+      }
+      S->ingest_cv.notify_all();
       w3 = now_s();
       if (rc == CHPIR_OK) rc = run_batch(S, *B, nq, &tc);
     }
