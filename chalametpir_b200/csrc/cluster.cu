@@ -924,6 +924,24 @@ int for_each_rank_parallel(uint32_t n, F f) {
   return CHPIR_OK;
 }
 
+// ncclCommInitAll takes about a second; it depends on nothing the setup computes, so it runs beside the XOF / GEMM phase and the hint
+// gather finds the communicators ready.
+struct EarlyNccl {
+  std::thread th;
+  EarlyNccl(chpir_cluster *cl, uint32_t n, const chpir_setup_opts &o) {
+    if (n > 1 && !o.skip_hint && !env_is("CHPIR_CLUSTER_GATHER", "p2p"))
+      th = std::thread([cl] {
+        DeviceRestore restore_device;
+        std::lock_guard<std::mutex> g(cl->mu);
+        (void)cl->ensure_comms();  // a failure is reported by the gather, which asks again
+      });
+  }
+  void wait() {
+    if (th.joinable()) th.join();
+  }
+  ~EarlyNccl() { wait(); }
+};
+
 // Where a setup flavour left D: the whole matrix in host memory, or the ranks' compact column slices in their HBM.
 struct DSource {
   const uint32_t *host = nullptr;
@@ -1205,12 +1223,14 @@ int chpir_cluster_server_setup_device(chpir_cluster *cl, const uint8_t seed[CHPI
   if (int rc = check_opts(cl, opts, &o); rc != CHPIR_OK) return rc;
   const double t0 = now_s();
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, rows_k, cols_n, b, o));
+  EarlyNccl nccl(cl, S->n, o);
   int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
     if (!d_slices[d]) return CHPIR_ERR_INVALID_ARGUMENT;
     const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, true, S->n);
     return chpir_server_setup_device(S->r[d].ctx, seed, d_slices[d], rows_k, S->r[d].pl.nc, b, &ro, nullptr, 0, nullptr, &S->r[d].srv);
   });
   if (rc != CHPIR_OK) return rc;
+  nccl.wait();
   DSource dsrc;
   dsrc.dev_slices = d_slices;
   if ((rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len)) != CHPIR_OK) return rc;
@@ -1234,11 +1254,13 @@ int chpir_cluster_server_setup(chpir_cluster *cl, const uint8_t seed[CHPIR_SEED_
   if (int rc = check_opts(cl, opts, &o); rc != CHPIR_OK) return rc;
   const double t0 = now_s();
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, rows_k, cols_n, b, o));
+  EarlyNccl nccl(cl, S->n, o);
   int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
     const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false, S->n);
     return server_setup_from_host_matrix(S->r[d].ctx, seed, d_host, rows_k, cols_n, b, &ro, nullptr, 0, nullptr, &S->r[d].srv, nullptr);
   });
   if (rc != CHPIR_OK) return rc;
+  nccl.wait();
   DSource dsrc;
   dsrc.host = d_host;
   if ((rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len)) != CHPIR_OK) return rc;
@@ -1271,6 +1293,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   if (N < uint64_t(cl->n)) return CHPIR_ERR_INVALID_ARGUMENT;
   const double t0 = now_s();
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, K, uint32_t(N), b, o));
+  EarlyNccl nccl(cl, S->n, o);
   std::unique_ptr<uint32_t[]> d_store;  // n > 1: D, encoded once on the host; lives until the row blocks have been cut from it
   if (S->n == 1) {
     // one GPU: the single-GPU call as it is (device row fill, its own early XOF start, its coalescer), hint slice = whole hint
@@ -1314,6 +1337,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
     if (rc != CHPIR_OK) return rc;
     for (uint32_t d = 0; d < S->n; d++) S->r[d].srv->timing.host_encode_s = t1 - t0;
   }
+  nccl.wait();
   DSource dsrc;
   dsrc.host = d_store.get();
   if (int rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len); rc != CHPIR_OK) return rc;
