@@ -16,7 +16,17 @@
 //   split_transpose_b  D[k][n] u32 (ld)       -> B8[NB][n][kp]  u8   (limb split + shared-memory tiled transpose)
 // The main kernel is warp specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, OOB zero fill for
 // the ragged M/N/K edges), warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld).
+//
+// Clusters.  TMEM holds one 128 x 128 output tile per SM (4 shift accumulators x 128 columns = all 512 columns), so a k-block costs
+// every CTA 64 KB of A (four limb tiles) + 32 KB of B from L2, and round 1 measured the kernel bound by exactly that: ~4700 B/clk
+// of L2 -> SM delivery chip-wide, 70 % tensor-pipe activity.  The N tiles of one K range all read the SAME A tile, so they form a
+// thread-block cluster along N (2, 4 or 8 CTAs) in which every CTA fetches 1/csz of the A tile and TMA-multicasts it to all of
+// them: L2 reads per CTA and k-block drop from 96 KB to 32 + 64/csz KB.  A stage is released to the producers by the MMA commits
+// of ALL CTAs of the cluster (tcgen05.commit ... multicast::cluster onto every CTA's `empty` barrier), since any of them may be
+// written by any peer.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -72,6 +82,23 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t cta_mask) {
+  // the tile lands at the same shared-memory offset of every CTA in cta_mask and completes bytes on the barrier at `bar`'s offset there
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, swizzled operand tile: rows of BK bytes (128B or 64B swizzle), 8-row groups 8*BK bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -95,6 +122,10 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -111,11 +142,13 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-// grid: (tiles_m * tiles_n, splits).  One output tile x one K range per CTA.
+// grid: (tiles_m * tiles_n, splits), cluster (csz, 1, 1) along the N tiles.  One output tile x one K range per CTA.
+// map_a: box of 128 rows (csz = 1); map_a64: box of 64 rows, the unit of the multicast A slices (csz > 1).
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, uint32_t *__restrict__ C, uint32_t m,
-                   uint32_t n, uint32_t tiles_n, uint32_t bn, uint32_t kblocks_total, uint32_t kblocks_per_split) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a64, const __grid_constant__ CUtensorMap map_b,
+                   uint32_t *__restrict__ C, uint32_t m, uint32_t n, uint32_t tiles_n, uint32_t bn, uint32_t kblocks_total, uint32_t kblocks_per_split,
+                   uint32_t csz) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ Barriers bars;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,14 +161,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (kb1 > kblocks_total) kb1 = kblocks_total;
   const uint32_t nkb = kb1 > kb0 ? kb1 - kb0 : 0;
 
+  const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = uint16_t((1u << csz) - 1u);
+
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(csz > 1 ? &map_a64 : &map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&bars.full[s], 1);
-      mbar_init(&bars.empty[s], 1);
+      mbar_init(&bars.empty[s], csz);  // one commit from every CTA that reads (and whose peers write) this stage
     }
     mbar_init(&bars.acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (csz > 1) cluster_sync_all();  // every CTA's barriers exist before a peer's multicast or commit can reach them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = bars.tmem_base;
 
@@ -162,8 +199,17 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_expect_tx(&bars.full[s], tx_bytes);
           uint8_t *st = smem + s * STAGE_BYTES;
           const int kc = int((kb0 + i) * BK);
+          if (csz == 1) {
 #pragma unroll
-          for (int l = 0; l < 4; l++) tma_load_3d(st + l * A_TILE, &map_a, &bars.full[s], kc, int(tile_m * BM), l);
+            for (int l = 0; l < 4; l++) tma_load_3d(st + l * A_TILE, &map_a, &bars.full[s], kc, int(tile_m * BM), l);
+          } else {
+            // the A stage is 8 half-limb slices of 64 rows; this CTA fetches 8 / csz of them for everybody
+            const uint32_t per = 8u / csz;
+            for (uint32_t j = crank * per; j < (crank + 1) * per; j++) {
+              const uint32_t l = j >> 1, half = j & 1u;
+              tma_load_3d_mc(st + l * A_TILE + half * (64 * BK), &map_a64, &bars.full[s], kc, int(tile_m * BM + half * 64), int(l), cmask);
+            }
+          }
 #pragma unroll
           for (int l = 0; l < NB; l++) tma_load_3d(st + 4 * A_TILE + l * B_TILE, &map_b, &bars.full[s], kc, int(tile_n * bn), l);
         }
@@ -212,7 +258,11 @@ __global__ void __launch_bounds__(kThreads, 1)
               }
             }
           }
-          umma_commit(&bars.empty[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose producers all write into it
+          if (csz == 1)
+            umma_commit(&bars.empty[s]);
+          else
+            umma_commit_mc(&bars.empty[s], cmask);
         }
         umma_commit(&bars.acc_full);
       }
@@ -244,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (csz > 1) cluster_sync_all();  // no CTA leaves while a peer's commit may still be on its way to this CTA's barriers
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
@@ -278,8 +329,12 @@ template <int NB>
 __global__ void __launch_bounds__(256) split_transpose_b(const uint32_t *__restrict__ B, uint64_t k, uint32_t n, uint32_t ld, uint64_t kp,
                                                           uint8_t *__restrict__ planes) {
   __shared__ __align__(4) uint8_t tile[NB][32][128 + 4];
-  const uint64_t k0 = uint64_t(blockIdx.x) * 128;
-  const uint32_t n0 = blockIdx.y * 32;
+  // the (1D) grid walks the n tiles of one band of 128 k-rows first: a row of B is not sector aligned (3760 bytes at N = 940), and the sectors
+  // two neighbouring tiles share are then requested by CTAs that run together (one DRAM read, an L2 hit for the other) instead of
+  // thousands of CTAs apart (round 1: 8.4 GB read for a 4.4 GB operand)
+  const uint32_t tiles_n = (n + 31) / 32;
+  const uint64_t k0 = uint64_t(blockIdx.x / tiles_n) * 128;
+  const uint32_t n0 = (blockIdx.x % tiles_n) * 32;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // ty in 0..7
   for (int kk = ty; kk < 128; kk += 8) {
     const uint64_t gk = k0 + kk;
@@ -339,7 +394,8 @@ struct GemmTcB {
   uint8_t *a_ring = nullptr;  // two panel buffers [4][128][kp]
   uint64_t k = 0, kp = 0;
   uint32_t n = 0, nb = 0, bn = 0, tiles_n = 0, kblocks = 0, kbps = 0, splits = 0;
-  CUtensorMap map_b{}, map_a[2]{};
+  uint32_t csz = 1;  // thread-block cluster along the N tiles (A multicast), 1 = none
+  CUtensorMap map_b{}, map_a[2]{}, map_a64[2]{};
   // Last reader of each ring buffer (the panel GEMM that consumed it), on whatever stream it ran: callers on different streams
   // -- concurrent respond_batch / coalesced respond / respond_device_tc on one server -- order themselves against it before
   // refilling the buffer (gemm_tc_buf_acquire / gemm_tc_buf_release), so the ring can be shared without serialising execution.
@@ -380,7 +436,12 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
       rc = CHPIR_ERR_CUDA_ALLOCATION_FAILED;
       break;
     }
-    dim3 grid(unsigned((g->kp + 127) / 128), (n + 31) / 32);
+    const uint64_t tr_tiles = uint64_t((n + 31) / 32) * ((g->kp + 127) / 128);
+    if (tr_tiles > 0x7fffffffull) {
+      rc = CHPIR_ERR_INVALID_ARGUMENT;
+      break;
+    }
+    dim3 grid{unsigned(tr_tiles)};
     if (g->nb == 1)
       split_transpose_b<1><<<grid, 256, 0, s>>>(B, k, n, ldb, g->kp, g->b8);
     else
@@ -390,12 +451,45 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
       break;
     }
     const uint32_t tiles_n0 = (n + BN_MAX - 1) / BN_MAX;
-    uint32_t bn = ((n + tiles_n0 - 1) / tiles_n0 + 15) / 16 * 16;
+    // cluster size: the largest power of two <= min(CHPIR_GEMM_CLUSTER (default 4), number of N tiles); the tile count is rounded up
+    // to a multiple of it (a tile past column n loads zeros and publishes nothing) and the tile width shrinks to match
+    uint32_t csz = 4;
+    if (const char *v = std::getenv("CHPIR_GEMM_CLUSTER"); v && *v) csz = uint32_t(std::strtoul(v, nullptr, 10));
+    if (csz != 1 && csz != 2 && csz != 4 && csz != 8) csz = 4;
+    while (csz > 1 && csz > tiles_n0) csz /= 2;
+    g->csz = csz;
+    const uint32_t tiles = (tiles_n0 + csz - 1) / csz * csz;
+    uint32_t bn = ((n + tiles - 1) / tiles + 15) / 16 * 16;
     if (bn < 16) bn = 16;
     g->bn = bn;
-    g->tiles_n = (n + bn - 1) / bn;
+    g->tiles_n = csz > 1 ? tiles : (n + bn - 1) / bn;
     g->kblocks = uint32_t((k + BK - 1) / BK);
-    // one launch = one 128-row panel: split K so that tiles_n * splits fills whole waves of sm_count CTAs
+    constexpr int smem1 = STAGES * (4 * A_TILE + 1 * B_TILE) + 1024, smem2 = STAGES * (4 * A_TILE + 2 * B_TILE) + 1024;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) {
+      rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+      break;
+    }
+    // CTAs of one wave: every SM, or -- with clusters -- as many whole clusters as the GPCs can host at once
+    uint32_t wave = uint32_t(sm_count);
+    if (csz > 1) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(g->tiles_n, 1, 1), cfg.blockDim = dim3(kThreads, 1, 1);
+      cfg.dynamicSmemBytes = g->nb == 1 ? smem1 : smem2;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = csz, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+      cfg.attrs = &at, cfg.numAttrs = 1;
+      int clusters = 0;
+      const cudaError_t e = g->nb == 1 ? cudaOccupancyMaxActiveClusters(&clusters, gemm_tc_kernel<1>, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&clusters, gemm_tc_kernel<2>, &cfg);
+      if (e != cudaSuccess || clusters < 1) {
+        (void)cudaGetLastError();
+        clusters = sm_count / int(csz);
+      }
+      wave = uint32_t(clusters) * csz;
+    }
+    // one launch = one 128-row panel: split K so that tiles_n * splits fills whole waves
     uint32_t best_splits = 1;
     double best_eff = 0.0;
     uint32_t max_splits = g->kblocks / (1024 / BK);  // every split keeps >= 1024 k of mainloop per epilogue
@@ -403,22 +497,18 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
     if (max_splits > 148) max_splits = 148;
     for (uint32_t sp = 1; sp <= max_splits; sp++) {
       const uint64_t units = uint64_t(g->tiles_n) * sp;
-      const uint64_t waves = (units + sm_count - 1) / sm_count;
-      const double eff = double(units) / double(waves * sm_count);
+      const uint64_t waves = (units + wave - 1) / wave;
+      const double eff = double(units) / double(waves * wave);
       if (eff > best_eff + 0.02) best_eff = eff, best_splits = sp;
     }
     g->kbps = (g->kblocks + best_splits - 1) / best_splits;
     g->splits = (g->kblocks + g->kbps - 1) / g->kbps;
     if ((rc = make_map(&g->map_b, g->b8, k, g->kp, n, g->nb, bn)) != CHPIR_OK) break;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 2; i++) {
       if ((rc = make_map(&g->map_a[i], g->a_ring + i * gemm_tc_panel_bytes(g), k, g->kp, BM, 4, BM)) != CHPIR_OK) break;
-    if (rc != CHPIR_OK) break;
-    constexpr int smem1 = STAGES * (4 * A_TILE + 1 * B_TILE) + 1024, smem2 = STAGES * (4 * A_TILE + 2 * B_TILE) + 1024;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess) {
-      rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-      break;
+      if ((rc = make_map(&g->map_a64[i], g->a_ring + i * gemm_tc_panel_bytes(g), k, g->kp, BM, 4, 64)) != CHPIR_OK) break;
     }
+    if (rc != CHPIR_OK) break;
   } while (false);
   if (rc != CHPIR_OK) {
     if (rc != CHPIR_ERR_INVALID_ARGUMENT) set_last_cuda_error(cudaGetLastError(), "gemm_tc_prepare");
@@ -431,15 +521,22 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
 
 // C_panel[rows x n] += A_panel . B  for the panel held in ring buffer `buf` (rows <= 128).  C must have been zeroed.
 int gemm_tc_panel(const GemmTcB *g, int buf, uint32_t rows, uint32_t *C_panel, cudaStream_t s) {
-  const dim3 grid(g->tiles_n, g->splits);
-  if (g->nb == 1) {
-    constexpr int smem_bytes = STAGES * (4 * A_TILE + 1 * B_TILE) + 1024;
-    gemm_tc_kernel<1><<<grid, kThreads, smem_bytes, s>>>(g->map_a[buf], g->map_b, C_panel, rows, g->n, g->tiles_n, g->bn, g->kblocks, g->kbps);
-  } else {
-    constexpr int smem_bytes = STAGES * (4 * A_TILE + 2 * B_TILE) + 1024;
-    gemm_tc_kernel<2><<<grid, kThreads, smem_bytes, s>>>(g->map_a[buf], g->map_b, C_panel, rows, g->n, g->tiles_n, g->bn, g->kblocks, g->kbps);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g->tiles_n, g->splits, 1), cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = STAGES * (4 * A_TILE + int(g->nb) * B_TILE) + 1024;
+  cfg.stream = s;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = g->csz, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+  cfg.attrs = &at, cfg.numAttrs = g->csz > 1 ? 1 : 0;
+  const cudaError_t e =
+      g->nb == 1 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, g->map_a[buf], g->map_a64[buf], g->map_b, C_panel, rows, g->n, g->tiles_n, g->bn, g->kblocks, g->kbps, g->csz)
+                 : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g->map_a[buf], g->map_a64[buf], g->map_b, C_panel, rows, g->n, g->tiles_n, g->bn, g->kblocks, g->kbps, g->csz);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   }
-  return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+  return CHPIR_OK;
 }
 
 // u32 rows [row0, row0 + rows) of A (row-major, k columns) -> limb planes of ring buffer `buf`.
