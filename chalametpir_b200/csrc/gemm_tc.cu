@@ -451,11 +451,19 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
       break;
     }
     const uint32_t tiles_n0 = (n + BN_MAX - 1) / BN_MAX;
-    // cluster size: the largest power of two <= min(CHPIR_GEMM_CLUSTER (default 4), number of N tiles); the tile count is rounded up
-    // to a multiple of it (a tile past column n loads zeros and publishes nothing) and the tile width shrinks to match
-    uint32_t csz = 4;
-    if (const char *v = std::getenv("CHPIR_GEMM_CLUSTER"); v && *v) csz = uint32_t(std::strtoul(v, nullptr, 10));
-    if (csz != 1 && csz != 2 && csz != 4 && csz != 8) csz = 4;
+    // Cluster size.  Measured on a B200 (profiles/r2_gemm_sweep.txt, 128-query batch incl. the limb split of the queries):
+    //   2^20 shape, 8 N tiles: 1.029 ms without clusters, 0.962 / 1.007 / 1.078 ms with clusters of 2 / 4 / 8;
+    //   2^18 shape, 7 N tiles: 0.235 ms without, 0.258+ with (the tile count is rounded up to a multiple of the cluster size -- a tile
+    //   past column n loads zeros and publishes nothing -- so an eighth, empty tile is paid for).
+    // Multicast removes L2 READS, and the gain is small: what bounds the kernel is the bytes DELIVERED to each SM's shared memory
+    // (96 KB per k-block whoever fetched them; ~31 B/clk per SM with all SMs streaming), and TMEM fixes the tile at 128 x 128 x 4
+    // accumulators, so the bytes per MAC cannot shrink further without pairing SMs (cta_group::2 would share the B tile: 80 KB).
+    // Default: pairs when the tile count is even, none otherwise; CHPIR_GEMM_CLUSTER = 1 / 2 / 4 / 8 overrides.
+    uint32_t csz = tiles_n0 % 2 == 0 ? 2 : 1;
+    if (const char *v = std::getenv("CHPIR_GEMM_CLUSTER"); v && *v) {
+      csz = uint32_t(std::strtoul(v, nullptr, 10));
+      if (csz != 1 && csz != 2 && csz != 4 && csz != 8) csz = 1;
+    }
     while (csz > 1 && csz > tiles_n0) csz /= 2;
     g->csz = csz;
     const uint32_t tiles = (tiles_n0 + csz - 1) / csz * csz;
