@@ -7,9 +7,18 @@
 //     own[e] = ( field_e(digest || value || 0x81) - D[o1][e] - D[o2][e] (- D[o3][e]) - mix(hash, e) ) & (2^b - 1)
 // where field_e is the e-th b-bit field, LSB first, of the byte string (the reference's bit packing), o1..o3 are the key's other
 // filter slots and mix is the reference's murmur finaliser (binary_fuse_filter.rs:553-560).  The rows a key reads belong to keys
-// peeled later, so the keys are processed in dependency waves (one launch per wave; a wave's members are mutually independent).
+// peeled later, so the keys are processed in dependency waves (a wave's members are mutually independent).
 // D is written row-major u32, exactly the matrix the reference would hold, so everything downstream (pack, limb split, GEMM)
 // is unchanged and the bytes can be compared with the host encoder one to one.
+//
+// Two schedules of the same arithmetic:
+//   * column ownership (default): ONE launch.  The dependency is per column -- own[e] needs o1[e], o2[e] of the SAME column e -- so
+//     a warp that owns 32 columns and walks ALL keys in wave order only ever reads what it wrote itself: program order replaces every
+//     inter-thread synchronisation.  N / 32 warps (30 at N = 940), one per SM, each keeping 8 keys x 3 rows of loads in flight
+//     inside a wave; the 28 600 waves of a 2^20-entry filter cost one L2 round trip each instead of one kernel launch each.
+//   * one launch per wave, one CTA per key (round 1; CHPIR_FILL=waves): kept as the cross-check.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace chpir {
@@ -94,6 +103,99 @@ __global__ void __launch_bounds__(kFillThreads) fill_wave_kernel(FillArgs a, uin
   }
 }
 
+// ---- column ownership ----------------------------------------------------------------------------------------------------------------
+struct FillRec {  // one key, in wave order: everything the fill needs that does not depend on the column
+  uint64_t hash, v0;
+  uint32_t own, o1, o2, o3;  // rows of D: the slot the key owns and its other slots
+  uint32_t vlen, key;
+};
+static_assert(sizeof(FillRec) == 40, "ten words per record");
+
+template <int ARITY>
+__global__ void __launch_bounds__(256) fill_prep_kernel(FillArgs a, uint64_t count, FillRec *__restrict__ rec) {
+  const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (j >= count) return;
+  const uint32_t i = a.members[j];
+  const uint64_t hash = a.order[i];
+  const uint32_t which = a.found[i], key = a.key_of_order[i];
+  uint32_t h[4];
+  slots_dev<ARITY>(hash, a.segment_length, a.segment_count_length, h);
+  FillRec r;
+  r.hash = hash, r.v0 = a.val_off[key], r.vlen = uint32_t(a.val_off[key + 1] - r.v0), r.key = key;
+  r.own = h[which], r.o1 = h[(which + 1) % ARITY], r.o2 = h[(which + 2) % ARITY], r.o3 = h[(which + 3) % ARITY];
+  rec[j] = r;
+}
+
+constexpr int kFillUnroll = 8;
+
+// One warp per CTA, lane = column blockIdx.x * 32 + lane.  Records are fetched 32 at a time (one per lane, coalesced, one chunk
+// ahead) and handed round by shuffles; within a chunk -- which never crosses a wave boundary -- kFillUnroll keys are in flight.
+template <int ARITY>
+__global__ void __launch_bounds__(32) fill_columns_kernel(const FillRec *__restrict__ rec, const uint32_t *__restrict__ level_start, uint32_t waves,
+                                                          const uint8_t *__restrict__ digests, const uint8_t *__restrict__ values, uint32_t *D,
+                                                          uint64_t N, uint32_t b) {
+  const uint32_t lane = threadIdx.x;
+  const uint64_t e = uint64_t(blockIdx.x) * 32 + lane;
+  const bool act = e < N;
+  const uint64_t ec = act ? e : N - 1;  // inactive lanes of the last warp shadow a real column (loads only)
+  const uint32_t bit = uint32_t(ec) * b, byte0 = bit >> 3, sh = bit & 7, mask = (1u << b) - 1;
+  const uint32_t *recw = reinterpret_cast<const uint32_t *>(rec);
+  const uint64_t base = level_start[0], total = level_start[waves] - base;  // rec[0] is the first key of the first wave
+
+  auto load_rec = [&](uint64_t j0, uint32_t r[10]) {  // lane t: record j0 + t (zeros past the end)
+    const uint64_t j = j0 + lane;
+#pragma unroll
+    for (int w = 0; w < 10; w++) r[w] = j < total ? __ldg(recw + j * 10 + w) : 0u;
+  };
+  // byte t of  digest || value || 0x81 || 0...
+  auto byte_at = [&](uint32_t key, uint64_t v0, uint32_t vlen, uint32_t t) -> uint32_t {
+    if (t < 32) return __ldg(digests + 32ull * key + t);
+    t -= 32;
+    if (t < vlen) return __ldg(values + v0 + t);
+    return t == vlen ? 0x81u : 0u;
+  };
+
+  uint32_t cur[10], nxt[10];
+  uint64_t j = 0;
+  load_rec(j, cur);
+  for (uint32_t l = 0; l < waves; l++) {
+    const uint64_t wave_end = level_start[l + 1] - base;
+    while (j < wave_end) {
+      const uint32_t chunk = uint32_t(wave_end - j < 32 ? wave_end - j : 32);
+      load_rec(j + chunk, nxt);  // the records follow each other whatever the waves are: always one chunk ahead
+      for (uint32_t u0 = 0; u0 < chunk; u0 += kFillUnroll) {
+        uint32_t own[kFillUnroll], v[kFillUnroll], d1[kFillUnroll], d2[kFillUnroll], d3[kFillUnroll];
+        uint64_t hs[kFillUnroll];
+#pragma unroll
+        for (int u = 0; u < kFillUnroll; u++) {
+          const uint32_t src = u0 + u < chunk ? u0 + u : u0;  // the tail of a chunk repeats its first key (result unused)
+          const uint32_t hl = __shfl_sync(0xffffffffu, cur[0], src), hh = __shfl_sync(0xffffffffu, cur[1], src);
+          const uint32_t vl = __shfl_sync(0xffffffffu, cur[2], src), vh = __shfl_sync(0xffffffffu, cur[3], src);
+          own[u] = __shfl_sync(0xffffffffu, cur[4], src);
+          const uint32_t o1 = __shfl_sync(0xffffffffu, cur[5], src), o2 = __shfl_sync(0xffffffffu, cur[6], src);
+          const uint32_t o3 = __shfl_sync(0xffffffffu, cur[7], src);
+          const uint32_t vlen = __shfl_sync(0xffffffffu, cur[8], src), key = __shfl_sync(0xffffffffu, cur[9], src);
+          hs[u] = (uint64_t(hh) << 32) | hl;
+          const uint64_t v0 = (uint64_t(vh) << 32) | vl;
+          d1[u] = __ldcg(D + uint64_t(o1) * N + ec);
+          d2[u] = __ldcg(D + uint64_t(o2) * N + ec);
+          d3[u] = ARITY == 4 ? __ldcg(D + uint64_t(o3) * N + ec) : 0u;
+          v[u] = byte_at(key, v0, vlen, byte0) | byte_at(key, v0, vlen, byte0 + 1) << 8 | byte_at(key, v0, vlen, byte0 + 2) << 16;
+        }
+#pragma unroll
+        for (int u = 0; u < kFillUnroll; u++) {
+          uint32_t x = (v[u] >> sh) & mask;
+          x -= d1[u] + d2[u] + d3[u] + static_cast<uint32_t>(fmix64_dev(hs[u] + ec));
+          if (act && u0 + u < chunk) D[uint64_t(own[u]) * N + e] = x & mask;
+        }
+      }
+      j += chunk;
+#pragma unroll
+      for (int w = 0; w < 10; w++) cur[w] = nxt[w];
+    }
+  }
+}
+
 }  // namespace
 
 // All pointers are device pointers; D must be zeroed.  One launch per wave, in wave order, on stream s.
@@ -113,6 +215,38 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
   a.b = b;
   a.segment_length = segment_length;
   a.segment_count_length = segment_count_length;
+  uint64_t count = 0;
+  for (uint32_t l = 0; l < waves; l++) count += level_start_host[l + 1] - level_start_host[l];
+  const char *mode = std::getenv("CHPIR_FILL");
+  if (count > 0 && !(mode && std::strcmp(mode, "waves") == 0)) {
+    // column ownership: records in wave order, then one launch of N / 32 single-warp CTAs
+    FillRec *rec = nullptr;
+    uint32_t *ls = nullptr;
+    if (cudaMalloc(&rec, count * sizeof(FillRec)) != cudaSuccess || cudaMalloc(&ls, (size_t(waves) + 1) * 4) != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (rec) cudaFree(rec);
+      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    }
+    int rc = CHPIR_OK;
+    a.members = members + level_start_host[0];
+    // the wave table is small and lives in pageable memory the caller may drop after this call: a synchronous copy
+    if (cudaMemcpy(ls, level_start_host, (size_t(waves) + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
+    if (rc == CHPIR_OK) {
+      const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((N + 31) / 32);
+      if (arity == 3) {
+        fill_prep_kernel<3><<<pg, 256, 0, s>>>(a, count, rec);
+        fill_columns_kernel<3><<<fg, 32, 0, s>>>(rec, ls, waves, digests, values, D, N, b);
+      } else {
+        fill_prep_kernel<4><<<pg, 256, 0, s>>>(a, count, rec);
+        fill_columns_kernel<4><<<fg, 32, 0, s>>>(rec, ls, waves, digests, values, D, N, b);
+      }
+      if (cudaGetLastError() != cudaSuccess) rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+      if (rc == CHPIR_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;  // rec and ls go away below
+    }
+    cudaFree(rec);
+    cudaFree(ls);
+    return rc;
+  }
   // every field e < N reads bytes [e*b/8, e*b/8 + 2]
   const uint32_t stream_bytes = uint32_t(((N - 1) * b) / 8 + 3 + 3) & ~3u;
   if (stream_bytes > 200 * 1024) return CHPIR_ERR_INVALID_ARGUMENT;

@@ -236,6 +236,47 @@ def test_full_size_respond_properties(arity, n_log2):
     srv.close()
 
 
+@pytest.mark.parametrize("n_log2", [18, 20])
+def test_full_size_respond_bytes_equal_oracle_on_encoded_db(n_log2):
+    """BASELINE.json configs[1] / configs[2] on a REAL encoded database (2^18 / 2^20 keys of 32 bytes, 1 kB values, 3-wise filter): D is
+    built by the host encoder (byte-identical to the oracle's from_kv_database, checked here in full at 2^18), the oracle keeps it in the
+    reference's layout (transposed + row_wise_compress'ed, matrix.rs:98-205) and answers with the reference's loop (matrix.rs:328-485);
+    the GPU server's response bytes -- streaming GEMV and tensor-core batch route -- must equal the oracle's byte for byte."""
+    import ctypes as C
+
+    from chalametpir_b200._lib import FILTER_PARAM_BYTE_LEN, lib
+    from chalametpir_b200.errors import check
+
+    n = 1 << n_log2
+    rs = np.random.default_rng(n_log2)
+    keys = rs.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    keys[:, :8] = np.arange(n, dtype="<u8").view(np.uint8).reshape(n, 8)  # distinct by construction
+    vals = rs.integers(0, 256, size=(n, 1024), dtype=np.uint8)
+    b = cp.find_mat_elem_bit_len(n)
+    K, N = cp.db_matrix_shape(3, n, 1024, b)
+    ko = np.arange(n + 1, dtype=np.uint64) * np.uint64(32)
+    vo = np.arange(n + 1, dtype=np.uint64) * np.uint64(1024)
+    D = np.empty((K, N), dtype=np.uint32)
+    fbytes = np.empty(FILTER_PARAM_BYTE_LEN, dtype=np.uint8)
+    rng_seed = C.c_uint64(11)
+    check(lib.chpir_encode_kv_database(3, n, keys.ctypes.data, ko.ctypes.data, vals.ctypes.data, vo.ctypes.data, b, 100, C.byref(rng_seed), D.ctypes.data,
+                                       fbytes.ctypes.data))
+    if n_log2 == 18:
+        db = {keys[i].tobytes(): vals[i].tobytes() for i in range(n)}
+        Do, fo = O.from_kv_database(db, b, 3, rng_seed=11)
+        assert fo.to_bytes() == fbytes.tobytes() and np.array_equal(Do, D)
+        del db, Do
+    osrv, _ = O.Server.setup_from_matrix(SEED, D, b, want_hint=False)
+    srv, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True, batch_tc=1)
+    del D
+    rng = np.random.default_rng(1 + n_log2)
+    qs = [rand_u32(rng, K) for _ in range(4)] + [np.ones(K, np.uint32), np.full(K, 0xFFFFFFFF, np.uint32)]
+    want = [osrv.respond(qbytes(q)) for q in qs]
+    assert [srv.respond(qbytes(q)) for q in qs] == want          # streaming GEMV
+    assert srv.respond_batch([qbytes(q) for q in qs]) == want    # 6 queries: the tensor-core limb GEMM
+    srv.close()
+
+
 def test_full_size_batched_tensor_core_respond():
     """BASELINE.json configs[3]: 2^20 entries, 4-wise filter, 64 queries per batch through the int8-limb GEMM.  Checked against
     the streaming GEMV for every query and, independently of both, through unit-vector and all-ones queries inside the batch."""
