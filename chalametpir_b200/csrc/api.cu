@@ -1181,6 +1181,15 @@ int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64
   if (a_rows == 0 || a_cols == 0 || b_rows == 0 || b_cols == 0) return CHPIR_ERR_INVALID_MATRIX_DIMENSION;
   if (a_cols != b_rows) return CHPIR_ERR_INCOMPATIBLE_DIMENSION_FOR_MATRIX_MULTIPLICATION;
   if (a_rows > 0xffffffffull || b_cols > 0xffffffffull) return CHPIR_ERR_INVALID_ARGUMENT;
+  if (b_elem_bit_len == 0 || b_elem_bit_len > 32) return CHPIR_ERR_INVALID_ARGUMENT;
+  // The limb GEMM splits B into two byte limbs: wider entries go to the u32 SIMT kernel (exact for any operand), and entries that
+  // do not fit the width the caller declared are refused instead of being truncated silently by the split.
+  if (variant == 0 && b_elem_bit_len > 16) variant = 1;
+  if (b_elem_bit_len < 32) {
+    const uint32_t limit = 1u << b_elem_bit_len;
+    for (uint64_t i = 0; i < b_rows * b_cols; i++)
+      if (b_host[i] >= limit) return CHPIR_ERR_INVALID_ARGUMENT;
+  }
   std::lock_guard<std::mutex> g(ctx->mu);
   CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
   DevBuf a, b, c;

@@ -357,6 +357,12 @@ __global__ void __launch_bounds__(kRingMaxThreads, 1)
           fma_fields<B>(w[j].x, w[j].y, qk[j], acc);
           fma_fields<B>(w[j].z, w[j].w, qk[j], acc + FPW);
         }
+        // The stage may be overwritten by the bulk-copy engine as soon as this warp has arrived on `empty` below.  Pin the
+        // multiply-adds that consume every word loaded from it in front of that arrive: instructions issue in order, so the arrive
+        // then cannot issue before the shared-memory loads have delivered their data (the write-after-read side of the ring; the
+        // read-after-write side is the acquire of the `full` barrier wait).  compute-sanitizer's racecheck does not model either
+        // mbarrier edge for async-proxy writes and reports the pair (profiles/r2_sanitizer.txt).
+        asm volatile("" : "+r"(acc[0]), "+r"(acc[FPW]));
       }
       __syncwarp();
       // the last stage of a query is handed back only after the epilogue, which uses it as scratch

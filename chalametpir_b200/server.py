@@ -367,7 +367,8 @@ def host_xof_impl() -> str:
 
 
 def matmul(a: np.ndarray, b: np.ndarray, b_elem_bit_len: int = 32, variant: int = 0, device: int = 0) -> np.ndarray:
-    """&A * &B mod 2^32 (matrix.rs:1040-1059) on the GPU. variant 0 = tensor-core limb GEMM, 1 = SIMT u32."""
+    """&A * &B mod 2^32 (matrix.rs:1040-1059) on the GPU. variant 0 = tensor-core limb GEMM (entries of B < 2^b_elem_bit_len <= 2^16;
+    wider B falls through to the SIMT kernel), 1 = SIMT u32.  Entries of B that do not fit b_elem_bit_len raise InvalidArgument."""
     a = np.ascontiguousarray(a, dtype=np.uint32)
     b = np.ascontiguousarray(b, dtype=np.uint32)
     out = np.empty((a.shape[0], b.shape[1]), dtype=np.uint32)

@@ -405,7 +405,9 @@ CHPIR_API int chpir_client_get_info(const chpir_client *client, chpir_client_inf
  * matrix are copied to out_host (row_count*cols u32).  The whole prefix of the XOF stream is walked on device. */
 CHPIR_API int chpir_generate_from_seed(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], uint64_t rows, uint64_t cols,
                              uint64_t row_begin, uint64_t row_count, uint32_t *out_host);
-/* &A * &D (matrix.rs:1040-1059) on device for host operands; variant as in chpir_setup_opts.gemm_variant. */
+/* &A * &D (matrix.rs:1040-1059) on device for host operands; variant as in chpir_setup_opts.gemm_variant.  Every entry of B must be
+ * < 2^b_elem_bit_len (CHPIR_ERR_INVALID_ARGUMENT otherwise); the tensor-core variant covers b_elem_bit_len <= 16 (two byte limbs),
+ * wider B is multiplied by the u32 SIMT kernel whatever `variant` says. */
 CHPIR_API int chpir_matmul(chpir_ctx *ctx, const uint32_t *a_host, uint64_t a_rows, uint64_t a_cols, const uint32_t *b_host, uint64_t b_rows,
                  uint64_t b_cols, uint32_t b_elem_bit_len, uint32_t variant, uint32_t *out_host);
 /* Matrix::generate_from_seed (matrix.rs:541-558) on a host core (csrc/host_xof.cpp; no GPU involved): rows

@@ -74,6 +74,22 @@ def test_matmul_dimension_errors():
     assert e.value.variant == "IncompatibleDimensionForMatrixMultiplication"
 
 
+def test_matmul_operand_width_is_checked_not_truncated():
+    """the default call must work for full-range B (u32 SIMT kernel behind the tensor-core variant's 16-bit limit), and
+    entries wider than the declared width are refused instead of being cut by the limb split."""
+    rng = np.random.default_rng(77)
+    A, B = rand_u32(rng, (33, 129)), rand_u32(rng, (129, 40))
+    assert np.array_equal(cp.matmul(A, B), O.matmul(A, B))          # default width 32 -> exact for any operand
+    B16 = rng.integers(0, 1 << 16, size=(129, 40), dtype=np.uint32)
+    assert np.array_equal(cp.matmul(A, B16, 16), O.matmul(A, B16))  # widest tensor-core width
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.matmul(A, B16 | 0x10000, 16)
+    assert e.value.variant == "InvalidArgument"
+    with pytest.raises(cp.ChalametPIRError) as e:
+        cp.matmul(A, np.full((129, 40), 512, np.uint32), 9)
+    assert e.value.variant == "InvalidArgument"
+
+
 # ------------------------------------------------------------------ Server::setup end to end
 @pytest.mark.parametrize("arity", [3, 4])
 @pytest.mark.parametrize("variant", [0, 1])
