@@ -1,5 +1,6 @@
-"""N > 1 host logic on CPU: two gloo ranks shard the columns, answer for their slice (the oracle stands in for the GPU
-kernels here -- this test is about partition / padding / gather / re-interleave, not arithmetic) and gather."""
+"""N > 1 host logic on CPU: gloo ranks shard the matrix, answer for their share (the oracle stands in for the GPU kernels here -- these
+tests are about partition / padding / gather / reduce, not arithmetic).  Both cuts of csrc/cluster.cu: row blocks of D with an exact
+sum of the partial responses (what respond runs on for n > 1) and column slices (hint; respond with CHPIR_CLUSTER_SHARD=cols)."""
 import os
 import socket
 
@@ -144,4 +145,44 @@ def _pipeline_worker(rank, world, port, K, N, b, steps, out_dir):
 @pytest.mark.parametrize("world", [2, 3])
 def test_pipelined_serving_schedule_with_a_second_group_for_the_gathers(tmp_path, world):
     mp.spawn(_pipeline_worker, args=(world, _free_port(), 503, 118, 9, 5, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
+
+
+def _row_cut_worker(rank, world, port, K, N, b, out_dir):
+    """The row cut of csrc/cluster.cu (respond, n > 1) with the library's own plan: rank r holds rows [k0_r, k0_r + kn_r) of D at full
+    width, zero rows up to the common pitch, and ONLY the words [k0_r, k0_r + kn_r) of every query (garbage behind them: those words
+    face zero rows); the partial responses are added mod 2^32 -- one exact reduce, no query word is exchanged."""
+    import chalametpir_b200 as cp
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(321)  # same D and queries on every rank (each rank USES only its share)
+        D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+        Q = 4
+        q = rng.integers(0, 2**32, size=(Q, K), dtype=np.uint64).astype(np.uint32)
+        pl = cp.cluster_plan(world, rank, K, N)
+        k0, kn, ks = pl["k_begin"], pl["k_count"], pl["k_pitch"]
+        block = np.zeros((ks, N), dtype=np.uint32)
+        block[:kn] = D[k0 : k0 + kn]
+        q_slice = np.full((Q, ks), 0x5A5A5A5A, dtype=np.uint32)
+        q_slice[:, :kn] = q[:, k0 : k0 + kn]
+        srv, _ = O.Server.setup_from_matrix(SEED, block, b, want_hint=False)
+        part = np.stack([O.matrix_from_bytes(srv.respond(O.matrix_to_bytes(q_slice[i : i + 1])))[0] for i in range(Q)])
+        # exact sum mod 2^32: gloo has no unsigned 32-bit sum, int64 lanes cannot overflow for <= 2^31 ranks
+        t = torch.from_numpy(part.astype(np.int64))
+        dist.reduce(t, 0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            total = (t.numpy() & 0xFFFFFFFF).astype(np.uint32)
+            ref, _ = O.Server.setup_from_matrix(SEED, D, b, want_hint=False)
+            for i in range(Q):
+                assert sharding.response_bytes(total[i]) == ref.respond(O.matrix_to_bytes(q[i : i + 1])), i
+            open(os.path.join(out_dir, "ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,K,N", [(2, 997, 37), (3, 4099, 118), (2, 7, 5), (4, 40, 9)])
+def test_gloo_row_cut_partial_responses_sum_to_the_full_response(tmp_path, world, K, N):
+    mp.spawn(_row_cut_worker, args=(world, _free_port(), K, N, 9, str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").read_text() == "ok"
