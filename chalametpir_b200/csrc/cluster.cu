@@ -399,9 +399,11 @@ struct chpir_cluster_server {
   uint32_t N = 0, b = 0, lwe = 0;
   std::vector<Rank> r;
   bool rows = false;        // respond runs on row blocks of D (see the head of this file); false: column slices
+  bool pipeline = false;    // chpir_cluster_server_respond goes through the coalescing pipeline below: always for n > 1, for one GPU
+                            // when chpir_setup_opts.respond_coalesce asks for it (otherwise a lone GPU serves every call on its own slot)
   bool tc = false;          // every rank keeps its limb planes: batches of >= kTcFrom queries take the tensor-core route
   uint32_t gemv_rows = 0;   // queries one GEMV-route batch may hold (column cut: capacity of CBatch::q_full)
-  // coalescer (n > 1; a one-GPU cluster delegates to the shard's own).  A batch passes two stages, each held by one batch at a time:
+  // coalescer.  A batch passes two stages, each held by one batch at a time:
   // ingest (its queries cross PCIe) and exec (kernels + result download); a third slot collects callers meanwhile.
   std::mutex mu;
   // one condition per reason to wait, so that a wake-up reaches only threads it concerns (hundreds of callers share this object):
@@ -543,12 +545,12 @@ int make_streams(chpir_cluster_server *S) {
   return CHPIR_OK;
 }
 
-// The coalescing slots (n > 1), once the shards respond runs on exist.
+// The coalescing slots, once the shards respond runs on exist.
 int make_slots(chpir_cluster_server *S) {
   S->tc = true;
   for (uint32_t d = 0; d < S->n; d++) S->tc = S->tc && S->r[d].srv->gemm != nullptr;
   S->gemv_rows = S->rows ? kMaxBatch : (S->tc ? kTcFrom - 1 : kMaxBatch);
-  if (S->n > 1) {
+  if (S->pipeline) {
     for (CBatch &B : S->cb)
       if (int rc = S->init_batch(B); rc != CHPIR_OK) return rc;
     S->co_ready = true;
@@ -1028,16 +1030,17 @@ chpir_cluster_server *new_server(chpir_cluster *cl, uint64_t K, uint32_t N, uint
   }
   S->ks = S->r[0].pl.ks;
   S->rows = S->n > 1 && !env_is("CHPIR_CLUSTER_SHARD", "cols");
+  S->pipeline = S->n > 1 || o.respond_coalesce != 0;
   return S;
 }
 
 // per-rank options: the rank's columns, hint slice kept in HBM for the gather, no per-shard coalescer (the cluster has its own)
-chpir_setup_opts rank_opts(const chpir_setup_opts &o, const Plan &pl, bool compact, uint32_t n) {
+chpir_setup_opts rank_opts(const chpir_setup_opts &o, const Plan &pl, bool compact) {
   chpir_setup_opts ro = o;
   ro.col_begin = compact ? 0 : pl.c0;
   ro.col_count = compact ? 0 : pl.nc;
   ro.hint_on_device = 1;
-  if (n > 1) ro.respond_coalesce = 0;
+  ro.respond_coalesce = 0;
   return ro;
 }
 
@@ -1226,7 +1229,7 @@ int chpir_cluster_server_setup_device(chpir_cluster *cl, const uint8_t seed[CHPI
   EarlyNccl nccl(cl, S->n, o);
   int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
     if (!d_slices[d]) return CHPIR_ERR_INVALID_ARGUMENT;
-    const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, true, S->n);
+    const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, true);
     return chpir_server_setup_device(S->r[d].ctx, seed, d_slices[d], rows_k, S->r[d].pl.nc, b, &ro, nullptr, 0, nullptr, &S->r[d].srv);
   });
   if (rc != CHPIR_OK) return rc;
@@ -1256,7 +1259,7 @@ int chpir_cluster_server_setup(chpir_cluster *cl, const uint8_t seed[CHPIR_SEED_
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, rows_k, cols_n, b, o));
   EarlyNccl nccl(cl, S->n, o);
   int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
-    const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false, S->n);
+    const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false);
     return server_setup_from_host_matrix(S->r[d].ctx, seed, d_host, rows_k, cols_n, b, &ro, nullptr, 0, nullptr, &S->r[d].srv, nullptr);
   });
   if (rc != CHPIR_OK) return rc;
@@ -1296,9 +1299,10 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   EarlyNccl nccl(cl, S->n, o);
   std::unique_ptr<uint32_t[]> d_store;  // n > 1: D, encoded once on the host; lives until the row blocks have been cut from it
   if (S->n == 1) {
-    // one GPU: the single-GPU call as it is (device row fill, its own early XOF start, its coalescer), hint slice = whole hint
+    // one GPU: the single-GPU call as it is (device row fill, its own early XOF start), hint slice = whole hint
     chpir_setup_opts ro = o;
     ro.hint_on_device = 1;
+    ro.respond_coalesce = 0;
     if (int rc = chpir_server_setup_from_db(S->r[0].ctx, arity, seed, n, key_blob, key_offsets, value_blob, value_offsets, filter_seed_rng, &ro, nullptr, 0,
                                             nullptr, filter_params_out, &S->r[0].srv);
         rc != CHPIR_OK)
@@ -1331,7 +1335,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
     if (rc != CHPIR_OK) return rc;
     const double t1 = now_s();
     rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
-      const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false, S->n);
+      const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false);
       return server_setup_from_host_matrix(S->r[d].ctx, seed, d_store.get(), K, uint32_t(N), b, &ro, nullptr, 0, nullptr, &S->r[d].srv, pipes[d].get());
     });
     if (rc != CHPIR_OK) return rc;
@@ -1389,7 +1393,7 @@ int chpir_cluster_server_load(chpir_cluster *cl, const char *path_prefix, const 
     }
   } cleanup{&shards};
   chpir_setup_opts ro = o;
-  if (n > 1) ro.respond_coalesce = 0;
+  ro.respond_coalesce = 0;  // the cluster has its own coalescer
   int rc = for_each_rank_parallel(n, [&](uint32_t d) -> int {
     const std::string p = std::string(path_prefix) + ".rank" + std::to_string(d) + "of" + std::to_string(n);
     return chpir_server_load(cl->ctx[d], p.c_str(), &ro, &shards[d]);
@@ -1435,7 +1439,7 @@ int chpir_cluster_server_respond(chpir_cluster_server *S, const uint8_t *query, 
   CHPIR_GUARD_BEGIN
   DeviceRestore restore_device;
   if (!S) return CHPIR_ERR_INVALID_ARGUMENT;
-  if (S->n == 1) return chpir_server_respond(S->r[0].srv, query, query_len, resp_out, resp_cap, resp_len);
+  if (!S->pipeline) return chpir_server_respond(S->r[0].srv, query, query_len, resp_out, resp_cap, resp_len);
   if (int rc = validate_query_bytes(S->K, query, query_len); rc != CHPIR_OK) return rc;
   const size_t need = 8 + size_t(S->N) * 4;
   if (!resp_out || resp_cap < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
@@ -1451,7 +1455,7 @@ int chpir_cluster_server_respond_batch(chpir_cluster_server *S, const uint8_t *c
   CHPIR_GUARD_BEGIN
   DeviceRestore restore_device;
   if (!S || !queries || !query_lens || !resp_out) return CHPIR_ERR_INVALID_ARGUMENT;
-  if (S->n == 1) return chpir_server_respond_batch(S->r[0].srv, queries, query_lens, nq, resp_out, resp_stride);
+  if (!S->pipeline) return chpir_server_respond_batch(S->r[0].srv, queries, query_lens, nq, resp_out, resp_stride);
   const size_t need = 8 + size_t(S->N) * 4;
   if (resp_stride < need) return CHPIR_ERR_BUFFER_TOO_SMALL;
   for (uint32_t i = 0; i < nq; i++)
@@ -1682,12 +1686,7 @@ int chpir_cluster_server_get_info(const chpir_cluster_server *S, chpir_cluster_s
   out->reshard_s = S->reshard_s;
   out->pulled_queries = S->pulled;
   out->ingest_wait_s = S->ingest_wait_s, out->ingest_s = S->ingest_s, out->exec_wait_s = S->exec_wait_s, out->exec_s = S->exec_s;
-  if (S->n == 1) {
-    const Coalescer &co = S->r[0].srv->co;
-    out->batches = co.batches, out->queries = co.queries, out->tc_batches = co.tc_batches;
-  } else {
-    out->batches = S->batches, out->queries = S->queries, out->tc_batches = S->tc_batches;
-  }
+  out->batches = S->batches, out->queries = S->queries, out->tc_batches = S->tc_batches;
   return CHPIR_OK;
 }
 

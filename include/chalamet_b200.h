@@ -287,7 +287,8 @@ CHPIR_API int chpir_cluster_plan(uint32_t n_ranks, uint32_t rank, uint64_t rows_
                                  uint64_t *k_begin, uint64_t *k_count, uint64_t *k_pitch);
 
 /* Server::setup on the cluster.  opts as for the single-GPU calls (col_begin / col_count / hint_on_device must be 0: the cluster
- * slices; respond_coalesce is implied for n_gpus > 1; db_encode = DEVICE needs n_gpus = 1).  hint_out receives the COMPLETE
+ * slices; respond_coalesce is implied for n_gpus > 1 and, for n_gpus = 1, selects the cluster's batching pipeline instead of one
+ * slot per call; db_encode = DEVICE needs n_gpus = 1).  hint_out receives the COMPLETE
  * wire-format hint (8 + 4 * lwe_rows * N bytes), byte-identical to a single-GPU setup: each rank computes its column slice and
  * the slices are gathered on GPU 0 (NCCL by default, see CHPIR_CLUSTER_GATHER below) and downloaded once. */
 CHPIR_API int chpir_cluster_server_setup_from_db(chpir_cluster *cluster, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN],

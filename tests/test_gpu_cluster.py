@@ -233,7 +233,7 @@ def test_cluster_tiny_matrix_with_empty_query_slices(n, cut):
 
 
 @pytest.mark.parametrize("cut", CUTS)
-@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("n", [1, 2, 3, 8])
 def test_cluster_page_locked_queries_are_fetched_by_the_gpus(n, cut):
     """Queries in chpir_host_alloc memory (any 4-byte alignment) are moved with one call per GPU and batch (cudaMemcpyBatchAsync, or the
     pull kernel with CHPIR_CLUSTER_INGEST=pull) instead of one DMA per query and GPU; pageable queries in the same batches take the
