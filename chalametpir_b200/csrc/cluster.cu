@@ -45,6 +45,9 @@ constexpr uint32_t kTcFrom = Coalescer::kTensorCoreFrom;   // below this many qu
 constexpr uint32_t kGemvChunk = 32;                        // device-resident GEMV path, column cut: queries per all-gather / launch
 constexpr uint32_t kIngestDepth = 2;                       // batches whose queries may be crossing PCIe at once: the second one's copies
                                                            // are queued while the first one's run, so the links never wait for a host thread
+constexpr uint32_t kSecondMin = 16;                        // ... but a second batch joins one that is still crossing only if it has at least this
+                                                           // many members: a tensor-core pass costs the same for 8 queries as for 128, so
+                                                           // with few callers fewer, larger batches keep the exec stage off the critical path
 constexpr uint32_t kSlots = 2 + kIngestDepth;              // coalescing slots: one collecting callers, kIngestDepth on PCIe, one on the SMs
 
 // ---- NCCL, resolved at run time (the library has no link-time dependency on it: single-GPU users never load it) -----------------
@@ -409,11 +412,9 @@ struct chpir_cluster_server {
   // one condition per reason to wait, so that a wake-up reaches only threads it concerns (hundreds of callers share this object):
   // callers waiting for a slot that takes members, a leader waiting for its members' uploads / for the next slot to be vacated,
   // members waiting for their batch's responses
-  std::condition_variable cv_open, cv_free, cv_issued[kSlots], cv_done[kSlots];
+  std::condition_variable cv_open, cv_free, cv_issued[kSlots], cv_done[kSlots], cv_ingest;
   std::mutex exec_mu;
-  // the ingest stage admits kIngestDepth batches (tickets handed out in arrival order)
-  std::mutex ingest_mu;
-  std::condition_variable ingest_cv;
+  // the ingest stage admits up to kIngestDepth batches, in arrival order (guarded by mu, waited for on cv_ingest)
   uint32_t ingest_busy = 0;
   uint64_t ingest_next = 0, ingest_serving = 0;
   CBatch cb[kSlots];
@@ -743,6 +744,7 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
     row = B->count++;
     B->pull.src[row] = pull ? query : nullptr;
     if (pull) B->n_pull++, B->issued++;  // nothing to upload from this thread: the leader moves it
+    if (B->count == kSecondMin) S->cv_ingest.notify_all();  // the batch has become worth a second place on PCIe
   }
   const bool leader = row == 0;
   if (!pull) {
@@ -758,18 +760,17 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
   }
   if (leader) {
     const double w0 = now_s();
-    {
-      std::unique_lock<std::mutex> lk(S->ingest_mu);
-      const uint64_t ticket = S->ingest_next++;
-      S->ingest_cv.wait(lk, [&] { return S->ingest_serving == ticket && S->ingest_busy < kIngestDepth; });
-      S->ingest_serving++, S->ingest_busy++;
-    }
-    S->ingest_cv.notify_all();
-    const double w1 = now_s();
+    double w1 = w0;
     uint32_t nq = 0;
     int rc = CHPIR_OK;
     {
       std::unique_lock<std::mutex> lk(S->mu);
+      const uint64_t ticket = S->ingest_next++;
+      S->cv_ingest.wait(lk, [&] {
+        return S->ingest_serving == ticket && (S->ingest_busy == 0 || (S->ingest_busy < kIngestDepth && B->count >= kSecondMin));
+      });
+      S->ingest_serving++, S->ingest_busy++;
+      w1 = now_s();
       B->closed = true;
       nq = B->count;
       S->cv_issued[si].wait(lk, [&] { return B->issued == nq; });
@@ -778,6 +779,7 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
       S->cv_free.wait(lk, [&] { return S->cb[next].count == 0 && !S->cb[next].closed; });
       S->open = next;
     }
+    S->cv_ingest.notify_all();  // the next leader in line may now be at the head
     S->cv_open.notify_all();
     const int in = ingest_batch(S, *B, nq);  // also on the error path: the members' DMAs must have drained
     if (rc == CHPIR_OK) rc = in;
@@ -787,10 +789,10 @@ int respond_coalesced(chpir_cluster_server *S, const uint8_t *query, size_t quer
     {
       std::lock_guard<std::mutex> ex(S->exec_mu);
       {
-        std::lock_guard<std::mutex> lk(S->ingest_mu);
+        std::lock_guard<std::mutex> lk(S->mu);
         S->ingest_busy--;
       }
-      S->ingest_cv.notify_all();
+      S->cv_ingest.notify_all();
       w3 = now_s();
       if (rc == CHPIR_OK) rc = run_batch(S, *B, nq, &tc);
     }
