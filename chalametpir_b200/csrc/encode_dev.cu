@@ -14,7 +14,7 @@
 // Two schedules of the same arithmetic:
 //   * column ownership (default): ONE launch.  The dependency is per column -- own[e] needs o1[e], o2[e] of the SAME column e -- so
 //     a thread that owns a column and walks ALL keys in wave order only ever reads what it wrote itself: program order replaces every
-//     inter-thread synchronisation.  N / 8 warps (118 at N = 940), one per SM, each keeping 32 keys x 3 rows of loads in flight
+//     inter-thread synchronisation.  N / 4 single-warp CTAs (235 at N = 940), each keeping 64 keys x 3 rows of loads in flight
 //     inside a wave; the 28 600 waves of a 2^20-entry filter cost one L2 round trip each instead of one kernel launch each.
 //   * one launch per wave, one CTA per key (round 1; CHPIR_FILL=waves): kept as the cross-check.
 #include <cstdlib>
@@ -126,16 +126,21 @@ __global__ void __launch_bounds__(256) fill_prep_kernel(FillArgs a, uint64_t cou
   rec[j] = r;
 }
 
-constexpr int kFillCols = 8;                    // columns owned by a warp (one 32-byte sector of a row of D)
+constexpr int kFillCols = 4;                    // columns owned by a warp
 constexpr int kFillGroups = 32 / kFillCols;     // keys a warp works on per slot: one per group of kFillCols lanes
-constexpr int kFillUnroll = 32 / kFillGroups;   // slots in flight: a whole 32-key chunk at once
+constexpr int kFillUnroll = 8;                  // slots in flight
+constexpr int kFillChunk = kFillGroups * kFillUnroll;  // keys in flight per warp: a whole chunk at once
+constexpr int kFillRpl = kFillChunk / 32;       // records held per lane
+static_assert(kFillChunk % 32 == 0 && 32 % kFillGroups == 0, "a slot's keys come from one record set");
 
-// One warp per CTA owns kFillCols columns; its four lane groups work on four different keys of the same wave at a time (same columns,
-// different rows), so a warp keeps 32 keys x (3 rows + 3 value bytes) of loads in flight -- the kernel is bound by the latency of
-// those scattered reads (DRAM + TLB misses over a 4.4 GB matrix), and N / 8 warps x 32 keys is what hides it (measured at 2^20
-// entries: 1.1-1.7 s with 30 warps x 8 keys and the value bytes combined inside the issue loop, 0.29 s with 59 warps x 16 keys).
-// Records are fetched 32 at a time (one per lane, one chunk ahead) and handed round by shuffles; a chunk never crosses a wave
-// boundary.  Every load is issued before the first result is used (the values of a slot are combined in the second loop only).
+// One warp per CTA owns kFillCols columns; its eight lane groups work on eight different keys of the same wave at a time (same
+// columns, different rows), so a warp keeps 64 keys x (3 rows + 3 value bytes) of loads in flight.  Every warp has to walk ALL keys, so
+// the wall time is (keys / keys in flight per warp) x the latency of those scattered reads (DRAM + TLB misses over a 4.4 GB matrix) --
+// more warps do not shorten it, more keys per warp do.  Measured at 2^20 entries: 1.1-1.7 s with 8 keys in flight (32 columns per
+// warp, value bytes combined inside the issue loop), 0.29 s with 16 keys (16 columns), 0.16-0.25 s with 32 keys (8 columns); narrower
+// ownership costs sector efficiency on the row reads (16 of every 32-byte sector are used), which at ~0.2 TB/s is irrelevant.
+// Records are fetched a chunk ahead (kFillRpl per lane, coalesced) and handed round by shuffles; a chunk never crosses a wave boundary.
+// Every load is issued before the first result is used (the values of a slot are combined in the second loop only).
 template <int ARITY>
 __global__ void __launch_bounds__(32) fill_columns_kernel(const FillRec *__restrict__ rec, const uint32_t *__restrict__ level_start, uint32_t waves,
                                                           const uint8_t *__restrict__ digests, const uint8_t *__restrict__ values, uint32_t *D,
@@ -148,13 +153,16 @@ __global__ void __launch_bounds__(32) fill_columns_kernel(const FillRec *__restr
   const uint32_t *recw = reinterpret_cast<const uint32_t *>(rec);
   const uint64_t base = level_start[0], total = level_start[waves] - base;  // rec[0] is the first key of the first wave
 
-  auto load_rec = [&](uint64_t j0, uint32_t r[10]) {  // lane t: record j0 + t (zeros past the end)
-    const uint64_t j = j0 + lane;
+  auto load_rec = [&](uint64_t j0, uint32_t r[kFillRpl][10]) {  // lane t: records j0 + t, j0 + 32 + t, ... (zeros past the end)
 #pragma unroll
-    for (int w = 0; w < 10; w++) r[w] = j < total ? __ldg(recw + j * 10 + w) : 0u;
+    for (int s = 0; s < kFillRpl; s++) {
+      const uint64_t j = j0 + 32 * s + lane;
+#pragma unroll
+      for (int w = 0; w < 10; w++) r[s][w] = j < total ? __ldg(recw + j * 10 + w) : 0u;
+    }
   };
 
-  uint32_t cur[10], nxt[10];
+  uint32_t cur[kFillRpl][10], nxt[kFillRpl][10];
   uint64_t j = 0;
   load_rec(j, cur);
   uint64_t end_next = level_start[waves > 1 ? 1 : waves] - base;  // wave ends are read one wave ahead (28 600 short waves at 2^20)
@@ -162,47 +170,50 @@ __global__ void __launch_bounds__(32) fill_columns_kernel(const FillRec *__restr
     const uint64_t wave_end = l == 0 ? level_start[1] - base : end_next;
     end_next = level_start[l + 2 <= waves ? l + 2 : waves] - base;
     while (j < wave_end) {
-      const uint32_t chunk = uint32_t(wave_end - j < 32 ? wave_end - j : 32);
+      const uint32_t chunk = uint32_t(wave_end - j < kFillChunk ? wave_end - j : kFillChunk);
       load_rec(j + chunk, nxt);  // the records follow each other whatever the waves are: always one chunk ahead
-      for (uint32_t u0 = 0; u0 < chunk; u0 += kFillGroups * kFillUnroll) {
-        uint32_t own[kFillUnroll], d1[kFillUnroll], d2[kFillUnroll], d3[kFillUnroll], by[kFillUnroll][3], hl[kFillUnroll], hh[kFillUnroll];
+      uint32_t own[kFillUnroll], d1[kFillUnroll], d2[kFillUnroll], d3[kFillUnroll], by[kFillUnroll][3], hl[kFillUnroll], hh[kFillUnroll];
 #pragma unroll
-        for (int u = 0; u < kFillUnroll; u++) {
-          const uint32_t idx = u0 + kFillGroups * u + group;
-          const uint32_t src = idx < chunk ? idx : u0;  // past the end of the chunk: its first key again (result unused)
-          hl[u] = __shfl_sync(0xffffffffu, cur[0], src), hh[u] = __shfl_sync(0xffffffffu, cur[1], src);
-          const uint32_t vl = __shfl_sync(0xffffffffu, cur[2], src), vh = __shfl_sync(0xffffffffu, cur[3], src);
-          own[u] = __shfl_sync(0xffffffffu, cur[4], src);
-          const uint32_t o1 = __shfl_sync(0xffffffffu, cur[5], src), o2 = __shfl_sync(0xffffffffu, cur[6], src);
-          const uint32_t o3 = __shfl_sync(0xffffffffu, cur[7], src);
-          const uint32_t vlen = __shfl_sync(0xffffffffu, cur[8], src), key = __shfl_sync(0xffffffffu, cur[9], src);
-          const uint64_t v0 = (uint64_t(vh) << 32) | vl;
-          d1[u] = __ldcg(D + uint64_t(o1) * N + ec);
-          d2[u] = __ldcg(D + uint64_t(o2) * N + ec);
-          d3[u] = ARITY == 4 ? __ldcg(D + uint64_t(o3) * N + ec) : 0u;
-          // bytes byte0 .. byte0+2 of  digest || value || 0x81 || 0...  : one predicated load each, no branches
+      for (int u = 0; u < kFillUnroll; u++) {
+        constexpr int kSlotsPerSet = 32 / kFillGroups;
+        const int set = u / kSlotsPerSet;                                    // which of the lane's records (compile time)
+        const uint32_t idx = kFillGroups * u + group;                        // key of the chunk this lane group works on
+        const uint32_t src = idx < chunk ? idx - 32 * set : 0;               // past the end of the chunk: lane 0's record of the set --
+        const uint32_t(&r)[10] = cur[set];                                   // a later key or all zeros, either way safe addresses; unused
+        hl[u] = __shfl_sync(0xffffffffu, r[0], src), hh[u] = __shfl_sync(0xffffffffu, r[1], src);
+        const uint32_t vl = __shfl_sync(0xffffffffu, r[2], src), vh = __shfl_sync(0xffffffffu, r[3], src);
+        own[u] = __shfl_sync(0xffffffffu, r[4], src);
+        const uint32_t o1 = __shfl_sync(0xffffffffu, r[5], src), o2 = __shfl_sync(0xffffffffu, r[6], src);
+        const uint32_t o3 = __shfl_sync(0xffffffffu, r[7], src);
+        const uint32_t vlen = __shfl_sync(0xffffffffu, r[8], src), key = __shfl_sync(0xffffffffu, r[9], src);
+        const uint64_t v0 = (uint64_t(vh) << 32) | vl;
+        d1[u] = __ldcg(D + uint64_t(o1) * N + ec);
+        d2[u] = __ldcg(D + uint64_t(o2) * N + ec);
+        d3[u] = ARITY == 4 ? __ldcg(D + uint64_t(o3) * N + ec) : 0u;
+        // bytes byte0 .. byte0+2 of  digest || value || 0x81 || 0...  : one predicated load each, no branches
 #pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const uint32_t t = byte0 + k;
-            const bool in_digest = t < 32, in_value = !in_digest && t - 32 < vlen;
-            const uint8_t *p = in_digest ? digests + 32ull * key + t : values + v0 + (t - 32);
-            uint32_t x = (!in_digest && t - 32 == vlen) ? 0x81u : 0u;
-            if (in_digest || in_value) x = __ldg(p);
-            by[u][k] = x;
-          }
+        for (int k = 0; k < 3; k++) {
+          const uint32_t t = byte0 + k;
+          const bool in_digest = t < 32, in_value = !in_digest && t - 32 < vlen;
+          const uint8_t *p = in_digest ? digests + 32ull * key + t : values + v0 + (t - 32);
+          uint32_t x = (!in_digest && t - 32 == vlen) ? 0x81u : 0u;
+          if (in_digest || in_value) x = __ldg(p);
+          by[u][k] = x;
         }
+      }
 #pragma unroll
-        for (int u = 0; u < kFillUnroll; u++) {
-          const uint32_t v = by[u][0] | by[u][1] << 8 | by[u][2] << 16;
-          const uint64_t hash = (uint64_t(hh[u]) << 32) | hl[u];
-          uint32_t x = (v >> sh) & mask;
-          x -= d1[u] + d2[u] + d3[u] + static_cast<uint32_t>(fmix64_dev(hash + ec));
-          if (act && u0 + kFillGroups * u + group < chunk) D[uint64_t(own[u]) * N + e] = x & mask;
-        }
+      for (int u = 0; u < kFillUnroll; u++) {
+        const uint32_t v = by[u][0] | by[u][1] << 8 | by[u][2] << 16;
+        const uint64_t hash = (uint64_t(hh[u]) << 32) | hl[u];
+        uint32_t x = (v >> sh) & mask;
+        x -= d1[u] + d2[u] + d3[u] + static_cast<uint32_t>(fmix64_dev(hash + ec));
+        if (act && kFillGroups * u + group < chunk) D[uint64_t(own[u]) * N + e] = x & mask;
       }
       j += chunk;
 #pragma unroll
-      for (int w = 0; w < 10; w++) cur[w] = nxt[w];
+      for (int s = 0; s < kFillRpl; s++)
+#pragma unroll
+        for (int w = 0; w < 10; w++) cur[s][w] = nxt[s][w];
     }
   }
 }
@@ -230,7 +241,7 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
   for (uint32_t l = 0; l < waves; l++) count += level_start_host[l + 1] - level_start_host[l];
   const char *mode = std::getenv("CHPIR_FILL");
   if (count > 0 && !(mode && std::strcmp(mode, "waves") == 0)) {
-    // column ownership: records in wave order, then one launch of N / 8 single-warp CTAs
+    // column ownership: records in wave order, then one launch of N / 4 single-warp CTAs
     FillRec *rec = nullptr;
     uint32_t *ls = nullptr;
     if (cudaMalloc(&rec, count * sizeof(FillRec)) != cudaSuccess || cudaMalloc(&ls, (size_t(waves) + 1) * 4) != cudaSuccess) {
