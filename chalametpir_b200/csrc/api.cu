@@ -333,6 +333,10 @@ int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const 
   const uint64_t val_bytes = val_off[n];
   if (int rc = d_values.alloc(val_bytes); rc != CHPIR_OK) return rc;
   if (int rc = d_valoff.alloc((n + 1) * 8); rc != CHPIR_OK) return rc;
+  // scratch of the single-launch row fill (per-key records, wave table: at most one wave per key), allocated up front with the rest
+  DevBuf d_fill_rec, d_fill_levels;
+  if (int rc = d_fill_rec.alloc(n * kFillRecordBytes); rc != CHPIR_OK) return rc;
+  if (int rc = d_fill_levels.alloc((n + 2) * 4); rc != CHPIR_OK) return rc;
   // values do not depend on the filter: their upload (pageable memory, staged by the driver) also precedes the peeling
   CHPIR_CUDA(cudaMemcpyAsync(d_valoff.p, val_off, (n + 1) * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   if (val_bytes) CHPIR_CUDA(cudaMemcpyAsync(d_values.p, val_blob, val_bytes, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
@@ -363,7 +367,7 @@ int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const 
   if (int rc = launch_device_row_fill(arity, d_members.as<uint32_t>(), plan.level_start.data(), waves, d_order.as<uint64_t>(),
                                       d_found.as<uint8_t>(), d_koo.as<uint32_t>(), d_digests.as<uint8_t>(), d_values.as<uint8_t>(),
                                       d_valoff.as<uint64_t>(), d_out->as<uint32_t>(), N, b, pr.params.segment_length,
-                                      pr.params.segment_count_length, st);
+                                      pr.params.segment_count_length, d_fill_rec.p, d_fill_levels.as<uint32_t>(), st);
       rc != CHPIR_OK)
     return rc;
   t_fill.stop(st);

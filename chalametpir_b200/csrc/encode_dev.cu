@@ -220,11 +220,13 @@ __global__ void __launch_bounds__(32) fill_columns_kernel(const FillRec *__restr
 
 }  // namespace
 
-// All pointers are device pointers; D must be zeroed.  One launch per wave, in wave order, on stream s.
+// All pointers except level_start_host are device pointers; D must be zeroed.  scratch_records: 40 bytes per key, scratch_levels:
+// waves + 1 words (both device memory; NULL selects the wave-per-launch schedule).  level_start_host must stay valid until the work
+// enqueued on s has been synchronised (it is copied with cudaMemcpyAsync from pageable memory, i.e. during the call).
 int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32_t *level_start_host, uint32_t waves, const uint64_t *order,
                            const uint8_t *found, const uint32_t *key_of_order, const uint8_t *digests, const uint8_t *values,
                            const uint64_t *val_off, uint32_t *D, uint64_t N, uint32_t b, uint32_t segment_length,
-                           uint32_t segment_count_length, cudaStream_t s) {
+                           uint32_t segment_count_length, void *scratch_records, uint32_t *scratch_levels, cudaStream_t s) {
   FillArgs a{};
   a.order = order;
   a.found = found;
@@ -240,34 +242,23 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
   uint64_t count = 0;
   for (uint32_t l = 0; l < waves; l++) count += level_start_host[l + 1] - level_start_host[l];
   const char *mode = std::getenv("CHPIR_FILL");
-  if (count > 0 && !(mode && std::strcmp(mode, "waves") == 0)) {
-    // column ownership: records in wave order, then one launch of N / 4 single-warp CTAs
-    FillRec *rec = nullptr;
-    uint32_t *ls = nullptr;
-    if (cudaMalloc(&rec, count * sizeof(FillRec)) != cudaSuccess || cudaMalloc(&ls, (size_t(waves) + 1) * 4) != cudaSuccess) {
-      (void)cudaGetLastError();
-      if (rec) cudaFree(rec);
-      return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
-    }
-    int rc = CHPIR_OK;
+  if (count > 0 && scratch_records && scratch_levels && !(mode && std::strcmp(mode, "waves") == 0)) {
+    // column ownership: records in wave order, then one launch of N / 4 single-warp CTAs.  The scratch (40 bytes per key + the wave
+    // table) comes from the caller, allocated before the host-side peeling: a cudaMalloc here would queue behind whatever large
+    // allocation another thread of the setup is making (the 8.4 GB panel ring of the XOF pipeline) with the GPU standing idle.
+    FillRec *rec = static_cast<FillRec *>(scratch_records);
     a.members = members + level_start_host[0];
-    // the wave table is small and lives in pageable memory the caller may drop after this call: a synchronous copy
-    if (cudaMemcpy(ls, level_start_host, (size_t(waves) + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = CHPIR_ERR_CUDA_TRANSFER_FAILED;
-    if (rc == CHPIR_OK) {
-      const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((N + kFillCols - 1) / kFillCols);
-      if (arity == 3) {
-        fill_prep_kernel<3><<<pg, 256, 0, s>>>(a, count, rec);
-        fill_columns_kernel<3><<<fg, 32, 0, s>>>(rec, ls, waves, digests, values, D, N, b);
-      } else {
-        fill_prep_kernel<4><<<pg, 256, 0, s>>>(a, count, rec);
-        fill_columns_kernel<4><<<fg, 32, 0, s>>>(rec, ls, waves, digests, values, D, N, b);
-      }
-      if (cudaGetLastError() != cudaSuccess) rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-      if (rc == CHPIR_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;  // rec and ls go away below
+    if (cudaMemcpyAsync(scratch_levels, level_start_host, (size_t(waves) + 1) * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return CHPIR_ERR_CUDA_TRANSFER_FAILED;
+    const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((N + kFillCols - 1) / kFillCols);
+    if (arity == 3) {
+      fill_prep_kernel<3><<<pg, 256, 0, s>>>(a, count, rec);
+      fill_columns_kernel<3><<<fg, 32, 0, s>>>(rec, scratch_levels, waves, digests, values, D, N, b);
+    } else {
+      fill_prep_kernel<4><<<pg, 256, 0, s>>>(a, count, rec);
+      fill_columns_kernel<4><<<fg, 32, 0, s>>>(rec, scratch_levels, waves, digests, values, D, N, b);
     }
-    cudaFree(rec);
-    cudaFree(ls);
-    return rc;
+    return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   }
   // every field e < N reads bytes [e*b/8, e*b/8 + 2]
   const uint32_t stream_bytes = uint32_t(((N - 1) * b) / 8 + 3 + 3) & ~3u;
