@@ -300,6 +300,198 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+// ----------------------------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// The same product with the roles of the operands swapped and two SMs working on one MMA:  C^T[n][m] = D^T . A^T.
+//   M side of the MMA (256 rows per pair, 128 per CTA) = rows of D's limb planes d0, d1 (columns of the hint / response),
+//   N side                                              = rows of A's limb planes (rows of A / queries), mq <= 128 of them per pass.
+// A cta_group::2 MMA takes half of its N-side operand from each CTA of the pair, so a CTA stages only
+//   d0, d1 of its own 128 columns (2 x 16 KB), ONE of the limbs A0 / A1 for all mq rows (CTA 0: A0, CTA 1: A1), and its half of the rows
+//   of A2 and A3                                                                          = 64 KB per k-block of 128 at mq = 128
+// against 96 KB for the one-SM kernel above (three stages fit instead of two), and every MMA reads less shared memory per MAC
+// (34 KB per 32-deep k-step instead of 44 KB).  Accumulators: shift s = i + j at TMEM columns [s * mq, (s + 1) * mq), lanes = the CTA's
+// 128 columns of D.  Per 32-deep k-step the leader CTA issues
+//   d0 x [A0 | A1] -> (s0, s1)   N = 2 mq        d0 x A2 -> s2   N = mq        d0 x A3 -> s3   N = mq
+//   d1 x [A0 | A1] -> (s1, s2)   N = 2 mq        d1 x A2 -> s3   N = mq                         (d1 x A3 vanishes mod 2^32)
+// in exactly this order: the first three overwrite all four accumulators on the very first k-step, the last two always accumulate.
+// mq is the number of A rows rounded up to 32 (an N = mq MMA of a pair needs N % 32 == 0): a 64-query batch pays for 64 rows, not 128.
+// Both CTAs run a TMA producer (signalling the LEADER's `full` barrier), only the leader issues MMAs, and its commits are multicast
+// to both CTAs' `empty` / `acc_full` barriers.  The epilogue thread owns one column of D and walks the mq rows: for a fixed row the
+// 32 lanes of a warp add into 32 consecutive words of C (one coalesced reduction per instruction).
+constexpr int D_TILE = 128 * BK;  // 16 KB: one limb of D, the CTA's 128 columns
+template <int NB>
+__host__ __device__ constexpr int pair_stage_bytes() {
+  return NB * D_TILE + 2 * BM * BK;  // d limbs + (A0|A1: 128 rows) + (A2, A3: 64 rows each)
+}
+template <int NB>
+__host__ __device__ constexpr int pair_stages() {
+  return NB == 2 ? 3 : 4;
+}
+constexpr int kPairMaxStages = 4;
+
+struct __align__(8) PairBarriers {
+  uint64_t full[kPairMaxStages];
+  uint64_t empty[kPairMaxStages];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+// box -> this CTA's shared memory, bytes completed on a barrier that may live in the peer CTA (the leader's `full`)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
+// grid: (2 * pairs, splits), cluster (2, 1, 1): CTA x owns columns [128 x, 128 x + 128) of D; one K range per blockIdx.y.
+// map_ah: A's limb planes [4][128][kp], box = mq / 2 rows; map_d: D's limb planes [NB][n][kp], box = 128 rows.
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_d, uint32_t *__restrict__ C, uint32_t m,
+                        uint32_t n, uint32_t mq, uint32_t kblocks_total, uint32_t kblocks_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PairBarriers bars;
+  constexpr int ST = pair_stages<NB>();
+  constexpr int STAGE_BYTES = pair_stage_bytes<NB>();
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs, owns the `full` barriers)
+  const uint32_t n0 = blockIdx.x * 128u;
+  const uint32_t kb0 = blockIdx.y * kblocks_per_split;
+  uint32_t kb1 = kb0 + kblocks_per_split;
+  if (kb1 > kblocks_total) kb1 = kblocks_total;
+  const uint32_t nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+  const uint32_t half = mq / 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ah)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_d)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < ST; s++) {
+      mbar_init(&bars.full[s], 1);   // the leader's producer arrives once with the bytes of BOTH CTAs' loads
+      mbar_init(&bars.empty[s], 1);  // one multicast commit of the leader's MMA thread
+    }
+    mbar_init(&bars.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before a load or a commit can reach them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = bars.tmem_base;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      if (lane == 0) {
+        const uint32_t tx_bytes = 2u * (NB * D_TILE + mq * 2u * BK);  // both CTAs of the pair
+        for (uint32_t i = 0; i < nkb; i++) {
+          const int s = i % ST;
+          const uint32_t ph = (i / ST) & 1;
+          mbar_wait(&bars.empty[s], ph ^ 1);
+          if (crank == 0) mbar_expect_tx(&bars.full[s], tx_bytes);
+          const uint32_t full = mapa_u32(smem_u32(&bars.full[s]), 0);
+          const uint32_t st = smem + s * STAGE_BYTES;
+          const int kc = int((kb0 + i) * BK);
+#pragma unroll
+          for (int l = 0; l < NB; l++) tma_load_3d_pair(st + l * D_TILE, &map_d, full, kc, int(n0), l);
+          const uint32_t ax = st + NB * D_TILE;
+          tma_load_3d_pair(ax, &map_ah, full, kc, 0, int(crank));                       // A0 (leader) / A1 (peer), rows [0, mq/2)
+          tma_load_3d_pair(ax + half * BK, &map_ah, full, kc, int(half), int(crank));   //                        rows [mq/2, mq)
+          tma_load_3d_pair(ax + mq * BK, &map_ah, full, kc, int(crank * half), 2);      // this CTA's half of A2
+          tma_load_3d_pair(ax + mq * BK + half * BK, &map_ah, full, kc, int(crank * half), 3);  // and of A3
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer (one thread of the leader CTA)
+      if (lane == 0 && crank == 0) {
+        // kind::i8, u8 x u8 -> s32 (wrapping), K-major operands, M = 256 over the pair
+        const uint32_t idesc_wide = (2u << 4) | (((2u * mq) >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+        const uint32_t idesc_half = (2u << 4) | ((mq >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+        for (uint32_t i = 0; i < nkb; i++) {
+          const int s = i % ST;
+          const uint32_t ph = (i / ST) & 1;
+          mbar_wait(&bars.full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_base = smem + s * STAGE_BYTES;
+          const uint32_t ax = d_base + NB * D_TILE, a2 = ax + mq * BK, a3 = a2 + half * BK;
+#pragma unroll
+          for (int kk = 0; kk < BK / 32; kk++) {
+            const uint32_t acc = (i == 0 && kk == 0) ? 0u : 1u;
+            const uint64_t dd0 = umma_desc_sw128(d_base + kk * 32), dax = umma_desc_sw128(ax + kk * 32);
+            const uint64_t da2 = umma_desc_sw128(a2 + kk * 32), da3 = umma_desc_sw128(a3 + kk * 32);
+            umma_i8_pair(tmem + 0 * mq, dd0, dax, idesc_wide, acc);
+            umma_i8_pair(tmem + 2 * mq, dd0, da2, idesc_half, acc);
+            umma_i8_pair(tmem + 3 * mq, dd0, da3, idesc_half, acc);
+            if (NB == 2) {
+              const uint64_t dd1 = umma_desc_sw128(d_base + D_TILE + kk * 32);
+              umma_i8_pair(tmem + 1 * mq, dd1, dax, idesc_wide, 1u);
+              umma_i8_pair(tmem + 3 * mq, dd1, da2, idesc_half, 1u);
+            }
+          }
+          umma_commit_pair(&bars.empty[s], 0b11);  // both CTAs' producers may refill the stage once these MMAs have read it
+        }
+        umma_commit_pair(&bars.acc_full, 0b11);
+      }
+    } else {
+      // ---------------------------------------------------------------- epilogue (both CTAs): TMEM -> registers -> atomics on C
+      mbar_wait(&bars.acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_group = warp % 4;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+      const uint32_t col = n0 + lane_group * 32 + lane;
+      const uint32_t taddr = tmem + ((lane_group * 32) << 16);
+      for (uint32_t r0 = 0; r0 < mq; r0 += 16) {
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tmem_ld16(taddr + 0 * mq + r0, v0);
+        tmem_ld16(taddr + 1 * mq + r0, v1);
+        tmem_ld16(taddr + 2 * mq + r0, v2);
+        tmem_ld16(taddr + 3 * mq + r0, v3);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (col < n) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const uint32_t v = v0[j] + (v1[j] << 8) + (v2[j] << 16) + (v3[j] << 24);
+            if (r0 + j < m) atomicAdd(C + uint64_t(r0 + j) * n + col, v);
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs wrote this CTA's TMEM and its commits target this CTA's barriers: leave together
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
 // A[m][k] u32 -> planes[l][plane_rows][kp] u8 (rows 0..m-1 filled), l = byte index.  One thread per 4 consecutive k.
 __global__ void split_a_limbs(const uint32_t *__restrict__ A, uint32_t m, uint64_t k, uint64_t kp, uint32_t plane_rows,
                               uint8_t *__restrict__ planes) {
@@ -396,6 +588,10 @@ struct GemmTcB {
   uint32_t n = 0, nb = 0, bn = 0, tiles_n = 0, kblocks = 0, kbps = 0, splits = 0;
   uint32_t csz = 1;  // thread-block cluster along the N tiles (A multicast), 1 = none
   CUtensorMap map_b{}, map_a[2]{}, map_a64[2]{};
+  // CTA-pair kernel (cta_group::2, the default): 2 * pairs CTAs of 128 columns, its own K split; A maps with boxes of 16 / 32 / 48 / 64 rows
+  bool pair = true;
+  uint32_t p_ctas = 0, p_kbps = 0, p_splits = 0;
+  CUtensorMap map_d{}, map_ah[2][4]{};
   // Last reader of each ring buffer (the panel GEMM that consumed it), on whatever stream it ran: callers on different streams
   // -- concurrent respond_batch / coalesced respond / respond_device_tc on one server -- order themselves against it before
   // refilling the buffer (gemm_tc_buf_acquire / gemm_tc_buf_release), so the ring can be shared without serialising execution.
@@ -497,21 +693,55 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
       }
       wave = uint32_t(clusters) * csz;
     }
-    // one launch = one 128-row panel: split K so that tiles_n * splits fills whole waves
-    uint32_t best_splits = 1;
-    double best_eff = 0.0;
-    uint32_t max_splits = g->kblocks / (1024 / BK);  // every split keeps >= 1024 k of mainloop per epilogue
-    if (max_splits < 1) max_splits = 1;
-    if (max_splits > 148) max_splits = 148;
-    for (uint32_t sp = 1; sp <= max_splits; sp++) {
-      const uint64_t units = uint64_t(g->tiles_n) * sp;
-      const uint64_t waves = (units + wave - 1) / wave;
-      const double eff = double(units) / double(waves * wave);
-      if (eff > best_eff + 0.02) best_eff = eff, best_splits = sp;
-    }
-    g->kbps = (g->kblocks + best_splits - 1) / best_splits;
-    g->splits = (g->kblocks + g->kbps - 1) / g->kbps;
+    // one launch = one 128-row panel: split K so that tiles * splits fills whole waves
+    auto split_k = [&](uint32_t tiles, uint32_t wave_ctas, uint32_t *kbps, uint32_t *splits) {
+      uint32_t best_splits = 1;
+      double best_eff = 0.0;
+      uint32_t max_splits = g->kblocks / (1024 / BK);  // every split keeps >= 1024 k of mainloop per epilogue
+      if (max_splits < 1) max_splits = 1;
+      if (max_splits > 148) max_splits = 148;
+      for (uint32_t sp = 1; sp <= max_splits; sp++) {
+        const uint64_t units = uint64_t(tiles) * sp;
+        const uint64_t waves = (units + wave_ctas - 1) / wave_ctas;
+        const double eff = double(units) / double(waves * wave_ctas);
+        if (eff > best_eff + 0.02) best_eff = eff, best_splits = sp;
+      }
+      *kbps = (g->kblocks + best_splits - 1) / best_splits;
+      *splits = (g->kblocks + *kbps - 1) / *kbps;
+    };
+    split_k(g->tiles_n, wave, &g->kbps, &g->splits);
     if ((rc = make_map(&g->map_b, g->b8, k, g->kp, n, g->nb, bn)) != CHPIR_OK) break;
+    // CTA pairs (cta_group::2): the default; CHPIR_GEMM_KERNEL=1sm keeps the one-SM kernel (the measured comparison)
+    if (const char *v = std::getenv("CHPIR_GEMM_KERNEL"); v && v[0] == '1') g->pair = false;
+    {
+      constexpr int psmem1 = pair_stages<1>() * pair_stage_bytes<1>() + 1024, psmem2 = pair_stages<2>() * pair_stage_bytes<2>() + 1024;
+      if (cudaFuncSetAttribute(gemm_tc_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem1) != cudaSuccess ||
+          cudaFuncSetAttribute(gemm_tc_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem2) != cudaSuccess) {
+        rc = CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+        break;
+      }
+      g->p_ctas = 2 * ((n + 255) / 256);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(g->p_ctas, 1, 1), cfg.blockDim = dim3(kThreads, 1, 1);
+      cfg.dynamicSmemBytes = g->nb == 1 ? psmem1 : psmem2;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+      cfg.attrs = &at, cfg.numAttrs = 1;
+      int clusters = 0;
+      const cudaError_t e = g->nb == 1 ? cudaOccupancyMaxActiveClusters(&clusters, gemm_tc_pair_kernel<1>, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&clusters, gemm_tc_pair_kernel<2>, &cfg);
+      if (e != cudaSuccess || clusters < 1) {
+        (void)cudaGetLastError();
+        clusters = sm_count / 2;
+      }
+      split_k(g->p_ctas, uint32_t(clusters) * 2u, &g->p_kbps, &g->p_splits);
+      if ((rc = make_map(&g->map_d, g->b8, k, g->kp, n, g->nb, 128)) != CHPIR_OK) break;
+      for (int i = 0; i < 2 && rc == CHPIR_OK; i++)
+        for (int h = 0; h < 4 && rc == CHPIR_OK; h++)
+          rc = make_map(&g->map_ah[i][h], g->a_ring + i * gemm_tc_panel_bytes(g), k, g->kp, BM, 4, 16u * uint32_t(h + 1));
+      if (rc != CHPIR_OK) break;
+    }
     for (int i = 0; i < 2; i++) {
       if ((rc = make_map(&g->map_a[i], g->a_ring + i * gemm_tc_panel_bytes(g), k, g->kp, BM, 4, BM)) != CHPIR_OK) break;
       if ((rc = make_map(&g->map_a64[i], g->a_ring + i * gemm_tc_panel_bytes(g), k, g->kp, BM, 4, 64)) != CHPIR_OK) break;
@@ -529,6 +759,27 @@ int gemm_tc_prepare(const uint32_t *B, uint32_t ldb, uint64_t k, uint32_t n, uin
 
 // C_panel[rows x n] += A_panel . B  for the panel held in ring buffer `buf` (rows <= 128).  C must have been zeroed.
 int gemm_tc_panel(const GemmTcB *g, int buf, uint32_t rows, uint32_t *C_panel, cudaStream_t s) {
+  if (g->pair) {
+    if (rows == 0) return CHPIR_OK;
+    if (rows > uint32_t(BM)) return CHPIR_ERR_INVALID_ARGUMENT;
+    const uint32_t mq = (rows + 31) / 32 * 32;  // rows of A per pass: an N = mq MMA of a CTA pair needs mq % 32 == 0
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g->p_ctas, g->p_splits, 1), cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = g->nb == 1 ? pair_stages<1>() * pair_stage_bytes<1>() + 1024 : pair_stages<2>() * pair_stage_bytes<2>() + 1024;
+    cfg.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+    cfg.attrs = &at, cfg.numAttrs = 1;
+    const CUtensorMap &ah = g->map_ah[buf][mq / 32 - 1];
+    const cudaError_t e = g->nb == 1 ? cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<1>, ah, g->map_d, C_panel, rows, g->n, mq, g->kblocks, g->p_kbps)
+                                     : cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<2>, ah, g->map_d, C_panel, rows, g->n, mq, g->kblocks, g->p_kbps);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+    }
+    return CHPIR_OK;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g->tiles_n, g->splits, 1), cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = STAGES * (4 * A_TILE + int(g->nb) * B_TILE) + 1024;
