@@ -85,7 +85,7 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
                            const uint8_t *found, const uint32_t *key_of_order, const uint8_t *digests, const uint8_t *values,
                            const uint64_t *val_off, uint32_t *D, uint64_t N, uint32_t b, uint32_t segment_length,
                            uint32_t segment_count_length, void *scratch_records, uint32_t *scratch_levels, cudaStream_t s);
-constexpr size_t kFillRecordBytes = 40;  // scratch_records: this many bytes per key
+constexpr size_t kFillRecordBytes = 48;  // scratch_records: this many bytes per key
 
 // C[m x n] = A[m x k] * B[k x n] mod 2^32, all u32 row-major in device memory (B with leading dimension ldb).
 int launch_gemm_simt(const uint32_t *A, const uint32_t *B, uint32_t ldb, uint32_t *C, uint32_t m, uint64_t k, uint32_t n, cudaStream_t s);

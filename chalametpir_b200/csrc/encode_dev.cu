@@ -12,10 +12,12 @@
 // is unchanged and the bytes can be compared with the host encoder one to one.
 //
 // Two schedules of the same arithmetic:
-//   * column ownership (default): ONE launch.  The dependency is per column -- own[e] needs o1[e], o2[e] of the SAME column e -- so
-//     a thread that owns a column and walks ALL keys in wave order only ever reads what it wrote itself: program order replaces every
-//     inter-thread synchronisation.  N / 4 single-warp CTAs (235 at N = 940), each keeping 64 keys x 3 rows of loads in flight
-//     inside a wave; the 28 600 waves of a 2^20-entry filter cost one L2 round trip each instead of one kernel launch each.
+//   * column ownership (default): the part of a row that depends on the key alone (field_e - mix) is written for every key at once
+//     (encode_rows_kernel), then ONE launch solves the dependent part.  The dependency is per column -- own[e] needs o1[e], o2[e] of
+//     the SAME column e -- so a thread that owns a column and walks ALL keys in wave order only ever reads what it wrote itself:
+//     program order replaces every inter-thread synchronisation.  N / 4 single-warp CTAs (235 at N = 940), each keeping 128 keys x
+//     3 rows of loads in flight inside a wave; the 28 600 waves of a 2^20-entry filter cost one L2 round trip each instead of one
+//     kernel launch each.
 //   * one launch per wave, one CTA per key (round 1; CHPIR_FILL=waves): kept as the cross-check.
 #include <cstdlib>
 
@@ -104,15 +106,21 @@ __global__ void __launch_bounds__(kFillThreads) fill_wave_kernel(FillArgs a, uin
 }
 
 // ---- column ownership ----------------------------------------------------------------------------------------------------------------
-struct FillRec {  // one key, in wave order: everything the fill needs that does not depend on the column
+// The recurrence is linear:  own = ( t - D[o1] - D[o2] (- D[o3]) ) mod 2^b  with  t = field_e(digest || value || 0x81) - mix(hash, e),
+// and t depends on nothing but the key.  So the fill runs as two kernels:
+//   encode_rows_kernel    every key at once, no dependencies: its byte string goes through shared memory, D[own] = t & mask.  This is
+//                         encode_kv_as_row + the hash mix, HBM bound (reads the values once, writes every owned row once: ~2 ms at 2^20).
+//   solve_columns_kernel  the dependent part, D[own] -= D[o1] + D[o2] (+ D[o3]) in wave order: per key four row numbers (16 bytes),
+//                         three or four loads, two or three subtractions, one store -- nothing else is left on the dependency chain.
+struct FillRec {  // one key, in wave order: what the row encoding needs
   uint64_t hash, v0;
-  uint32_t own, o1, o2, o3;  // rows of D: the slot the key owns and its other slots
-  uint32_t vlen, key;
+  uint32_t vlen, key, own, pad;
 };
-static_assert(sizeof(FillRec) == 40, "ten words per record");
+static_assert(sizeof(FillRec) == 32, "eight words per record");
+static_assert(sizeof(FillRec) + sizeof(uint4) == kFillRecordBytes, "scratch per key: one record + one set of row numbers");
 
 template <int ARITY>
-__global__ void __launch_bounds__(256) fill_prep_kernel(FillArgs a, uint64_t count, FillRec *__restrict__ rec) {
+__global__ void __launch_bounds__(256) fill_prep_kernel(FillArgs a, uint64_t count, FillRec *__restrict__ rec, uint4 *__restrict__ rows) {
   const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (j >= count) return;
   const uint32_t i = a.members[j];
@@ -121,106 +129,131 @@ __global__ void __launch_bounds__(256) fill_prep_kernel(FillArgs a, uint64_t cou
   uint32_t h[4];
   slots_dev<ARITY>(hash, a.segment_length, a.segment_count_length, h);
   FillRec r;
-  r.hash = hash, r.v0 = a.val_off[key], r.vlen = uint32_t(a.val_off[key + 1] - r.v0), r.key = key;
-  r.own = h[which], r.o1 = h[(which + 1) % ARITY], r.o2 = h[(which + 2) % ARITY], r.o3 = h[(which + 3) % ARITY];
+  r.hash = hash, r.v0 = a.val_off[key], r.vlen = uint32_t(a.val_off[key + 1] - r.v0), r.key = key, r.own = h[which], r.pad = 0;
   rec[j] = r;
+  // the row the key owns and the rows it reads; for 3-wise filters the fourth entry repeats the own row (never read)
+  rows[j] = make_uint4(h[which], h[(which + 1) % ARITY], h[(which + 2) % ARITY], ARITY == 4 ? h[(which + 3) % ARITY] : h[which]);
 }
 
-constexpr int kFillCols = 4;                    // columns owned by a warp
-constexpr int kFillGroups = 32 / kFillCols;     // keys a warp works on per slot: one per group of kFillCols lanes
-constexpr int kFillUnroll = 8;                  // slots in flight
-constexpr int kFillChunk = kFillGroups * kFillUnroll;  // keys in flight per warp: a whole chunk at once
-constexpr int kFillRpl = kFillChunk / 32;       // records held per lane
-static_assert(kFillChunk % 32 == 0 && 32 % kFillGroups == 0, "a slot's keys come from one record set");
+// dynamic shared memory: a key's byte string (as in fill_wave_kernel); CTAs stride over the keys
+__global__ void __launch_bounds__(kFillThreads) encode_rows_kernel(const FillRec *__restrict__ rec, uint64_t count, const uint8_t *__restrict__ digests,
+                                                                   const uint8_t *__restrict__ values, uint32_t *__restrict__ D, uint64_t N, uint32_t b,
+                                                                   uint32_t stream_bytes) {
+  extern __shared__ __align__(4) uint8_t sbytes[];
+  const uint32_t mask = (1u << b) - 1;
+  for (uint64_t j = blockIdx.x; j < count; j += gridDim.x) {
+    const FillRec r = rec[j];
+    for (uint32_t t = threadIdx.x; t < stream_bytes; t += kFillThreads) {
+      uint8_t v = 0;
+      if (t < 32)
+        v = __ldg(digests + 32ull * r.key + t);
+      else if (t - 32 < r.vlen)
+        v = __ldg(values + r.v0 + (t - 32));
+      else if (t - 32 == r.vlen)
+        v = 0x81;
+      sbytes[t] = v;
+    }
+    __syncthreads();
+    uint32_t *own = D + uint64_t(r.own) * N;
+    for (uint64_t e = threadIdx.x; e < N; e += kFillThreads) {
+      const uint32_t bit = uint32_t(e) * b, byte = bit >> 3, sh = bit & 7;
+      const uint32_t w = uint32_t(sbytes[byte]) | uint32_t(sbytes[byte + 1]) << 8 | uint32_t(sbytes[byte + 2]) << 16;
+      own[e] = ((w >> sh) - static_cast<uint32_t>(fmix64_dev(r.hash + e))) & mask;
+    }
+    __syncthreads();
+  }
+}
 
-// One warp per CTA owns kFillCols columns; its eight lane groups work on eight different keys of the same wave at a time (same
-// columns, different rows), so a warp keeps 64 keys x (3 rows + 3 value bytes) of loads in flight.  Every warp has to walk ALL keys, so
-// the wall time is (keys / keys in flight per warp) x the latency of those scattered reads (DRAM + TLB misses over a 4.4 GB matrix) --
-// more warps do not shorten it, more keys per warp do.  Measured at 2^20 entries: 1.1-1.7 s with 8 keys in flight (32 columns per
-// warp, value bytes combined inside the issue loop), 0.29 s with 16 keys (16 columns), 0.16-0.25 s with 32 keys (8 columns); narrower
-// ownership costs sector efficiency on the row reads (16 of every 32-byte sector are used), which at ~0.2 TB/s is irrelevant.
-// Records are fetched a chunk ahead (kFillRpl per lane, coalesced) and handed round by shuffles; a chunk never crosses a wave boundary.
-// Every load is issued before the first result is used (the values of a slot are combined in the second loop only).
+constexpr int kFillCols = 4;                            // columns owned by a warp
+constexpr int kFillGroups = 32 / kFillCols;             // keys a warp works on per slot: one per group of kFillCols lanes
+constexpr int kFillUnroll = 16;                         // slots in flight
+constexpr int kFillChunk = kFillGroups * kFillUnroll;   // keys in flight per warp (128)
+constexpr int kFillRing = 4 * kFillChunk;               // row-number records staged in shared memory (8 KB)
+static_assert(kFillChunk % 32 == 0, "the ring is refilled in whole warp loads");
+
+// One warp per CTA owns kFillCols columns and walks ALL keys in wave order, so every value it reads was written by itself: program
+// order replaces all synchronisation.  Its eight lane groups work on eight keys of the same wave per slot, sixteen slots (128 keys x
+// 3-4 loads) are in flight inside a wave; a chunk never crosses a wave boundary, and a short wave only issues the slots it has.
+// The wall time is (dependent steps) x (one round trip to L2 / HBM): 28 600 waves at 2^20 entries plus keys / 128 chunk steps --
+// more warps do not shorten it, less work per step does.  Row numbers reach the lanes through a shared-memory ring that the warp
+// refills 128 records at a time, two refills ahead of the walk (the loads are in flight for a whole step before they are stored).
 template <int ARITY>
-__global__ void __launch_bounds__(32) fill_columns_kernel(const FillRec *__restrict__ rec, const uint32_t *__restrict__ level_start, uint32_t waves,
-                                                          const uint8_t *__restrict__ digests, const uint8_t *__restrict__ values, uint32_t *D,
-                                                          uint64_t N, uint32_t b) {
+__global__ void __launch_bounds__(32) solve_columns_kernel(const uint4 *__restrict__ rows, const uint32_t *__restrict__ level_start, uint32_t waves,
+                                                           uint32_t *D, uint64_t N, uint32_t b) {
+  __shared__ uint4 ring[kFillRing];
   const uint32_t lane = threadIdx.x, group = lane / kFillCols;
   const uint64_t e = uint64_t(blockIdx.x) * kFillCols + (lane % kFillCols);
   const bool act = e < N;
   const uint64_t ec = act ? e : N - 1;  // inactive lanes of the last warp shadow a real column (loads only)
-  const uint32_t bit = uint32_t(ec) * b, byte0 = bit >> 3, sh = bit & 7, mask = (1u << b) - 1;
-  const uint32_t *recw = reinterpret_cast<const uint32_t *>(rec);
-  const uint64_t base = level_start[0], total = level_start[waves] - base;  // rec[0] is the first key of the first wave
+  const uint32_t mask = (1u << b) - 1;
+  const uint64_t base = level_start[0], total = level_start[waves] - base;  // rows[0] is the first key of the first wave
+  constexpr int kPer = kFillChunk / 32;
 
-  auto load_rec = [&](uint64_t j0, uint32_t r[kFillRpl][10]) {  // lane t: records j0 + t, j0 + 32 + t, ... (zeros past the end)
+  auto fetch = [&](uint64_t j0, uint4 r[kPer]) {  // lane t: records j0 + t, j0 + 32 + t, ... (row 0 past the end: a safe address)
 #pragma unroll
-    for (int s = 0; s < kFillRpl; s++) {
+    for (int s = 0; s < kPer; s++) {
       const uint64_t j = j0 + 32 * s + lane;
-#pragma unroll
-      for (int w = 0; w < 10; w++) r[s][w] = j < total ? __ldg(recw + j * 10 + w) : 0u;
+      r[s] = j < total ? __ldg(rows + j) : make_uint4(0, 0, 0, 0);
     }
   };
+  auto stash = [&](uint64_t j0, const uint4 r[kPer]) {
+#pragma unroll
+    for (int s = 0; s < kPer; s++) ring[(j0 + 32 * s + lane) % kFillRing] = r[s];
+  };
 
-  uint32_t cur[kFillRpl][10], nxt[kFillRpl][10];
+  uint4 nx[kPer];
+  for (int i = lane; i < kFillRing; i += 32) ring[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  uint64_t filled = 0;
+  for (int i = 0; i < 2; i++) {
+    fetch(filled, nx);
+    stash(filled, nx);
+    filled += kFillChunk;
+  }
+  __syncwarp();
+
   uint64_t j = 0;
-  load_rec(j, cur);
   uint64_t end_next = level_start[waves > 1 ? 1 : waves] - base;  // wave ends are read one wave ahead (28 600 short waves at 2^20)
   for (uint32_t l = 0; l < waves; l++) {
     const uint64_t wave_end = l == 0 ? level_start[1] - base : end_next;
     end_next = level_start[l + 2 <= waves ? l + 2 : waves] - base;
     while (j < wave_end) {
       const uint32_t chunk = uint32_t(wave_end - j < kFillChunk ? wave_end - j : kFillChunk);
-      load_rec(j + chunk, nxt);  // the records follow each other whatever the waves are: always one chunk ahead
-      uint32_t own[kFillUnroll], d1[kFillUnroll], d2[kFillUnroll], d3[kFillUnroll], by[kFillUnroll][3], hl[kFillUnroll], hh[kFillUnroll];
+      const bool refill = filled < total && filled - j < 2 * kFillChunk;  // warp uniform
+      if (refill) fetch(filled, nx);
+      uint32_t v0[kFillUnroll], v1[kFillUnroll], v2[kFillUnroll], v3[kFillUnroll];
 #pragma unroll
       for (int u = 0; u < kFillUnroll; u++) {
-        constexpr int kSlotsPerSet = 32 / kFillGroups;
-        const int set = u / kSlotsPerSet;                                    // which of the lane's records (compile time)
-        const uint32_t idx = kFillGroups * u + group;                        // key of the chunk this lane group works on
-        const uint32_t src = idx < chunk ? idx - 32 * set : 0;               // past the end of the chunk: lane 0's record of the set --
-        const uint32_t(&r)[10] = cur[set];                                   // a later key or all zeros, either way safe addresses; unused
-        hl[u] = __shfl_sync(0xffffffffu, r[0], src), hh[u] = __shfl_sync(0xffffffffu, r[1], src);
-        const uint32_t vl = __shfl_sync(0xffffffffu, r[2], src), vh = __shfl_sync(0xffffffffu, r[3], src);
-        own[u] = __shfl_sync(0xffffffffu, r[4], src);
-        const uint32_t o1 = __shfl_sync(0xffffffffu, r[5], src), o2 = __shfl_sync(0xffffffffu, r[6], src);
-        const uint32_t o3 = __shfl_sync(0xffffffffu, r[7], src);
-        const uint32_t vlen = __shfl_sync(0xffffffffu, r[8], src), key = __shfl_sync(0xffffffffu, r[9], src);
-        const uint64_t v0 = (uint64_t(vh) << 32) | vl;
-        d1[u] = __ldcg(D + uint64_t(o1) * N + ec);
-        d2[u] = __ldcg(D + uint64_t(o2) * N + ec);
-        d3[u] = ARITY == 4 ? __ldcg(D + uint64_t(o3) * N + ec) : 0u;
-        // bytes byte0 .. byte0+2 of  digest || value || 0x81 || 0...  : one predicated load each, no branches
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const uint32_t t = byte0 + k;
-          const bool in_digest = t < 32, in_value = !in_digest && t - 32 < vlen;
-          const uint8_t *p = in_digest ? digests + 32ull * key + t : values + v0 + (t - 32);
-          uint32_t x = (!in_digest && t - 32 == vlen) ? 0x81u : 0u;
-          if (in_digest || in_value) x = __ldg(p);
-          by[u][k] = x;
+        if (kFillGroups * u < chunk) {  // warp uniform: a short wave issues only the slots it has
+          // groups past the end of the chunk read a later key's (or an all-zero) record: valid rows, loads only
+          const uint4 r = ring[(j + kFillGroups * u + group) % kFillRing];
+          v0[u] = __ldcg(D + uint64_t(r.x) * N + ec);
+          v1[u] = __ldcg(D + uint64_t(r.y) * N + ec);
+          v2[u] = __ldcg(D + uint64_t(r.z) * N + ec);
+          v3[u] = ARITY == 4 ? __ldcg(D + uint64_t(r.w) * N + ec) : 0u;
         }
       }
 #pragma unroll
       for (int u = 0; u < kFillUnroll; u++) {
-        const uint32_t v = by[u][0] | by[u][1] << 8 | by[u][2] << 16;
-        const uint64_t hash = (uint64_t(hh[u]) << 32) | hl[u];
-        uint32_t x = (v >> sh) & mask;
-        x -= d1[u] + d2[u] + d3[u] + static_cast<uint32_t>(fmix64_dev(hash + ec));
-        if (act && kFillGroups * u + group < chunk) D[uint64_t(own[u]) * N + e] = x & mask;
+        if (kFillGroups * u < chunk) {
+          const uint32_t own = ring[(j + kFillGroups * u + group) % kFillRing].x;
+          if (act && kFillGroups * u + group < chunk) D[uint64_t(own) * N + e] = (v0[u] - v1[u] - v2[u] - v3[u]) & mask;
+        }
       }
       j += chunk;
-#pragma unroll
-      for (int s = 0; s < kFillRpl; s++)
-#pragma unroll
-        for (int w = 0; w < 10; w++) cur[s][w] = nxt[s][w];
+      if (refill) {
+        __syncwarp();  // every lane has read the records this refill overwrites (all of them lie before j)
+        stash(filled, nx);
+        filled += kFillChunk;
+        __syncwarp();
+      }
     }
   }
 }
 
 }  // namespace
 
-// All pointers except level_start_host are device pointers; D must be zeroed.  scratch_records: 40 bytes per key, scratch_levels:
+// All pointers except level_start_host are device pointers; D must be zeroed.  scratch_records: kFillRecordBytes per key, scratch_levels:
 // waves + 1 words (both device memory; NULL selects the wave-per-launch schedule).  level_start_host must stay valid until the work
 // enqueued on s has been synchronised (it is copied with cudaMemcpyAsync from pageable memory, i.e. during the call).
 int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32_t *level_start_host, uint32_t waves, const uint64_t *order,
@@ -241,28 +274,36 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
   a.segment_count_length = segment_count_length;
   uint64_t count = 0;
   for (uint32_t l = 0; l < waves; l++) count += level_start_host[l + 1] - level_start_host[l];
-  const char *mode = std::getenv("CHPIR_FILL");
-  if (count > 0 && scratch_records && scratch_levels && !(mode && std::strcmp(mode, "waves") == 0)) {
-    // column ownership: records in wave order, then one launch of N / 4 single-warp CTAs.  The scratch (40 bytes per key + the wave
-    // table) comes from the caller, allocated before the host-side peeling: a cudaMalloc here would queue behind whatever large
-    // allocation another thread of the setup is making (the 8.4 GB panel ring of the XOF pipeline) with the GPU standing idle.
-    FillRec *rec = static_cast<FillRec *>(scratch_records);
-    a.members = members + level_start_host[0];
-    if (cudaMemcpyAsync(scratch_levels, level_start_host, (size_t(waves) + 1) * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
-      return CHPIR_ERR_CUDA_TRANSFER_FAILED;
-    const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((N + kFillCols - 1) / kFillCols);
-    if (arity == 3) {
-      fill_prep_kernel<3><<<pg, 256, 0, s>>>(a, count, rec);
-      fill_columns_kernel<3><<<fg, 32, 0, s>>>(rec, scratch_levels, waves, digests, values, D, N, b);
-    } else {
-      fill_prep_kernel<4><<<pg, 256, 0, s>>>(a, count, rec);
-      fill_columns_kernel<4><<<fg, 32, 0, s>>>(rec, scratch_levels, waves, digests, values, D, N, b);
-    }
-    return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-  }
   // every field e < N reads bytes [e*b/8, e*b/8 + 2]
   const uint32_t stream_bytes = uint32_t(((N - 1) * b) / 8 + 3 + 3) & ~3u;
   if (stream_bytes > 200 * 1024) return CHPIR_ERR_INVALID_ARGUMENT;
+  const char *mode = std::getenv("CHPIR_FILL");
+  if (count > 0 && scratch_records && scratch_levels && !(mode && std::strcmp(mode, "waves") == 0)) {
+    // column ownership: records in wave order, the independent row encoding, then one launch of N / 4 single-warp CTAs for the
+    // dependent part.  The scratch (48 bytes per key + the wave table) comes from the caller, allocated before the host-side peeling:
+    // a cudaMalloc here would queue behind whatever large allocation another thread of the setup is making (the 8.4 GB panel ring of
+    // the XOF pipeline) with the GPU standing idle.
+    FillRec *rec = static_cast<FillRec *>(scratch_records);
+    uint4 *rows = reinterpret_cast<uint4 *>(rec + count);
+    a.members = members + level_start_host[0];
+    if (cudaMemcpyAsync(scratch_levels, level_start_host, (size_t(waves) + 1) * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return CHPIR_ERR_CUDA_TRANSFER_FAILED;
+    if (stream_bytes > 48 * 1024 &&
+        cudaFuncSetAttribute(encode_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream_bytes)) != cudaSuccess)
+      return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+    const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((N + kFillCols - 1) / kFillCols);
+    const unsigned eg = unsigned(count < 148ull * 32 ? count : 148ull * 32);
+    if (arity == 3)
+      fill_prep_kernel<3><<<pg, 256, 0, s>>>(a, count, rec, rows);
+    else
+      fill_prep_kernel<4><<<pg, 256, 0, s>>>(a, count, rec, rows);
+    encode_rows_kernel<<<eg, kFillThreads, stream_bytes, s>>>(rec, count, digests, values, D, N, b, stream_bytes);
+    if (arity == 3)
+      solve_columns_kernel<3><<<fg, 32, 0, s>>>(rows, scratch_levels, waves, D, N, b);
+    else
+      solve_columns_kernel<4><<<fg, 32, 0, s>>>(rows, scratch_levels, waves, D, N, b);
+    return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
+  }
   if (stream_bytes > 48 * 1024) {
     cudaError_t e = arity == 3 ? cudaFuncSetAttribute(fill_wave_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream_bytes))
                                : cudaFuncSetAttribute(fill_wave_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream_bytes));

@@ -307,12 +307,16 @@ def test_full_size_batched_tensor_core_respond():
     srv.close()
 
 
-@pytest.mark.parametrize("b,K,N,nq", [(9, 4099, 941, 5), (10, 30011, 846, 130), (8, 2500, 37, 64), (14, 777, 129, 3), (4, 5000, 300, 128)])
-def test_respond_tensor_core_batch_matches_oracle(b, K, N, nq):
+@pytest.mark.parametrize("kernel", ["pair", "1sm"])
+@pytest.mark.parametrize("b,K,N,nq", [(9, 4099, 941, 5), (10, 30011, 846, 130), (8, 2500, 37, 64), (14, 777, 129, 3), (4, 5000, 300, 128),
+                                      (9, 3001, 600, 96), (10, 2049, 257, 40), (12, 129, 513, 33)])
+def test_respond_tensor_core_batch_matches_oracle(monkeypatch, kernel, b, K, N, nq):
     """Batched respond as a limb-decomposed int8 GEMM (north_star (2)): bit-exact against the oracle's Server::respond
     for every query of the batch, and identical to the streaming GEMV path."""
     import torch
 
+    # the CTA-pair kernel (cta_group::2; A rows in passes of 32 / 64 / 96 / 128) is the default, the one-SM kernel the kept comparison
+    monkeypatch.setenv("CHPIR_GEMM_KERNEL", kernel)
     rng = np.random.default_rng(b * 1000 + nq)
     D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
     srv, _ = cp.Server.setup_from_matrix(SEED, D, b, skip_hint=True, batch_tc=1)
