@@ -326,6 +326,7 @@ int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const 
                               uint64_t K, uint64_t N, DevBuf *d_out, uint8_t filter_bytes[68], double *host_s, double *device_s) {
   cudaStream_t st = ctx->stream;
   const double t0 = now_s();
+  double tt = trace_now();
   // D is allocated and cleared first so the memset runs under the host-side filter construction
   if (int rc = d_out->alloc(K * N * 4); rc != CHPIR_OK) return rc;
   CHPIR_CUDA(cudaMemsetAsync(d_out->p, 0, K * N * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
@@ -337,10 +338,15 @@ int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const 
   DevBuf d_fill_rec, d_fill_levels;
   if (int rc = d_fill_rec.alloc(n * kFillRecordBytes); rc != CHPIR_OK) return rc;
   if (int rc = d_fill_levels.alloc((n + 2) * 4); rc != CHPIR_OK) return rc;
-  // values do not depend on the filter: their upload (pageable memory, staged by the driver) also precedes the peeling
+  trace_phase("device allocations", tt);
+  // values do not depend on the filter: their upload (pageable memory) also precedes the peeling
   CHPIR_CUDA(cudaMemcpyAsync(d_valoff.p, val_off, (n + 1) * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  if (val_bytes) CHPIR_CUDA(cudaMemcpyAsync(d_values.p, val_blob, val_bytes, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  double tt = trace_now();
+  // (several helper threads with page-locked bounce buffers: the driver's own staging of a pageable copy is one core, ~3 GB/s here)
+  StagedUpload values_up;
+  if (!values_up.start(&ctx->stage, ctx->device, d_values.p, val_blob, val_bytes, st)) {
+    set_last_cuda_error(cudaGetLastError(), "values upload");
+    return CHPIR_ERR_CUDA_TRANSFER_FAILED;
+  }
   trace_phase("values upload (enqueue)", tt);
   std::vector<uint8_t> digests;
   PeelResult pr;
@@ -361,6 +367,12 @@ int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const 
   CHPIR_CUDA(cudaMemcpyAsync(d_found.p, pr.found.data(), n, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   CHPIR_CUDA(cudaMemcpyAsync(d_koo.p, pr.key_of_order.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   CHPIR_CUDA(cudaMemcpyAsync(d_digests.p, digests.data(), n * 32, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  trace_phase("plan upload (enqueue)", tt);
+  if (!values_up.finish(st)) {
+    set_last_cuda_error(cudaGetLastError(), "values upload");
+    return CHPIR_ERR_CUDA_TRANSFER_FAILED;
+  }
+  trace_phase("values upload (rest)", tt);
   const double t1 = now_s();
   EventTimer t_fill;
   t_fill.start(st);
@@ -493,6 +505,7 @@ void chpir_ctx_destroy(chpir_ctx *ctx) {
     cudaStreamDestroy(ctx->stream);
   }
   if (ctx->a_cache.a) cudaFree(ctx->a_cache.a);
+  ctx->stage.release();
   delete ctx;
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/chalamet_b200.h"
+#include "staged_upload.cuh"
 
 namespace chpir {
 
@@ -125,4 +126,5 @@ struct chpir_ctx {
     uint32_t *a = nullptr;
     bool matches(const uint8_t *s, uint32_t m_, uint64_t K_) const { return a && m == m_ && K == K_ && std::memcmp(seed, s, 32) == 0; }
   } a_cache;
+  chpir::StagePool stage;  // page-locked bounce buffers of the multi-threaded pageable upload (staged_upload.cuh), allocated on first use
 };

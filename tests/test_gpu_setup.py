@@ -248,6 +248,20 @@ def test_device_row_fill_is_byte_identical_to_host_encode(arity, n, val_len):
         assert fd == fo.to_bytes() and np.array_equal(Dd, Do)
 
 
+def test_device_row_fill_with_the_multi_threaded_values_upload(monkeypatch):
+    """The values reach HBM through four helper threads and page-locked bounce buffers once they are large (csrc/staged_upload.cuh);
+    forced here on a 9 MB value blob whose last 4 MB chunk is ragged: D must not change."""
+    db = make_db(9000, seed=77, val_len=(900, 1100))
+    b = O.find_mat_elem_bit_len(len(db))
+    D0, f0 = cp.encode_kv_database_device(db, b, 3, filter_seed_rng=5)
+    monkeypatch.setenv("CHPIR_STAGE_MIN_BYTES", "1")
+    for _ in range(2):  # the second run reuses the ctx's bounce buffers
+        D1, f1 = cp.encode_kv_database_device(db, b, 3, filter_seed_rng=5)
+        assert f0 == f1 and np.array_equal(D0, D1)
+    Dh, fh = cp.encode_kv_database(db, b, 3, filter_seed_rng=5)
+    assert fh == f0 and np.array_equal(Dh, D0)
+
+
 @pytest.mark.parametrize("arity", [3, 4])
 def test_setup_with_device_row_fill_end_to_end(arity):
     db = make_db(4000, seed=arity + 100, val_len=(1, 256))
