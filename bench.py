@@ -504,17 +504,22 @@ def batched_leg(cp, torch, cluster, srv, plans, K, N, b, BQ, iters, seed, Ds=Non
     ms = srv.respond_device(ptrs, BQ, out_tc.data_ptr(), mode=cp.RESPOND_TC, repeats=iters) / iters
     nlimb = 7 if b > 8 else 4
     tiles = -(-BQ // 128)
+    pair = not os.environ.get("CHPIR_GEMM_KERNEL", "").startswith("1")
+    # rows of the query operand the MMAs are issued for: the CTA-pair kernel rounds every pass to 32 rows, the one-SM kernel always pays for 128
+    rows_issued = sum(-(-min(128, BQ - 128 * t) // 32) * 32 for t in range(tiles)) if pair else 128 * tiles
 
-    def n_pad(nc):
+    def n_pad(nc):  # columns of D the MMAs are issued for: 128 per CTA, CTAs in pairs (one-SM kernel: tiles of <= 128 columns)
+        if pair:
+            return -(-nc // 256) * 256
         return -(-nc // 16) * 16 if nc <= 128 else -(-nc // 128) * 128
 
     by_rows = bool(srv.get_info()["respond_by_rows"])
-    if by_rows:  # every rank: 128 x N_pad x k_pitch
-        issued = nlimb * 2 * 128 * srv.k_pitch * n_pad(N) * cluster.n_gpus * tiles
+    if by_rows:  # every rank: rows_issued x N_pad x k_pitch
+        issued = nlimb * 2 * rows_issued * srv.k_pitch * n_pad(N) * cluster.n_gpus
         plane_bytes = (2 if b > 8 else 1) * srv.k_pitch * N * cluster.n_gpus * tiles
         inc = "limb split of each rank's own query words, int8-limb GEMM over its rows of D on every rank, sum of the partial responses on GPU 0 (peer reads)"
     else:
-        issued = sum(nlimb * 2 * 128 * K * n_pad(p["col_count"]) for p in plans) * tiles
+        issued = sum(nlimb * 2 * rows_issued * K * n_pad(p["col_count"]) for p in plans)
         plane_bytes = sum((2 if b > 8 else 1) * K * p["col_count"] for p in plans) * tiles
         inc = "NVLink gather of the K-sliced queries fused with the limb split, int8-limb GEMM on every rank, strided peer copy of the columns to GPU 0"
     return {"label": label, "queries_per_batch": BQ, "ms_per_batch": ms, "queries_per_s": BQ / (ms * 1e-3),
@@ -569,13 +574,20 @@ def run_b200(args):
         nc0 = plans[0]["col_count"]
         nlimb = 7 if b > 8 else 4
         m_pad = -(-LWE // 128) * 128
-        n_pad = -(-nc0 // 128) * 128 if nc0 > 128 else -(-nc0 // 16) * 16
+        pair = not os.environ.get("CHPIR_GEMM_KERNEL", "").startswith("1")
+        n_pad = -(-nc0 // 256) * 256 if pair else (-(-nc0 // 128) * 128 if nc0 > 128 else -(-nc0 // 16) * 16)
+        m_pad = (LWE // 128) * 128 + -(-(LWE % 128) // 32) * 32 if pair else m_pad  # the pair kernel issues the last panel in 32-row steps
         issued, useful = nlimb * 2 * m_pad * K * n_pad, nlimb * 2 * LWE * K * nc0
         int8_peak, int8_src = int8_peak_live(torch, dev0)
         gs = shard_infos[0]["gemm_ms"] * 1e-3
-        setup["gemm_roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::i8 limb GEMM, 14 panel launches, rank 0's column slice)",
-                                  "achieved": issued / gs / 1e12, "useful": useful / gs / 1e12, "peak": int8_peak, "peak_source": int8_src, "unit": "TOP/s",
-                                  "frac": issued / gs / 1e12 / int8_peak, "u32_mac_equivalent_tmacs": LWE * K * nc0 / gs / 1e12}
+        setup["gemm_roofline"] = {"bound": "tensor", "kernel": ("gemm_tc_pair_kernel (tcgen05 cta_group::2 kind::i8 limb GEMM on CTA pairs" if pair else "gemm_tc_kernel (tcgen05 kind::i8 limb GEMM") + ", 14 panel launches, rank 0's column slice)",
+                                  "achieved": issued / gs / 1e12, "useful": useful / gs / 1e12, "unit": "TOP/s",
+                                  # denominators: the measured dense bf16 rate of this pool (MEASURED_PEAKS.json, burst) x 2 for int8 -- the
+                                  # prescribed one --, the library's own int8 GEMM timed in this run, and the nominal 4.5 POP/s
+                                  "peak": 2 * peaks()["bf16_tflops"], "peak_source": "2 x bf16_tflops (burst; every panel GEMM is timed alone) of MEASURED_PEAKS.json: " + peaks()["source"],
+                                  "frac": issued / gs / 1e12 / (2 * peaks()["bf16_tflops"]),
+                                  "library_int8_tops": int8_peak, "library_int8_source": int8_src, "frac_of_library_int8": issued / gs / 1e12 / int8_peak,
+                                  "frac_of_nominal_4500": issued / gs / 1e12 / 4500.0, "u32_mac_equivalent_tmacs": LWE * K * nc0 / gs / 1e12}
         busy = tmax["xof_host_busy_s"] if tmax["xof_host_busy_s"] > 0 else tmax["expand_a_s"]
         setup["xof_ns_per_permutation"] = busy / (LWE * K * 4 / 168.0) * 1e9
         # hint parity: rows 0..1 of the GATHERED hint against exact products with the head of the XOF stream, on columns of every rank
