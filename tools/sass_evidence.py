@@ -12,8 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "chalametpir_b200", "libchalamet_b200.so")
-KERNELS = ["gemm_tc_kernelILi2", "gemm_tc_kernelILi1", "respond_ring_kernelILi9ELi4ELb0", "respond_ring_kernelILi10ELi4ELb0", "pull_slices_kernel",
-           "reduce_parts_kernelI5uint4", "fill_columns_kernelILi3", "split_transpose_bILi2", "pack_kernelILi9", "vec_x_mat_kernel", "expand_kernel"]
+KERNELS = ["gemm_tc_pair_kernelILi2", "gemm_tc_pair_kernelILi1", "gemm_tc_kernelILi2", "gemm_tc_kernelILi1", "respond_ring_kernelILi9ELi4ELb0", "respond_ring_kernelILi10ELi4ELb0", "pull_slices_kernel",
+           "reduce_parts_kernelI5uint4", "solve_columns_kernelILi3", "encode_rows_kernel", "split_transpose_bILi2", "pack_kernelILi9", "vec_x_mat_kernel", "expand_kernel"]
 MNEMONICS = ["UTCIMMA", "UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTCBAR", "LDTM", "STTM", "UTCCP", "UBLKCP", "SYNCS", "UCGABAR", "ATOMG", "REDG", "RED.E",
              "LDG.E.128", "LDS.128", "SHFL"]
 
