@@ -261,14 +261,15 @@ CHPIR_API int chpir_server_respond_device_tc(chpir_server *srv, const uint32_t *
 
 /* ---- cluster: the same server on 1..8 GPUs of ONE process (north_star (3)) ---------------------------
  * The reference's public surface cannot grow a rank argument -- `Server::setup(seed, db)` (server.rs:103) and
- * `Server::respond(&self, query)` (server.rs:184) -- so the sharding lives behind the handle: D, the hint and every response are
- * split by COLUMN slices over the GPUs (rank r owns chpir_cluster_plan's columns; no cross-rank arithmetic), the library owns the
- * per-device contexts, peer mappings, streams and NCCL communicators, and the Rust stub in INTEGRATION.md reaches all GPUs through
- * the unchanged two calls.  Data movement inside a respond:
- *   host query --(every GPU's own PCIe link: its K/n words)--> HBM --(NVLink peer reads, fused with the limb split / CE copies)-->
- *   whole query on every GPU --> GEMV or tensor-core GEMM on the column slice --> response columns written straight into the
- *   caller-visible row (strided D2H per GPU; no gather kernel).
- * NCCL (libnccl.so.2, resolved at run time) gathers the hint slices once per setup. */
+ * `Server::respond(&self, query)` (server.rs:184) -- so the sharding lives behind the handle: the library owns the per-device
+ * contexts, peer mappings, streams and NCCL communicators, and the Rust stub in INTEGRATION.md reaches all GPUs through the
+ * unchanged two calls.  Two cuts of D, each where it moves the fewest bytes:
+ *   setup   -- COLUMN slices: rank r computes hint columns chpir_cluster_plan gives it (no cross-rank arithmetic); the slices are
+ *              gathered on GPU 0 (NCCL, libnccl.so.2 resolved at run time; CHPIR_CLUSTER_GATHER=p2p: peer copies) and downloaded once;
+ *   respond -- ROW blocks (default for n > 1): rank r keeps rows [k_begin, +k_count) of D at full width and needs exactly the query
+ *              words it ingests over its own PCIe link; what crosses NVLink is each rank's N-word partial response, summed on GPU 0
+ *              (exact: addition mod 2^32 is order independent).  CHPIR_CLUSTER_SHARD=cols keeps the column cut for respond as well
+ *              (the whole query is then gathered on every GPU by NVLink peer reads). */
 typedef struct chpir_cluster chpir_cluster;
 typedef struct chpir_cluster_server chpir_cluster_server;
 

@@ -428,3 +428,20 @@ def test_plain_c_program_over_the_header_runs_setup_and_respond(n):
     out = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "dropin_test ok" in out.stdout
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_cpp_mirror_of_server_and_client_runs_the_reference_integration_tests(n):
+    """tests/cpp/test_pir.cpp over include/chalamet_b200.hpp (Server::setup / Server::respond / Client::* with the reference's names and
+    error variants): the reference's end-to-end tests for both arities (integrations/src/test_pir.rs), the error behaviour of
+    setup / respond / query / process_response, and one Server shared by 16 concurrent tasks -- on n GPUs via $CHPIR_GPUS."""
+    need(n)
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "build", "test_pir_cpp")
+    assert os.path.exists(exe), "build() did not produce build/test_pir_cpp"
+    out = subprocess.run([exe, "2", "13"], capture_output=True, text=True, timeout=600, env={**os.environ, "CHPIR_GPUS": str(n)})
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "test_pir_cpp ok" in out.stdout

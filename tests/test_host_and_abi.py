@@ -41,6 +41,28 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert e.value.variant == "CudaDeviceNotFound"
 
 
+def test_cpp_mirror_builds_and_fails_loudly_without_a_gpu():
+    """include/chalamet_b200.hpp (Server / Client / ChalametPIRError over the C ABI) compiles as plain C++17 on its own, and the test
+    program built from it (tests/cpp/test_pir.cpp, the reference's integration tests) aborts with the CUDA variant instead of answering
+    from anywhere else when there is no GPU."""
+    import subprocess
+
+    import torch
+
+    from conftest import ROOT
+
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, os.path.join(inc, "chalamet_b200.hpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = os.path.join(ROOT, "build", "test_pir_cpp")
+    assert os.path.exists(exe), "build() did not produce build/test_pir_cpp"
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the program is run by tests/test_gpu_cluster.py")
+    out = subprocess.run([exe, "1", "9"], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "CudaDeviceNotFound" in out.stderr
+
+
 @pytest.mark.parametrize("n", [1, 2, 10, 100, 2**8, 2**12, 2**16, 2**18, 2**20, 2**22, 2**30, 2**42])
 def test_bit_len_matches_oracle(n):
     assert cp.find_mat_elem_bit_len(n) == O.find_mat_elem_bit_len(n)
