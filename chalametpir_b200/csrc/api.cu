@@ -595,6 +595,13 @@ int chpir_encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, 
 int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k,
                               uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
                               size_t *hint_len, chpir_server **out) {
+  return server_setup_from_device_matrix(ctx, seed, d_device, rows_k, cols_n, b, opts, hint_out, hint_cap, hint_len, out, nullptr);
+}
+
+extern "C++" {
+int chpir::server_setup_from_device_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k,
+                                           uint32_t cols_n, uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap,
+                                           size_t *hint_len, chpir_server **out, HostAPipe *pipe) {
   CHPIR_GUARD_BEGIN
   if (!ctx || !seed || !d_device || !out) return CHPIR_ERR_INVALID_ARGUMENT;
   *out = nullptr;
@@ -610,7 +617,7 @@ int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE
   CHPIR_CUDA(cudaDeviceSynchronize(), CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED);
   const double t0 = now_s();
   chpir_server *srv = new chpir_server();
-  int rc = setup_core(ctx, seed, d_device, rows_k, cols_n, c0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv);
+  int rc = setup_core(ctx, seed, d_device, rows_k, cols_n, c0, nc, c0, b, o, hint_out, hint_cap, hint_len, srv, pipe);
   if (rc != CHPIR_OK) {
     delete srv;
     return rc;
@@ -620,6 +627,7 @@ int chpir_server_setup_device(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE
   return CHPIR_OK;
   CHPIR_GUARD_END
 }
+}  // extern "C++"
 
 extern "C++" {
 int chpir::server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k,

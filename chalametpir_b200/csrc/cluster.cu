@@ -946,6 +946,68 @@ struct EarlyNccl {
   ~EarlyNccl() { wait(); }
 };
 
+// ONE XOF chain for the whole cluster.  Every rank needs all of A = generate_from_seed(lwe, K, seed) and the squeeze is serial, so
+// the first rank that has no cached A runs the host pipeline (one producer core, one upload over its PCIe link) and its uploader
+// forwards every finished 128-row panel from its HBM to the other ranks' rings over NVLink (HostAPipe::start_mirror): 8.4 GB cross
+// PCIe once instead of n times, n - 1 host cores and their memory traffic are free for the filter / row encoding, and the chain runs
+// at its solo speed (n producers side by side: 105-107 ns per permutation and up to 0.5 s of stalls at n = 8 instead of 104 ns).
+// CHPIR_CLUSTER_XOF=per_rank keeps one chain per rank (the measured comparison).  all_panels: rings as deep as A (the chain starts
+// before the consumers exist, or A is to be kept); otherwise two panels.
+struct SharedChain {
+  std::vector<std::unique_ptr<HostAPipe>> pipes;  // per rank; null where A comes from the ctx cache or no host chain is wanted
+  HostAPipe *leader = nullptr;
+  ~SharedChain() {
+    if (leader) leader->shutdown();  // its uploader writes into the mirrors: it goes first
+  }
+  HostAPipe *of(uint32_t d) const { return pipes[d].get(); }
+  int start(chpir_cluster_server *S, const chpir_setup_opts &o, const uint8_t *seed, uint64_t K, bool all_panels) {
+    pipes.resize(S->n);
+    if (o.a_expand == CHPIR_A_EXPAND_DEVICE || o.skip_hint || o.gemm_variant != 0) return CHPIR_OK;
+    const uint32_t panels = (S->lwe + 127) / 128, depth = all_panels || o.a_cache ? panels : 2;
+    const bool per_rank = env_is("CHPIR_CLUSTER_XOF", "per_rank");
+    std::vector<uint32_t> need;
+    for (uint32_t d = 0; d < S->n; d++) {
+      bool cached = false;
+      if (o.a_cache) {
+        std::lock_guard<std::mutex> g(S->r[d].ctx->mu);
+        cached = S->r[d].ctx->a_cache.matches(seed, S->lwe, K);
+      }
+      if (!cached) need.push_back(d);
+    }
+    if (need.empty()) return CHPIR_OK;
+    if (per_rank) {
+      for (uint32_t d : need) {
+        pipes[d].reset(new HostAPipe());
+        if (int rc = pipes[d]->start(S->r[d].dev, seed, S->lwe, K, o.host_chunk_rows, depth); rc != CHPIR_OK) return rc;
+      }
+      return CHPIR_OK;
+    }
+    // the chain first (it is the critical path of the whole setup), the mirrors' rings while it is already squeezing: the leader
+    // starts forwarding with its first complete panel, ~0.4 s in
+    std::vector<HostAPipe *> mirrors;
+    for (size_t i = 1; i < need.size(); i++) {
+      pipes[need[i]].reset(new HostAPipe());
+      mirrors.push_back(pipes[need[i]].get());
+    }
+    pipes[need[0]].reset(new HostAPipe());
+    leader = pipes[need[0]].get();
+    std::vector<std::thread> th;
+    std::vector<int> rcs(need.size(), CHPIR_OK);
+    for (size_t i = 1; i < need.size(); i++)
+      th.emplace_back([&, i] { rcs[i] = pipes[need[i]]->start_mirror(S->r[need[i]].dev, S->lwe, K, depth); });
+    // (start() returns once the leader's own ring exists; its uploader waits for `mirrors_ready` before the first forward)
+    rcs[0] = leader->start(S->r[need[0]].dev, seed, S->lwe, K, o.host_chunk_rows, depth, mirrors);
+    for (auto &t : th) t.join();
+    for (int rc : rcs)
+      if (rc != CHPIR_OK) {
+        leader->shutdown();  // before the first forward: a mirror without a ring must never be written to
+        return rc;
+      }
+    leader->mirrors_ready();
+    return CHPIR_OK;
+  }
+};
+
 // Where a setup flavour left D: the whole matrix in host memory, or the ranks' compact column slices in their HBM.
 struct DSource {
   const uint32_t *host = nullptr;
@@ -1229,10 +1291,14 @@ int chpir_cluster_server_setup_device(chpir_cluster *cl, const uint8_t seed[CHPI
   const double t0 = now_s();
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, rows_k, cols_n, b, o));
   EarlyNccl nccl(cl, S->n, o);
+  SharedChain chain;
+  if (S->n > 1)
+    if (int rc = chain.start(S.get(), o, seed, rows_k, false); rc != CHPIR_OK) return rc;
   int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
     if (!d_slices[d]) return CHPIR_ERR_INVALID_ARGUMENT;
     const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, true);
-    return chpir_server_setup_device(S->r[d].ctx, seed, d_slices[d], rows_k, S->r[d].pl.nc, b, &ro, nullptr, 0, nullptr, &S->r[d].srv);
+    return server_setup_from_device_matrix(S->r[d].ctx, seed, d_slices[d], rows_k, S->r[d].pl.nc, b, &ro, nullptr, 0, nullptr, &S->r[d].srv,
+                                           S->n > 1 ? chain.of(d) : nullptr);
   });
   if (rc != CHPIR_OK) return rc;
   nccl.wait();
@@ -1260,9 +1326,13 @@ int chpir_cluster_server_setup(chpir_cluster *cl, const uint8_t seed[CHPIR_SEED_
   const double t0 = now_s();
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, rows_k, cols_n, b, o));
   EarlyNccl nccl(cl, S->n, o);
+  SharedChain chain;
+  if (S->n > 1)
+    if (int rc = chain.start(S.get(), o, seed, rows_k, false); rc != CHPIR_OK) return rc;
   int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
     const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false);
-    return server_setup_from_host_matrix(S->r[d].ctx, seed, d_host, rows_k, cols_n, b, &ro, nullptr, 0, nullptr, &S->r[d].srv, nullptr);
+    return server_setup_from_host_matrix(S->r[d].ctx, seed, d_host, rows_k, cols_n, b, &ro, nullptr, 0, nullptr, &S->r[d].srv,
+                                         S->n > 1 ? chain.of(d) : nullptr);
   });
   if (rc != CHPIR_OK) return rc;
   nccl.wait();
@@ -1300,6 +1370,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   std::unique_ptr<chpir_cluster_server> S(new_server(cl, K, uint32_t(N), b, o));
   EarlyNccl nccl(cl, S->n, o);
   std::unique_ptr<uint32_t[]> d_store;  // n > 1: D, encoded once on the host; lives until the row blocks have been cut from it
+  SharedChain chain;
   if (S->n == 1) {
     // one GPU: the single-GPU call as it is (device row fill, its own early XOF start), hint slice = whole hint
     chpir_setup_opts ro = o;
@@ -1310,27 +1381,16 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
         rc != CHPIR_OK)
       return rc;
   } else {
-    // Every rank needs all of A = generate_from_seed(lwe, K, seed), and the XOF chain is serial: each rank's host pipeline starts
-    // NOW (its own producer core, ring as deep as A) and squeezes beside the host filter/encode phase below, exactly as the
-    // single-GPU call does; D is encoded once on the host and every rank uploads its own columns.
+    // Every rank needs all of A = generate_from_seed(lwe, K, seed), and the XOF chain is serial: it starts NOW (one producer core,
+    // rings as deep as A on every GPU, panels forwarded over NVLink) and squeezes beside the host filter/encode phase below, exactly
+    // as the single-GPU call does; D is encoded once on the host and every rank uploads its own columns.
     const bool host_a = o.a_expand != CHPIR_A_EXPAND_DEVICE && !o.skip_hint && o.gemm_variant == 0;
-    std::vector<std::unique_ptr<HostAPipe>> pipes(S->n);
-    if (host_a) {
-      for (uint32_t d = 0; d < S->n; d++) {
-        bool cached = false;
-        if (o.a_cache) {
-          std::lock_guard<std::mutex> g(S->r[d].ctx->mu);
-          cached = S->r[d].ctx->a_cache.matches(seed, S->lwe, K);
-        }
-        if (cached) continue;
-        pipes[d].reset(new HostAPipe());
-        if (int rc = pipes[d]->start(S->r[d].dev, seed, S->lwe, K, o.host_chunk_rows, (S->lwe + 127) / 128); rc != CHPIR_OK) return rc;
-      }
-    }
+    if (int rc = chain.start(S.get(), o, seed, K, true); rc != CHPIR_OK) return rc;
     d_store.reset(new (std::nothrow) uint32_t[K * N]);
     if (!d_store) return CHPIR_ERR_HOST_ALLOCATION_FAILED;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    if (host_a) set_encode_threads(hw > S->n + 2 ? hw - S->n - 1 : 1);  // the producer cores stay free for the chains
+    const unsigned chains = chain.leader ? 1u : S->n;
+    if (host_a) set_encode_threads(hw > chains + 2 ? hw - chains - 1 : 1);  // the producer cores stay free for the chains
     int rc = encode_kv_database(arity, n, key_blob, key_offsets, value_blob, value_offsets, b, CHPIR_SERVER_SETUP_MAX_ATTEMPT_COUNT, filter_seed_rng,
                                 d_store.get(), filter_params_out);
     set_encode_threads(0);
@@ -1338,7 +1398,7 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
     const double t1 = now_s();
     rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
       const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, false);
-      return server_setup_from_host_matrix(S->r[d].ctx, seed, d_store.get(), K, uint32_t(N), b, &ro, nullptr, 0, nullptr, &S->r[d].srv, pipes[d].get());
+      return server_setup_from_host_matrix(S->r[d].ctx, seed, d_store.get(), K, uint32_t(N), b, &ro, nullptr, 0, nullptr, &S->r[d].srv, chain.of(d));
     });
     if (rc != CHPIR_OK) return rc;
     for (uint32_t d = 0; d < S->n; d++) S->r[d].srv->timing.host_encode_s = t1 - t0;

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "host_xof.hpp"
@@ -106,7 +108,41 @@ class HostAPipe {
     if (up_) cudaStreamDestroy(up_);
   }
 
-  int start(int device, const uint8_t seed[32], uint32_t m, uint64_t K, uint32_t chunk_rows_opt, uint32_t depth) {
+  // A follower of another pipe's chain (n GPUs of one process need the same A, and the chain is serial): no producer, no host
+  // buffers -- the leader's uploader forwards every finished panel from its own HBM over NVLink (copy engines) into this pipe's
+  // ring and signals it exactly as an uploader of its own would.  Must be set up before the leader's start() is given the pointer,
+  // and outlive the leader's threads (shut the leader down first).
+  int start_mirror(int device, uint32_t m, uint64_t K, uint32_t depth) {
+    device_ = device, m_ = m, K_ = K, mirror_ = true;
+    row_bytes_ = K * 4;
+    panels_ = (m + 127) / 128;
+    panel_bytes_ = uint64_t(std::min(m, 128u)) * row_bytes_;
+    depth_ = std::max(1u, std::min(depth, panels_));
+    while (depth_ > 2 && uint64_t(depth_) * panel_bytes_ > (48ull << 30)) depth_--;
+    if (cudaSetDevice(device) != cudaSuccess) return CHPIR_ERR_CUDA_DEVICE_NOT_FOUND;
+    if (int rc = panels_dev_.alloc(uint64_t(depth_) * panel_bytes_); rc != CHPIR_OK) return rc;
+    ready_.assign(panels_, nullptr);
+    consumed_.assign(panels_, nullptr);
+    for (uint32_t p = 0; p < panels_; p++)
+      if (cudaEventCreateWithFlags(&ready_[p], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&consumed_[p], cudaEventDisableTiming) != cudaSuccess)
+        return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    if (cudaStreamCreateWithFlags(&up_, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
+    return CHPIR_OK;
+  }
+  bool is_mirror() const { return mirror_; }
+  // Leader: the mirrors handed to start() have finished start_mirror() (their rings are allocated beside the running chain).
+  void mirrors_ready() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      mirrors_ready_ = true;
+    }
+    cv_.notify_all();
+  }
+
+  int start(int device, const uint8_t seed[32], uint32_t m, uint64_t K, uint32_t chunk_rows_opt, uint32_t depth,
+            std::vector<HostAPipe *> mirrors = {}) {
+    mirrors_ = std::move(mirrors);
     device_ = device, m_ = m, K_ = K;
     std::memcpy(seed_, seed, 32);
     row_bytes_ = K * 4;
@@ -230,6 +266,56 @@ class HostAPipe {
       abort_ = true;
     }
     cv_.notify_all();
+    fail_mirrors(rc);
+  }
+
+  // Leader's uploader: panel p is complete in this pipe's ring (ready_[p] recorded on up_) -- send it on to every mirror.
+  bool forward_panel(uint32_t p) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return mirrors_ready_ || abort_; });
+      if (!mirrors_ready_) return true;
+    }
+    const uint32_t rows = std::min(m_, (p + 1) * 128) - p * 128;
+    const uint8_t *src = panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_;
+    bool ok = true;
+    for (HostAPipe *m : mirrors_) {
+      if (p >= m->depth_) {  // the ring slot's previous tenant must have been read by the mirror's consumer
+        std::unique_lock<std::mutex> lk(m->mu_);
+        // (not broken by this pipe's own shutdown(): the leader's consumer is done as soon as IT has the last panel, the mirrors
+        // still need theirs; shutdown() joins this thread)
+        m->cv_.wait(lk, [&] { return m->released_panels_ > p - m->depth_ || m->abort_ || m->rc_ != CHPIR_OK; });
+        if (m->abort_ || m->rc_ != CHPIR_OK) continue;  // that rank gave up: nobody reads its ring any more
+      }
+      uint8_t *dst = m->panels_dev_.as<uint8_t>() + uint64_t(p % m->depth_) * m->panel_bytes_;
+      ok = ok && cudaSetDevice(m->device_) == cudaSuccess;
+      if (p >= m->depth_) ok = ok && cudaStreamWaitEvent(m->up_, m->consumed_[p - m->depth_], 0) == cudaSuccess;
+      ok = ok && cudaStreamWaitEvent(m->up_, ready_[p], 0) == cudaSuccess &&
+           cudaMemcpyPeerAsync(dst, m->device_, src, device_, uint64_t(rows) * row_bytes_, m->up_) == cudaSuccess &&
+           cudaEventRecord(m->ready_[p], m->up_) == cudaSuccess;
+      // this pipe's own ring slot may only be refilled once the mirror has copied it out
+      if (ok && p + depth_ < panels_) {
+        std::lock_guard<std::mutex> lk(mu_);
+        forwarded_.push_back({p, m});
+      }
+      if (!ok) break;
+      {
+        std::lock_guard<std::mutex> lk(m->mu_);
+        m->uploaded_panels_ = p + 1;
+      }
+      m->cv_.notify_all();
+    }
+    cudaSetDevice(device_);
+    return ok;
+  }
+  void fail_mirrors(int rc) {
+    for (HostAPipe *m : mirrors_) {  // their consumers wait for panels that will never come
+      {
+        std::lock_guard<std::mutex> lk(m->mu_);
+        if (m->rc_ == CHPIR_OK) m->rc_ = rc;
+      }
+      m->cv_.notify_all();
+    }
   }
 
   void produce() {
@@ -271,6 +357,19 @@ class HostAPipe {
   }
 
   void upload() {
+    upload_chunks();
+    if (mirrors_.empty()) return;
+    bool complete;
+    int rc;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      complete = issued_ == chunks_.size();
+      rc = rc_;
+    }
+    if (!complete) fail_mirrors(rc != CHPIR_OK ? rc : CHPIR_ERR_CUDA_TRANSFER_FAILED);  // the chain was stopped early: no more panels
+  }
+
+  void upload_chunks() {
     cudaSetDevice(device_);
     for (uint64_t i = 0; i < chunks_.size(); i++) {
       const uint32_t r0 = chunks_[i].first, nr = chunks_[i].second, p = r0 / 128, panel_end = std::min(m_, (p + 1) * 128);
@@ -284,6 +383,15 @@ class HostAPipe {
         }
       }
       if (r0 == p * 128 && p >= depth_ && cudaStreamWaitEvent(up_, consumed_[p - depth_], 0) != cudaSuccess) return fail(CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+      if (r0 == p * 128 && p >= depth_ && !mirrors_.empty()) {  // ... and copied out by every mirror (their ready event of that panel)
+        std::vector<std::pair<uint32_t, HostAPipe *>> f;
+        {
+          std::lock_guard<std::mutex> lk(mu_);
+          f = forwarded_;
+        }
+        for (auto &pm : f)
+          if (pm.first == p - depth_ && cudaStreamWaitEvent(up_, pm.second->ready_[pm.first], 0) != cudaSuccess) return fail(CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+      }
       const int b = int(i % kBufs);
       uint8_t *dst = panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_ + uint64_t(r0 - p * 128) * row_bytes_;
       if (cudaMemcpyAsync(dst, pinned_[b], uint64_t(nr) * row_bytes_, cudaMemcpyHostToDevice, up_) != cudaSuccess ||
@@ -299,9 +407,16 @@ class HostAPipe {
         if (last) uploaded_panels_ = p + 1;
       }
       cv_.notify_all();
+      if (last && !mirrors_.empty() && !forward_panel(p)) {
+        set_last_cuda_error(cudaGetLastError(), "XOF panel forward over NVLink");
+        return fail(CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      }
     }
   }
 
+  bool mirror_ = false, mirrors_ready_ = false;
+  std::vector<HostAPipe *> mirrors_;                       // leader only
+  std::vector<std::pair<uint32_t, HostAPipe *>> forwarded_;  // leader only: (panel, mirror) copies whose source slot will be reused
   int device_ = 0;
   uint32_t m_ = 0, panels_ = 0, depth_ = 0;
   uint64_t K_ = 0, row_bytes_ = 0, panel_bytes_ = 0;

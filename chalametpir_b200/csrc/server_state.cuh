@@ -52,6 +52,9 @@ class HostAPipe;
 int server_setup_from_host_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_host, uint64_t rows_k, uint32_t cols_n,
                                   uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out,
                                   HostAPipe *pipe);
+int server_setup_from_device_matrix(chpir_ctx *ctx, const uint8_t seed[CHPIR_SEED_BYTE_LEN], const uint32_t *d_device, uint64_t rows_k, uint32_t cols_n,
+                                    uint32_t b, const chpir_setup_opts *opts, uint8_t *hint_out, size_t hint_cap, size_t *hint_len, chpir_server **out,
+                                    HostAPipe *pipe);
 // registry of the page-locked ranges chpir_host_alloc handed out (device-readable from every GPU of the process)
 void pinned_registry_add(const void *p, size_t bytes);
 void pinned_registry_remove(const void *p);

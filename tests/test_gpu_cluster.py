@@ -414,6 +414,36 @@ def test_full_size_cluster_respond_equals_single_gpu_bytes(n):
     cl.close()
 
 
+@pytest.mark.parametrize("mode", ["shared", "per_rank"])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_cluster_walks_one_xof_chain_and_forwards_the_panels(n, mode, monkeypatch):
+    """A = generate_from_seed(lwe, K, seed) for n GPUs from ONE host chain: the leader's uploader forwards every 128-row panel over
+    NVLink into the other ranks' rings (csrc/host_pipe.cuh start_mirror).  Four panels through two-panel rings (slots reused on the
+    leader and on the mirrors), then rings as deep as A that stay behind as the ctx cache, then a setup served from those caches:
+    the hint must be the oracle's every time, as with one chain per rank (CHPIR_CLUSTER_XOF=per_rank)."""
+    need(n)
+    monkeypatch.setenv("CHPIR_CLUSTER_XOF", mode)
+    rng = np.random.default_rng(7 * n)
+    K, N, b, lwe = 3001, 97, 9, 400
+    D = rng.integers(0, 1 << b, size=(K, N), dtype=np.uint32)
+    ohint = O.Server.setup_from_matrix(SEED, D, b, lwe_rows=lwe)[1]
+    cl = cp.Cluster(n_gpus=n)
+    try:
+        for a_cache in (False, True, True):
+            srv, hint = cp.ClusterServer.setup_from_matrix(cl, SEED, D, b, lwe_rows=lwe, a_cache=a_cache, host_chunk_rows=37)
+            assert hint == ohint, (mode, a_cache)
+            srv.close()
+        assert all(x == lwe * K * 4 for x in cl.drop_a_cache())
+        db = make_db(1500, seed=n, val_len=(1, 90))
+        srv, hint, fbytes = cp.ClusterServer.setup(cl, SEED, db, 3, filter_seed_rng=3, lwe_rows=300)  # the chain starts before D exists
+        s1, h1, f1 = cp.Server.setup(SEED, db, 3, filter_seed_rng=3, lwe_rows=300)
+        assert hint == h1 and fbytes == f1
+        srv.close()
+        s1.close()
+    finally:
+        cl.close()
+
+
 @pytest.mark.parametrize("n", [1, 2, 8])
 def test_plain_c_program_over_the_header_runs_setup_and_respond(n):
     """tests/c/dropin_test.c: includes include/chalamet_b200.h as C11, links libchalamet_b200.so, runs Server::setup -> Server::respond
