@@ -348,6 +348,40 @@ struct chpir_cluster {
     }
     return CHPIR_OK;
   }
+  // The first send/recv between two ranks sets up their channels (~0.2 s at n = 8); the hint gather is the only NCCL traffic of a
+  // setup and sits on its critical path after the XOF chain, so the same rank d -> rank 0 pattern is run once with a few bytes
+  // right after the communicators exist (on the helper thread, beside the chain).
+  bool comms_warm = false;
+  int warm_comms() {
+    if (comms_warm || n < 2 || comms.empty()) return CHPIR_OK;
+    NcclApi *api = nccl_api();
+    if (!api) return CHPIR_ERR_NCCL_FAILED;
+    std::vector<void *> buf(size_t(n), nullptr);
+    std::vector<cudaStream_t> st(size_t(n), nullptr);
+    bool ok = true;
+    for (int d = 0; d < n && ok; d++)
+      ok = cudaSetDevice(dev[size_t(d)]) == cudaSuccess && cudaMalloc(&buf[size_t(d)], 256 * size_t(n)) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&st[size_t(d)], cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) {
+      ncclResult_t nr = api->GroupStart();
+      for (int d = 1; d < n && nr == ncclSuccess; d++) {
+        nr = api->Send(buf[size_t(d)], 64, ncclUint32, 0, comms[size_t(d)], st[size_t(d)]);
+        if (nr == ncclSuccess) nr = api->Recv(static_cast<char *>(buf[0]) + 256 * d, 64, ncclUint32, d, comms[0], st[0]);
+      }
+      ok = api->GroupEnd() == ncclSuccess && nr == ncclSuccess;
+    }
+    for (int d = 0; d < n; d++) {
+      cudaSetDevice(dev[size_t(d)]);
+      if (st[size_t(d)]) {
+        if (cudaStreamSynchronize(st[size_t(d)]) != cudaSuccess) ok = false;
+        cudaStreamDestroy(st[size_t(d)]);
+      }
+      if (buf[size_t(d)]) cudaFree(buf[size_t(d)]);
+    }
+    (void)cudaGetLastError();
+    comms_warm = ok;
+    return ok ? CHPIR_OK : CHPIR_ERR_NCCL_FAILED;
+  }
   ~chpir_cluster() {
     if (!comms.empty()) {
       NcclApi *api = nccl_api();
@@ -937,7 +971,7 @@ struct EarlyNccl {
       th = std::thread([cl] {
         DeviceRestore restore_device;
         std::lock_guard<std::mutex> g(cl->mu);
-        (void)cl->ensure_comms();  // a failure is reported by the gather, which asks again
+        if (cl->ensure_comms() == CHPIR_OK) (void)cl->warm_comms();  // a failure is reported by the gather, which asks again
       });
   }
   void wait() {
@@ -991,12 +1025,14 @@ struct SharedChain {
     }
     pipes[need[0]].reset(new HostAPipe());
     leader = pipes[need[0]].get();
-    std::vector<std::thread> th;
+    // (the leader's own start-up first: the mirrors' allocations would queue in front of its ring and hold its uploader back while
+    // the chunk ring fills; its forwarder thread waits for `mirrors_ready`, the uploader does not)
     std::vector<int> rcs(need.size(), CHPIR_OK);
-    for (size_t i = 1; i < need.size(); i++)
-      th.emplace_back([&, i] { rcs[i] = pipes[need[i]]->start_mirror(S->r[need[i]].dev, S->lwe, K, depth); });
-    // (start() returns once the leader's own ring exists; its uploader waits for `mirrors_ready` before the first forward)
     rcs[0] = leader->start(S->r[need[0]].dev, seed, S->lwe, K, o.host_chunk_rows, depth, mirrors);
+    std::vector<std::thread> th;
+    if (rcs[0] == CHPIR_OK)
+      for (size_t i = 1; i < need.size(); i++)
+        th.emplace_back([&, i] { rcs[i] = pipes[need[i]]->start_mirror(S->r[need[i]].dev, S->lwe, K, depth); });
     for (auto &t : th) t.join();
     for (int rc : rcs)
       if (rc != CHPIR_OK) {

@@ -201,6 +201,7 @@ class HostAPipe {
         return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
     if (cudaStreamCreateWithFlags(&up_, cudaStreamNonBlocking) != cudaSuccess) return CHPIR_ERR_CUDA_ALLOCATION_FAILED;
     uploader_ = std::thread([this] { upload(); });  // the first chunks are already waiting for it
+    if (!mirrors_.empty()) forwarder_ = std::thread([this] { forward_loop(); });
     return CHPIR_OK;
   }
 
@@ -233,6 +234,7 @@ class HostAPipe {
     cv_.notify_all();
     if (producer_.joinable()) producer_.join();
     if (uploader_.joinable()) uploader_.join();
+    if (forwarder_.joinable()) forwarder_.join();
     if (up_) cudaStreamSynchronize(up_);
     free_chunks();  // the chunk ring is only needed while the chain runs (a client keeps the pipe alive as the owner of A)
   }
@@ -271,11 +273,6 @@ class HostAPipe {
 
   // Leader's uploader: panel p is complete in this pipe's ring (ready_[p] recorded on up_) -- send it on to every mirror.
   bool forward_panel(uint32_t p) {
-    {
-      std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [&] { return mirrors_ready_ || abort_; });
-      if (!mirrors_ready_) return true;
-    }
     const uint32_t rows = std::min(m_, (p + 1) * 128) - p * 128;
     const uint8_t *src = panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_;
     bool ok = true;
@@ -293,11 +290,6 @@ class HostAPipe {
       ok = ok && cudaStreamWaitEvent(m->up_, ready_[p], 0) == cudaSuccess &&
            cudaMemcpyPeerAsync(dst, m->device_, src, device_, uint64_t(rows) * row_bytes_, m->up_) == cudaSuccess &&
            cudaEventRecord(m->ready_[p], m->up_) == cudaSuccess;
-      // this pipe's own ring slot may only be refilled once the mirror has copied it out
-      if (ok && p + depth_ < panels_) {
-        std::lock_guard<std::mutex> lk(mu_);
-        forwarded_.push_back({p, m});
-      }
       if (!ok) break;
       {
         std::lock_guard<std::mutex> lk(m->mu_);
@@ -308,6 +300,34 @@ class HostAPipe {
     cudaSetDevice(device_);
     return ok;
   }
+  // Leader's forwarder thread: panels go on to the mirrors in order, as soon as they are complete here; the uploader never waits for
+  // a mirror except to reuse a ring slot.  Keeps going after shutdown() until everything uploaded has been forwarded (the leader's
+  // consumer is done as soon as IT has the last panel; shutdown() joins this thread).
+  void forward_loop() {
+    cudaSetDevice(device_);
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return mirrors_ready_ || abort_; });
+      if (!mirrors_ready_) return;
+    }
+    for (uint32_t p = 0; p < panels_; p++) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return uploaded_panels_ > p || abort_; });
+        if (uploaded_panels_ <= p) return;  // stopped early; upload() tells the mirrors
+      }
+      if (!forward_panel(p)) {
+        set_last_cuda_error(cudaGetLastError(), "XOF panel forward over NVLink");
+        return fail(CHPIR_ERR_CUDA_TRANSFER_FAILED);
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        forwarded_panels_ = p + 1;
+      }
+      cv_.notify_all();
+    }
+  }
+
   void fail_mirrors(int rc) {
     for (HostAPipe *m : mirrors_) {  // their consumers wait for panels that will never come
       {
@@ -384,13 +404,13 @@ class HostAPipe {
       }
       if (r0 == p * 128 && p >= depth_ && cudaStreamWaitEvent(up_, consumed_[p - depth_], 0) != cudaSuccess) return fail(CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
       if (r0 == p * 128 && p >= depth_ && !mirrors_.empty()) {  // ... and copied out by every mirror (their ready event of that panel)
-        std::vector<std::pair<uint32_t, HostAPipe *>> f;
         {
-          std::lock_guard<std::mutex> lk(mu_);
-          f = forwarded_;
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&] { return forwarded_panels_ > p - depth_ || abort_; });
+          if (forwarded_panels_ <= p - depth_) return;
         }
-        for (auto &pm : f)
-          if (pm.first == p - depth_ && cudaStreamWaitEvent(up_, pm.second->ready_[pm.first], 0) != cudaSuccess) return fail(CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
+        for (HostAPipe *m : mirrors_)
+          if (cudaStreamWaitEvent(up_, m->ready_[p - depth_], 0) != cudaSuccess) return fail(CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED);
       }
       const int b = int(i % kBufs);
       uint8_t *dst = panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_ + uint64_t(r0 - p * 128) * row_bytes_;
@@ -407,16 +427,12 @@ class HostAPipe {
         if (last) uploaded_panels_ = p + 1;
       }
       cv_.notify_all();
-      if (last && !mirrors_.empty() && !forward_panel(p)) {
-        set_last_cuda_error(cudaGetLastError(), "XOF panel forward over NVLink");
-        return fail(CHPIR_ERR_CUDA_TRANSFER_FAILED);
-      }
     }
   }
 
   bool mirror_ = false, mirrors_ready_ = false;
   std::vector<HostAPipe *> mirrors_;                       // leader only
-  std::vector<std::pair<uint32_t, HostAPipe *>> forwarded_;  // leader only: (panel, mirror) copies whose source slot will be reused
+  uint32_t forwarded_panels_ = 0;                          // leader only: panels handed to every mirror's stream
   int device_ = 0;
   uint32_t m_ = 0, panels_ = 0, depth_ = 0;
   uint64_t K_ = 0, row_bytes_ = 0, panel_bytes_ = 0;
@@ -435,7 +451,7 @@ class HostAPipe {
   uint32_t uploaded_panels_ = 0, released_panels_ = 0;
   bool abort_ = false;
   int rc_ = CHPIR_OK;
-  std::thread producer_, uploader_;
+  std::thread producer_, uploader_, forwarder_;
   double busy_ = 0.0, wait_ = 0.0;
 };
 
