@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include "common.cuh"
+#include "device_fill.cuh"
 #include "host_encode.hpp"
 #include "host_pipe.cuh"
 #include "host_xof.hpp"
@@ -319,67 +320,85 @@ int setup_core(chpir_ctx *ctx, const uint8_t *seed, const uint32_t *d_dev, uint6
   return CHPIR_OK;
 }
 
-// Matrix::from_kv_database::<ARITY> with the row fill on the GPU: host = key digests + filter construction + wave plan, device =
-// row encoding + dependent fill.  d_out receives the K x N u32 matrix in HBM (the caller's stream `st` is synchronised on return).
-int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off,
-                              const uint8_t *val_blob, const uint64_t *val_off, uint32_t b, uint32_t max_attempts, const uint64_t *seed_rng,
-                              uint64_t K, uint64_t N, DevBuf *d_out, uint8_t filter_bytes[68], double *host_s, double *device_s) {
-  cudaStream_t st = ctx->stream;
-  const double t0 = now_s();
+// Matrix::from_kv_database::<ARITY> with the row fill on the GPU: host = key digests + filter construction + wave plan (once, whatever
+// the number of GPUs), device = row encoding + dependent fill of a COLUMN RANGE of D (the recurrence couples rows, never columns, so
+// every GPU of a cluster builds its own columns from the same plan).  d_out receives columns [c0, c0 + nc) as a K x nc u32 matrix.
+}  // namespace
+
+int DeviceFillHost::prepare(uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off, uint32_t b, uint32_t max_attempts,
+                            const uint64_t *seed_rng) {
+  if (int rc = digest_and_peel(arity, n, key_blob, key_off, b, max_attempts, seed_rng, &digests, &pr); rc != CHPIR_OK) return rc;
   double tt = trace_now();
-  // D is allocated and cleared first so the memset runs under the host-side filter construction
-  if (int rc = d_out->alloc(K * N * 4); rc != CHPIR_OK) return rc;
-  CHPIR_CUDA(cudaMemsetAsync(d_out->p, 0, K * N * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  DevBuf d_values, d_valoff;
+  plan_fill_levels(arity, pr, &plan);
+  trace_phase("fill wave plan", tt);
+  pr.params.to_bytes(filter_bytes);
+  return CHPIR_OK;
+}
+
+// Step 1 (before the host-side peeling, so that the memset and the values upload run under it): allocations, D cleared, values on
+// their way through the ctx's bounce buffers.  Holds the ctx's setup mutex until finish() or destruction.
+int DeviceFillRank::begin(chpir_ctx *ctx, uint64_t n, const uint8_t *val_blob, const uint64_t *val_off, uint64_t K, uint32_t nc, DevBuf *d_out) {
+  ctx_ = ctx, n_ = n, K_ = K, nc_ = nc, d_out_ = d_out;
+  lock_ = std::unique_lock<std::mutex>(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  cudaStream_t st = ctx->stream;
+  double tt = trace_now();
+  if (int rc = d_out->alloc(K * nc * 4); rc != CHPIR_OK) return rc;
+  CHPIR_CUDA(cudaMemsetAsync(d_out->p, 0, K * nc * 4, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   const uint64_t val_bytes = val_off[n];
-  if (int rc = d_values.alloc(val_bytes); rc != CHPIR_OK) return rc;
-  if (int rc = d_valoff.alloc((n + 1) * 8); rc != CHPIR_OK) return rc;
-  // scratch of the single-launch row fill (per-key records, wave table: at most one wave per key), allocated up front with the rest
-  DevBuf d_fill_rec, d_fill_levels;
-  if (int rc = d_fill_rec.alloc(n * kFillRecordBytes); rc != CHPIR_OK) return rc;
-  if (int rc = d_fill_levels.alloc((n + 2) * 4); rc != CHPIR_OK) return rc;
+  if (int rc = d_values_.alloc(val_bytes); rc != CHPIR_OK) return rc;
+  if (int rc = d_valoff_.alloc((n + 1) * 8); rc != CHPIR_OK) return rc;
+  // scratch of the row fill (per-key records, wave table: at most one wave per key), allocated up front with the rest
+  if (int rc = d_fill_rec_.alloc(n * kFillRecordBytes); rc != CHPIR_OK) return rc;
+  if (int rc = d_fill_levels_.alloc((n + 2) * 4); rc != CHPIR_OK) return rc;
+  if (int rc = d_members_.alloc(n * 4); rc != CHPIR_OK) return rc;
+  if (int rc = d_order_.alloc(n * 8); rc != CHPIR_OK) return rc;
+  if (int rc = d_found_.alloc(n); rc != CHPIR_OK) return rc;
+  if (int rc = d_koo_.alloc(n * 4); rc != CHPIR_OK) return rc;
+  if (int rc = d_digests_.alloc(n * 32); rc != CHPIR_OK) return rc;
   trace_phase("device allocations", tt);
   // values do not depend on the filter: their upload (pageable memory) also precedes the peeling
-  CHPIR_CUDA(cudaMemcpyAsync(d_valoff.p, val_off, (n + 1) * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_valoff_.p, val_off, (n + 1) * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   // (several helper threads with page-locked bounce buffers: the driver's own staging of a pageable copy is one core, ~3 GB/s here)
-  StagedUpload values_up;
-  if (!values_up.start(&ctx->stage, ctx->device, d_values.p, val_blob, val_bytes, st)) {
+  if (!values_up_.start(&ctx->stage, ctx->device, d_values_.p, val_blob, val_bytes, st)) {
     set_last_cuda_error(cudaGetLastError(), "values upload");
     return CHPIR_ERR_CUDA_TRANSFER_FAILED;
   }
   trace_phase("values upload (enqueue)", tt);
-  std::vector<uint8_t> digests;
-  PeelResult pr;
-  if (int rc = digest_and_peel(arity, n, key_blob, key_off, b, max_attempts, seed_rng, &digests, &pr); rc != CHPIR_OK) return rc;
-  tt = trace_now();
-  FillPlan plan;
-  plan_fill_levels(arity, pr, &plan);
-  trace_phase("fill wave plan", tt);
-  const uint32_t waves = uint32_t(plan.level_start.size() - 1);
-  DevBuf d_members, d_order, d_found, d_koo, d_digests;
-  if (int rc = d_members.alloc(n * 4); rc != CHPIR_OK) return rc;
-  if (int rc = d_order.alloc(n * 8); rc != CHPIR_OK) return rc;
-  if (int rc = d_found.alloc(n); rc != CHPIR_OK) return rc;
-  if (int rc = d_koo.alloc(n * 4); rc != CHPIR_OK) return rc;
-  if (int rc = d_digests.alloc(n * 32); rc != CHPIR_OK) return rc;
-  CHPIR_CUDA(cudaMemcpyAsync(d_members.p, plan.members.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  CHPIR_CUDA(cudaMemcpyAsync(d_order.p, pr.order.data(), n * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  CHPIR_CUDA(cudaMemcpyAsync(d_found.p, pr.found.data(), n, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  CHPIR_CUDA(cudaMemcpyAsync(d_koo.p, pr.key_of_order.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
-  CHPIR_CUDA(cudaMemcpyAsync(d_digests.p, digests.data(), n * 32, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  return CHPIR_OK;
+}
+
+// Step 2 (after DeviceFillHost::prepare): the plan goes up, the fill runs; the ctx's stream is synchronised on return.
+int DeviceFillRank::finish(uint32_t arity, const DeviceFillHost &h, uint64_t N, uint32_t c0, uint32_t b, double *device_s) {
+  struct Unlock {
+    std::unique_lock<std::mutex> &l;
+    ~Unlock() {
+      if (l.owns_lock()) l.unlock();
+    }
+  } unlock{lock_};
+  chpir_ctx *ctx = ctx_;
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
+  cudaStream_t st = ctx->stream;
+  const uint64_t n = n_;
+  const uint32_t waves = uint32_t(h.plan.level_start.size() - 1);
+  double tt = trace_now();
+  CHPIR_CUDA(cudaMemcpyAsync(d_members_.p, h.plan.members.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_order_.p, h.pr.order.data(), n * 8, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_found_.p, h.pr.found.data(), n, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_koo_.p, h.pr.key_of_order.data(), n * 4, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
+  CHPIR_CUDA(cudaMemcpyAsync(d_digests_.p, h.digests.data(), n * 32, cudaMemcpyHostToDevice, st), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   trace_phase("plan upload (enqueue)", tt);
-  if (!values_up.finish(st)) {
+  if (!values_up_.finish(st)) {
     set_last_cuda_error(cudaGetLastError(), "values upload");
     return CHPIR_ERR_CUDA_TRANSFER_FAILED;
   }
   trace_phase("values upload (rest)", tt);
-  const double t1 = now_s();
   EventTimer t_fill;
   t_fill.start(st);
-  if (int rc = launch_device_row_fill(arity, d_members.as<uint32_t>(), plan.level_start.data(), waves, d_order.as<uint64_t>(),
-                                      d_found.as<uint8_t>(), d_koo.as<uint32_t>(), d_digests.as<uint8_t>(), d_values.as<uint8_t>(),
-                                      d_valoff.as<uint64_t>(), d_out->as<uint32_t>(), N, b, pr.params.segment_length,
-                                      pr.params.segment_count_length, d_fill_rec.p, d_fill_levels.as<uint32_t>(), st);
+  if (int rc = launch_device_row_fill(arity, d_members_.as<uint32_t>(), h.plan.level_start.data(), waves, d_order_.as<uint64_t>(),
+                                      d_found_.as<uint8_t>(), d_koo_.as<uint32_t>(), d_digests_.as<uint8_t>(), d_values_.as<uint8_t>(),
+                                      d_valoff_.as<uint64_t>(), d_out_->as<uint32_t>(), N, c0, nc_, b, h.pr.params.segment_length,
+                                      h.pr.params.segment_count_length, d_fill_rec_.p, d_fill_levels_.as<uint32_t>(), st);
       rc != CHPIR_OK)
     return rc;
   t_fill.stop(st);
@@ -388,11 +407,26 @@ int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const 
     set_last_cuda_error(e, "device row fill");
     return CHPIR_ERR_CUDA_KERNEL_EXECUTION_FAILED;
   }
-  trace_phase("device row fill (waves)", tt);
-  pr.params.to_bytes(filter_bytes);
-  if (host_s) *host_s = t1 - t0;
+  trace_phase("device row fill", tt);
   if (device_s) *device_s = t_fill.ms() * 1e-3;
-  (void)waves;
+  return CHPIR_OK;
+}
+
+namespace {
+
+// One GPU, all columns (the caller holds no lock: DeviceFillRank takes the ctx's setup mutex and releases it before returning).
+int encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, const uint8_t *key_blob, const uint64_t *key_off,
+                              const uint8_t *val_blob, const uint64_t *val_off, uint32_t b, uint32_t max_attempts, const uint64_t *seed_rng,
+                              uint64_t K, uint64_t N, DevBuf *d_out, uint8_t filter_bytes[68], double *host_s, double *device_s) {
+  const double t0 = now_s();
+  DeviceFillRank rank;
+  if (int rc = rank.begin(ctx, n, val_blob, val_off, K, uint32_t(N), d_out); rc != CHPIR_OK) return rc;
+  DeviceFillHost h;
+  if (int rc = h.prepare(arity, n, key_blob, key_off, b, max_attempts, seed_rng); rc != CHPIR_OK) return rc;
+  const double t1 = now_s();
+  if (int rc = rank.finish(arity, h, N, 0, b, device_s); rc != CHPIR_OK) return rc;
+  std::memcpy(filter_bytes, h.filter_bytes, 68);
+  if (host_s) *host_s = t1 - t0;
   return CHPIR_OK;
 }
 
@@ -580,13 +614,13 @@ int chpir_encode_kv_database_device(chpir_ctx *ctx, uint32_t arity, uint64_t n, 
   uint64_t max_vlen = 0, K = 0, N = 0;
   for (uint64_t i = 0; i < n; i++) max_vlen = std::max<uint64_t>(max_vlen, value_offsets[i + 1] - value_offsets[i]);
   if (int rc = db_matrix_shape(arity, n, max_vlen, b, &K, &N); rc != CHPIR_OK) return rc;
-  std::lock_guard<std::mutex> g(ctx->mu);
-  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
   DevBuf d;
   if (int rc = encode_kv_database_device(ctx, arity, n, key_blob, key_offsets, value_blob, value_offsets, b, max_attempt_count, filter_seed_rng, K, N,
                                          &d, filter_params_out, nullptr, nullptr);
       rc != CHPIR_OK)
     return rc;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
   CHPIR_CUDA(cudaMemcpy(d_out, d.p, K * N * 4, cudaMemcpyDeviceToHost), CHPIR_ERR_CUDA_TRANSFER_FAILED);
   return CHPIR_OK;
   CHPIR_GUARD_END
@@ -715,8 +749,6 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
     chpir_setup_opts o = *opts;
     uint32_t c0, nc;
     if (int rc = resolve_slice(o, uint32_t(N), &c0, &nc); rc != CHPIR_OK) return rc;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
     if (pipe_p) set_encode_threads(std::max(1u, std::thread::hardware_concurrency()) > 3 ? std::thread::hardware_concurrency() - 2 : 1);
     DevBuf d;
     double enc_host_s = 0, enc_dev_s = 0;
@@ -724,6 +756,8 @@ int chpir_server_setup_from_db(chpir_ctx *ctx, uint32_t arity, const uint8_t see
                                        filter_seed_rng, K, N, &d, filter_params_out, &enc_host_s, &enc_dev_s);
     set_encode_threads(0);
     if (rc != CHPIR_OK) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);  // (the fill took and released it itself)
+    CHPIR_CUDA(cudaSetDevice(ctx->device), CHPIR_ERR_CUDA_DEVICE_NOT_FOUND);
     const double t1 = now_s();
     {
       double tt = t0;

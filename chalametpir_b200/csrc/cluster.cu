@@ -33,6 +33,7 @@
 
 #include "common.cuh"
 #include "host_encode.hpp"
+#include "device_fill.cuh"
 #include "host_pipe.cuh"
 #include "server_state.cuh"
 
@@ -935,7 +936,6 @@ int check_opts(const chpir_cluster *cl, const chpir_setup_opts *opts, chpir_setu
   *o = chpir_setup_opts{};
   if (opts) *o = *opts;
   if (o->col_begin != 0 || o->col_count != 0 || o->hint_on_device != 0) return CHPIR_ERR_INVALID_ARGUMENT;
-  if (cl->n > 1 && o->db_encode == CHPIR_DB_ENCODE_DEVICE) return CHPIR_ERR_INVALID_ARGUMENT;
   return CHPIR_OK;
 }
 
@@ -1407,6 +1407,8 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   EarlyNccl nccl(cl, S->n, o);
   std::unique_ptr<uint32_t[]> d_store;  // n > 1: D, encoded once on the host; lives until the row blocks have been cut from it
   SharedChain chain;
+  std::vector<DevBuf> d_dev;              // n > 1, db_encode = device: every rank's columns of D, built in its HBM
+  std::vector<const uint32_t *> d_ptrs;
   if (S->n == 1) {
     // one GPU: the single-GPU call as it is (device row fill, its own early XOF start), hint slice = whole hint
     chpir_setup_opts ro = o;
@@ -1416,6 +1418,42 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
                                             nullptr, filter_params_out, &S->r[0].srv);
         rc != CHPIR_OK)
       return rc;
+  } else if (o.db_encode == CHPIR_DB_ENCODE_DEVICE) {
+    // Row encoding + dependent fill on the GPUs: the host does the key digests, the peeling and the wave plan ONCE; every rank
+    // receives the raw values over its own PCIe link (beside the peeling) and builds ITS columns of D in its HBM -- the recurrence
+    // couples rows, never columns.  The host never holds D, and the row blocks are cut from the slices over NVLink afterwards.
+    if (int rc = chain.start(S.get(), o, seed, K, true); rc != CHPIR_OK) return rc;
+    const double t_enc0 = now_s();
+    std::vector<std::unique_ptr<DeviceFillRank>> fill(S->n);
+    d_dev.resize(S->n);
+    int rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
+      fill[d].reset(new DeviceFillRank());
+      return fill[d]->begin(S->r[d].ctx, n, value_blob, value_offsets, K, S->r[d].pl.nc, &d_dev[d]);
+    });
+    if (rc != CHPIR_OK) return rc;
+    DeviceFillHost fh;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (chain.leader) set_encode_threads(hw > 3 ? hw - 2 : 1);  // the producer core stays free for the chain
+    rc = fh.prepare(arity, n, key_blob, key_offsets, b, CHPIR_SERVER_SETUP_MAX_ATTEMPT_COUNT, filter_seed_rng);
+    set_encode_threads(0);
+    if (rc != CHPIR_OK) return rc;
+    std::memcpy(filter_params_out, fh.filter_bytes, CHPIR_FILTER_PARAM_BYTE_LEN);
+    std::vector<double> fill_s(S->n, 0.0);
+    rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int { return fill[d]->finish(arity, fh, N, S->r[d].pl.c0, b, &fill_s[d]); });
+    fill.clear();  // values, records: gone before the hint phase allocates
+    if (rc != CHPIR_OK) return rc;
+    const double t_enc1 = now_s();
+    rc = for_each_rank_parallel(S->n, [&](uint32_t d) -> int {
+      const chpir_setup_opts ro = rank_opts(o, S->r[d].pl, true);
+      return server_setup_from_device_matrix(S->r[d].ctx, seed, d_dev[d].as<uint32_t>(), K, S->r[d].pl.nc, b, &ro, nullptr, 0, nullptr, &S->r[d].srv,
+                                             chain.of(d));
+    });
+    if (rc != CHPIR_OK) return rc;
+    for (uint32_t d = 0; d < S->n; d++) {
+      S->r[d].srv->timing.host_encode_s = t_enc1 - t_enc0;
+      S->r[d].srv->timing.device_encode_s = fill_s[d];
+    }
+    for (uint32_t d = 0; d < S->n; d++) d_ptrs.push_back(d_dev[d].as<uint32_t>());
   } else {
     // Every rank needs all of A = generate_from_seed(lwe, K, seed), and the XOF chain is serial: it starts NOW (one producer core,
     // rings as deep as A on every GPU, panels forwarded over NVLink) and squeezes beside the host filter/encode phase below, exactly
@@ -1442,8 +1480,10 @@ int chpir_cluster_server_setup_from_db(chpir_cluster *cl, uint32_t arity, const 
   nccl.wait();
   DSource dsrc;
   dsrc.host = d_store.get();
+  if (!d_ptrs.empty()) dsrc.dev_slices = d_ptrs.data();
   if (int rc = complete_setup(S.get(), o, seed, dsrc, hint_out, hint_cap, hint_len); rc != CHPIR_OK) return rc;
   d_store.reset();
+  d_dev.clear();
   S->setup_total_s = now_s() - t0;
   *out = S.release();
   return CHPIR_OK;

@@ -80,11 +80,11 @@ int expand_begin(const uint8_t seed[32], uint8_t *state_scratch_dev, cudaStream_
 int launch_expand_planes(uint8_t *ring_dev, uint64_t rows, uint64_t cols, uint64_t kp, uint8_t *state_scratch_dev, uint64_t block_begin,
                          uint64_t block_count, cudaStream_t s);
 
-// Row fill of Matrix::from_kv_database on the GPU (encode_dev.cu): D (K x N u32, zeroed) is filled wave by wave; every pointer
-// except level_start_host is a device pointer.
+// Row fill of Matrix::from_kv_database on the GPU (encode_dev.cu): columns [c0, c0 + nc) of the K x N matrix, stored K x nc u32 (zeroed),
+// are filled in the dependency order of the peeling; every pointer except level_start_host is a device pointer.
 int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32_t *level_start_host, uint32_t waves, const uint64_t *order,
                            const uint8_t *found, const uint32_t *key_of_order, const uint8_t *digests, const uint8_t *values,
-                           const uint64_t *val_off, uint32_t *D, uint64_t N, uint32_t b, uint32_t segment_length,
+                           const uint64_t *val_off, uint32_t *D, uint64_t N, uint32_t c0, uint32_t nc, uint32_t b, uint32_t segment_length,
                            uint32_t segment_count_length, void *scratch_records, uint32_t *scratch_levels, cudaStream_t s);
 constexpr size_t kFillRecordBytes = 48;  // scratch_records: this many bytes per key
 

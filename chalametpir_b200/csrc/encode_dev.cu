@@ -43,8 +43,9 @@ struct FillArgs {
   const uint8_t *digests;      // 32 bytes per key
   const uint8_t *values;       // value blob
   const uint64_t *val_off;     // n + 1 offsets
-  uint32_t *D;                 // K x N
+  uint32_t *D;                 // K x nc: columns [c0, c0 + nc) of the K x N matrix, row pitch nc
   uint64_t N;
+  uint32_t c0, nc;
   uint32_t b;
   uint32_t segment_length, segment_count_length;
 };
@@ -89,19 +90,20 @@ __global__ void __launch_bounds__(kFillThreads) fill_wave_kernel(FillArgs a, uin
   }
   uint32_t h[4];
   slots_dev<ARITY>(hash, a.segment_length, a.segment_count_length, h);
-  uint32_t *own = a.D + uint64_t(h[which]) * a.N;
-  const uint32_t *o1 = a.D + uint64_t(h[(which + 1) % ARITY]) * a.N;
-  const uint32_t *o2 = a.D + uint64_t(h[(which + 2) % ARITY]) * a.N;
-  const uint32_t *o3 = a.D + uint64_t(h[(which + 3) % ARITY]) * a.N;  // ARITY == 4 only
+  uint32_t *own = a.D + uint64_t(h[which]) * a.nc;
+  const uint32_t *o1 = a.D + uint64_t(h[(which + 1) % ARITY]) * a.nc;
+  const uint32_t *o2 = a.D + uint64_t(h[(which + 2) % ARITY]) * a.nc;
+  const uint32_t *o3 = a.D + uint64_t(h[(which + 3) % ARITY]) * a.nc;  // ARITY == 4 only
   const uint32_t mask = (1u << a.b) - 1;
   __syncthreads();
-  for (uint64_t e = threadIdx.x; e < a.N; e += kFillThreads) {
+  for (uint32_t j = threadIdx.x; j < a.nc; j += kFillThreads) {
+    const uint64_t e = uint64_t(a.c0) + j;  // column of the whole matrix
     const uint32_t bit = uint32_t(e) * a.b, byte = bit >> 3, sh = bit & 7;
     const uint32_t w = uint32_t(sbytes[byte]) | uint32_t(sbytes[byte + 1]) << 8 | uint32_t(sbytes[byte + 2]) << 16;
     uint32_t v = (w >> sh) & mask;
-    v -= __ldcg(o1 + e) + __ldcg(o2 + e) + static_cast<uint32_t>(fmix64_dev(hash + e));
-    if (ARITY == 4) v -= __ldcg(o3 + e);
-    own[e] = v & mask;
+    v -= __ldcg(o1 + j) + __ldcg(o2 + j) + static_cast<uint32_t>(fmix64_dev(hash + e));
+    if (ARITY == 4) v -= __ldcg(o3 + j);
+    own[j] = v & mask;
   }
 }
 
@@ -137,8 +139,8 @@ __global__ void __launch_bounds__(256) fill_prep_kernel(FillArgs a, uint64_t cou
 
 // dynamic shared memory: a key's byte string (as in fill_wave_kernel); CTAs stride over the keys
 __global__ void __launch_bounds__(kFillThreads) encode_rows_kernel(const FillRec *__restrict__ rec, uint64_t count, const uint8_t *__restrict__ digests,
-                                                                   const uint8_t *__restrict__ values, uint32_t *__restrict__ D, uint64_t N, uint32_t b,
-                                                                   uint32_t stream_bytes) {
+                                                                   const uint8_t *__restrict__ values, uint32_t *__restrict__ D, uint32_t c0, uint32_t nc,
+                                                                   uint32_t b, uint32_t stream_bytes) {
   extern __shared__ __align__(4) uint8_t sbytes[];
   const uint32_t mask = (1u << b) - 1;
   for (uint64_t j = blockIdx.x; j < count; j += gridDim.x) {
@@ -154,11 +156,12 @@ __global__ void __launch_bounds__(kFillThreads) encode_rows_kernel(const FillRec
       sbytes[t] = v;
     }
     __syncthreads();
-    uint32_t *own = D + uint64_t(r.own) * N;
-    for (uint64_t e = threadIdx.x; e < N; e += kFillThreads) {
+    uint32_t *own = D + uint64_t(r.own) * nc;
+    for (uint32_t j = threadIdx.x; j < nc; j += kFillThreads) {
+      const uint64_t e = uint64_t(c0) + j;  // column of the whole matrix
       const uint32_t bit = uint32_t(e) * b, byte = bit >> 3, sh = bit & 7;
       const uint32_t w = uint32_t(sbytes[byte]) | uint32_t(sbytes[byte + 1]) << 8 | uint32_t(sbytes[byte + 2]) << 16;
-      own[e] = ((w >> sh) - static_cast<uint32_t>(fmix64_dev(r.hash + e))) & mask;
+      own[j] = ((w >> sh) - static_cast<uint32_t>(fmix64_dev(r.hash + e))) & mask;
     }
     __syncthreads();
   }
@@ -179,7 +182,7 @@ static_assert(kFillChunk % 32 == 0, "the ring is refilled in whole warp loads");
 // refills 128 records at a time, two refills ahead of the walk (the loads are in flight for a whole step before they are stored).
 template <int ARITY>
 __global__ void __launch_bounds__(32) solve_columns_kernel(const uint4 *__restrict__ rows, const uint32_t *__restrict__ level_start, uint32_t waves,
-                                                           uint32_t *D, uint64_t N, uint32_t b) {
+                                                           uint32_t *D, uint64_t N /* columns of D as stored = its row pitch */, uint32_t b) {
   __shared__ uint4 ring[kFillRing];
   const uint32_t lane = threadIdx.x, group = lane / kFillCols;
   const uint64_t e = uint64_t(blockIdx.x) * kFillCols + (lane % kFillCols);
@@ -253,13 +256,14 @@ __global__ void __launch_bounds__(32) solve_columns_kernel(const uint4 *__restri
 
 }  // namespace
 
-// All pointers except level_start_host are device pointers; D must be zeroed.  scratch_records: kFillRecordBytes per key, scratch_levels:
+// All pointers except level_start_host are device pointers; D (K x nc u32: columns [c0, c0 + nc) of the K x N matrix) must be zeroed.  scratch_records: kFillRecordBytes per key, scratch_levels:
 // waves + 1 words (both device memory; NULL selects the wave-per-launch schedule).  level_start_host must stay valid until the work
 // enqueued on s has been synchronised (it is copied with cudaMemcpyAsync from pageable memory, i.e. during the call).
 int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32_t *level_start_host, uint32_t waves, const uint64_t *order,
                            const uint8_t *found, const uint32_t *key_of_order, const uint8_t *digests, const uint8_t *values,
-                           const uint64_t *val_off, uint32_t *D, uint64_t N, uint32_t b, uint32_t segment_length,
+                           const uint64_t *val_off, uint32_t *D, uint64_t N, uint32_t c0, uint32_t nc, uint32_t b, uint32_t segment_length,
                            uint32_t segment_count_length, void *scratch_records, uint32_t *scratch_levels, cudaStream_t s) {
+  if (nc == 0 || uint64_t(c0) + nc > N) return CHPIR_ERR_INVALID_ARGUMENT;
   FillArgs a{};
   a.order = order;
   a.found = found;
@@ -269,6 +273,7 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
   a.val_off = val_off;
   a.D = D;
   a.N = N;
+  a.c0 = c0, a.nc = nc;
   a.b = b;
   a.segment_length = segment_length;
   a.segment_count_length = segment_count_length;
@@ -291,17 +296,17 @@ int launch_device_row_fill(uint32_t arity, const uint32_t *members, const uint32
     if (stream_bytes > 48 * 1024 &&
         cudaFuncSetAttribute(encode_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream_bytes)) != cudaSuccess)
       return CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
-    const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((N + kFillCols - 1) / kFillCols);
+    const unsigned pg = unsigned((count + 255) / 256), fg = unsigned((nc + kFillCols - 1) / kFillCols);
     const unsigned eg = unsigned(count < 148ull * 32 ? count : 148ull * 32);
     if (arity == 3)
       fill_prep_kernel<3><<<pg, 256, 0, s>>>(a, count, rec, rows);
     else
       fill_prep_kernel<4><<<pg, 256, 0, s>>>(a, count, rec, rows);
-    encode_rows_kernel<<<eg, kFillThreads, stream_bytes, s>>>(rec, count, digests, values, D, N, b, stream_bytes);
+    encode_rows_kernel<<<eg, kFillThreads, stream_bytes, s>>>(rec, count, digests, values, D, c0, nc, b, stream_bytes);
     if (arity == 3)
-      solve_columns_kernel<3><<<fg, 32, 0, s>>>(rows, scratch_levels, waves, D, N, b);
+      solve_columns_kernel<3><<<fg, 32, 0, s>>>(rows, scratch_levels, waves, D, nc, b);
     else
-      solve_columns_kernel<4><<<fg, 32, 0, s>>>(rows, scratch_levels, waves, D, N, b);
+      solve_columns_kernel<4><<<fg, 32, 0, s>>>(rows, scratch_levels, waves, D, nc, b);
     return cudaGetLastError() == cudaSuccess ? CHPIR_OK : CHPIR_ERR_CUDA_KERNEL_LAUNCH_FAILED;
   }
   if (stream_bytes > 48 * 1024) {

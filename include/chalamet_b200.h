@@ -160,8 +160,8 @@ typedef struct chpir_setup_opts {
 /* chpir_setup_opts.db_encode.  Key digests and filter construction (peeling) always run on the host.
  *   HOST:   encode_kv_as_row + the dependent row fill of Matrix::from_kv_database run on the host (csrc/host_encode.cpp) and the
  *           K x N u32 matrix D (4.4 GB at 2^20 entries) is uploaded;
- *   DEVICE: the raw values (1.1 GB) are uploaded and D is built in HBM by csrc/encode_dev.cu, wave by wave in the dependency
- *           order the peeling implies -- the same D, byte for byte. */
+ *   DEVICE: the raw values (1.1 GB) are uploaded and D is built in HBM by csrc/encode_dev.cu in the dependency order the peeling
+ *           implies -- the same D, byte for byte; on a cluster every GPU builds its own columns. */
 #define CHPIR_DB_ENCODE_HOST 0u
 #define CHPIR_DB_ENCODE_DEVICE 1u
 
@@ -289,7 +289,7 @@ CHPIR_API int chpir_cluster_plan(uint32_t n_ranks, uint32_t rank, uint64_t rows_
 
 /* Server::setup on the cluster.  opts as for the single-GPU calls (col_begin / col_count / hint_on_device must be 0: the cluster
  * slices; respond_coalesce is implied for n_gpus > 1 and, for n_gpus = 1, selects the cluster's batching pipeline instead of one
- * slot per call; db_encode = DEVICE needs n_gpus = 1).  hint_out receives the COMPLETE
+ * slot per call; with db_encode = DEVICE every GPU builds its own columns of D in its HBM from one host-side peeling).  hint_out receives the COMPLETE
  * wire-format hint (8 + 4 * lwe_rows * N bytes), byte-identical to a single-GPU setup: each rank computes its column slice and
  * the slices are gathered on GPU 0 (NCCL by default, see CHPIR_CLUSTER_GATHER below) and downloaded once. */
 CHPIR_API int chpir_cluster_server_setup_from_db(chpir_cluster *cluster, uint32_t arity, const uint8_t seed[CHPIR_SEED_BYTE_LEN],

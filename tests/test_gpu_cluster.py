@@ -181,15 +181,17 @@ def test_cluster_device_resident_paths(n, b, cut):
     cl.close()
 
 
-@pytest.mark.parametrize("n", [1, 2, 8])
+@pytest.mark.parametrize("db_encode", ["host", "device"])
+@pytest.mark.parametrize("n", [1, 2, 3, 8])
 @pytest.mark.parametrize("arity", [3, 4])
-def test_cluster_setup_from_db_pir_round(n, arity):
+def test_cluster_setup_from_db_pir_round(n, arity, db_encode):
     """Server::setup(seed, db) on the cluster -> same hint and filter bytes as the single-GPU call and as the oracle; the oracle's client
-    recovers every queried value from the cluster's responses (integrations/src/test_pir.rs:12-142)."""
+    recovers every queried value from the cluster's responses (integrations/src/test_pir.rs:12-142).  db_encode = device: every GPU
+    builds its own columns of D in its HBM from one host-side peeling (csrc/device_fill.cuh), the row blocks are cut over NVLink."""
     need(n)
     db = make_db(3000, seed=40 + arity)
     cl = cp.Cluster(n_gpus=n)
-    srv, hint, fbytes = cp.ClusterServer.setup(cl, SEED, db, arity, filter_seed_rng=21, lwe_rows=200)
+    srv, hint, fbytes = cp.ClusterServer.setup(cl, SEED, db, arity, filter_seed_rng=21, lwe_rows=200, db_encode=db_encode)
     s1, h1, f1 = cp.Server.setup(SEED, db, arity, filter_seed_rng=21, lwe_rows=200)
     assert hint == h1 and fbytes == f1
     b = O.find_mat_elem_bit_len(len(db))
