@@ -1022,6 +1022,9 @@ static int respond_coalesced(chpir_server *srv, const uint8_t *query, uint8_t *r
     row = B->count++;
   }
   const bool leader = row == 0;
+  // Between joining the batch (count++) and reporting the upload (issued++) a member runs this one C call: nothing here can throw or
+  // return early, so a batch cannot be left waiting for a member that never reports; a failed enqueue is reported through B->rc and
+  // fails the whole batch.  (A thread killed from outside between the two points would wedge any lock-based protocol the same way.)
   const bool sent = cudaMemcpyAsync(B->d_q + size_t(row) * srv->K, query + 8, srv->K * 4, cudaMemcpyHostToDevice, B->copy) == cudaSuccess;
   {
     std::lock_guard<std::mutex> lk(co.mu);
