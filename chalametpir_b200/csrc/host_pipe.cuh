@@ -109,9 +109,9 @@ class HostAPipe {
   }
 
   // A follower of another pipe's chain (n GPUs of one process need the same A, and the chain is serial): no producer, no host
-  // buffers -- the leader's uploader forwards every finished panel from its own HBM over NVLink (copy engines) into this pipe's
-  // ring and signals it exactly as an uploader of its own would.  Must be set up before the leader's start() is given the pointer,
-  // and outlive the leader's threads (shut the leader down first).
+  // buffers -- the leader's forwarder thread sends every finished panel from its own HBM over NVLink (copy engines) into this pipe's
+  // ring and signals it exactly as an uploader of its own would.  The leader touches a mirror's ring only after mirrors_ready();
+  // a mirror must outlive the leader's threads (shut the leader down first).
   int start_mirror(int device, uint32_t m, uint64_t K, uint32_t depth) {
     device_ = device, m_ = m, K_ = K, mirror_ = true;
     row_bytes_ = K * 4;
@@ -271,7 +271,7 @@ class HostAPipe {
     fail_mirrors(rc);
   }
 
-  // Leader's uploader: panel p is complete in this pipe's ring (ready_[p] recorded on up_) -- send it on to every mirror.
+  // Leader's forwarder: panel p is complete in this pipe's ring (ready_[p] recorded on up_) -- send it on to every mirror.
   bool forward_panel(uint32_t p) {
     const uint32_t rows = std::min(m_, (p + 1) * 128) - p * 128;
     const uint8_t *src = panels_dev_.as<uint8_t>() + uint64_t(p % depth_) * panel_bytes_;
